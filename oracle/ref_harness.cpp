@@ -1,0 +1,269 @@
+// TEST INFRASTRUCTURE ONLY — never linked into, imported by or executed from the product path.
+//
+// Stage-by-stage driver for the UNMODIFIED reference encoder (KLab/YAIK), compiled by
+// oracle/Makefile from the sources where they lie under /root/reference into
+// oracle/_ref/ (git-ignored).  It calls the four hot-path members of `EncoderContext`
+// directly (they are `protected`, EncoderContext.h:299-339, hence the `Probe` subclass)
+// and dumps every observable result as named records that tests/ and bench.py read.
+//
+//   MipPrefilter            encoder/EncoderContext.cpp:1257
+//   FittingQuadSmooth ×7    encoder/EncoderContext.cpp:3710   (order: EC.cpp:9057-9093)
+//   DynamicTileCompressor   encoder/EncoderContext.cpp:8398   (R2, live range stage)
+//   DynamicTileEncode       encoder/EncoderContext.cpp:4365   (R1, 3/4-bit range stage)
+//
+// rgbStream (the pre-entropy corner colour stream of a gradient pass) is captured by
+// interposing PaletteCompressor (EC.cpp:3259): the reference is built as a -fPIC shared
+// library, this executable exports its own definition (-rdynamic) and forwards to the
+// real one through dlsym(RTLD_NEXT).  PaletteDecompressor cannot be used for this
+// (stale code-book bug).
+//
+// usage: yaik_ref <in.ykin> <out.ykout> [alpha] [grad] [r2] [r1] [r1_3bit] [reps=N]
+//   in : "YKIN" int32 w,h,nplanes, then nplanes*h*w bytes (u8 samples, plane-major)
+//   out: records { char name[32]; char dtype; u64 count; payload }, dtype in {i,B,H,d}
+
+#include "EncoderContext.h"
+#include "../external/zstd/zstd.h"
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <unistd.h>
+#include <vector>
+
+extern u8* streamType;   // EC.cpp:8217
+extern u8* pType;        // EC.cpp:8218
+void DynamicTileEncoderTable();   // EC.cpp:702
+
+// ---------------------------------------------------------------- rgbStream capture
+static std::vector<std::vector<u8>> g_rgbCaptured;
+static double g_paletteSeconds = 0.0;
+
+bool PaletteCompressor(u8* input, int size, u8* output, u32* maxSize) {
+    typedef bool (*fn_t)(u8*, int, u8*, u32*);
+    static fn_t real = (fn_t)dlsym(RTLD_NEXT, "_Z17PaletteCompressorPhiS_Pj");
+    if (!real) { fprintf(stderr, "yaik_ref: cannot resolve the real PaletteCompressor\n"); abort(); }
+    g_rgbCaptured.emplace_back(input, input + size);
+    auto t0 = std::chrono::steady_clock::now();
+    bool r = real(input, size, output, maxSize);
+    g_paletteSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return r;
+}
+
+// ---------------------------------------------------------------- output records
+static FILE* g_out = NULL;
+static void rec(const char* name, char dtype, const void* data, uint64_t count) {
+    char nm[32]; memset(nm, 0, sizeof nm); strncpy(nm, name, 31);
+    size_t esz = dtype == 'i' ? 4 : dtype == 'H' ? 2 : dtype == 'd' ? 8 : 1;
+    fwrite(nm, 1, 32, g_out); fwrite(&dtype, 1, 1, g_out); fwrite(&count, 8, 1, g_out);
+    if (count) fwrite(data, esz, count, g_out);
+}
+static void recPlane(const char* name, Plane* p) {
+    if (p) rec(name, 'i', p->GetPixels(), (uint64_t)p->GetWidth() * p->GetHeight());
+}
+static void recInts(const char* name, std::initializer_list<int> v) {
+    std::vector<int> t(v); rec(name, 'i', t.data(), t.size());
+}
+static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static std::vector<u8> unzstd(const u8* src, size_t n, size_t cap) {
+    std::vector<u8> out(cap ? cap : 1);
+    size_t r = ZSTD_decompress(out.data(), out.size(), src, n);
+    if (ZSTD_isError(r)) { fprintf(stderr, "yaik_ref: zstd: %s\n", ZSTD_getErrorName(r)); abort(); }
+    out.resize(r);
+    return out;
+}
+
+struct Probe : EncoderContext {
+    char*  memBuf = NULL; size_t memLen = 0;
+    void openOut()  { outFile = open_memstream(&memBuf, &memLen); fileOutSize = 0; }
+    size_t tell()   { fflush(outFile); return memLen; }
+    Image* img() { return original; }
+
+    void runAlpha(double* secs) {
+        size_t p0 = tell();
+        double t0 = now();
+        MipPrefilter(true);
+        *secs += now() - t0;
+        size_t p1 = tell();
+        recPlane("alpha.mask", mipmapMask);
+        recInts("alpha.bound", { boundX0, boundY0, boundX1, boundY1 });
+        recInts("alpha.remaining", { remainingPixels, mipMapTileSize });
+        if (p1 > p0) {   // 'MIPM' chunk: HeaderBase(8) MipmapHeader(16) bitmap pad
+            const u8* c = (const u8*)memBuf + p0;
+            MipmapHeader mh; memcpy(&mh, c + sizeof(HeaderBase), sizeof mh);
+            int nbytes = (mh.bbox.w * mh.bbox.h + 7) / 8;
+            recInts("alpha.chunk_bbox", { mh.bbox.x, mh.bbox.y, mh.bbox.w, mh.bbox.h, mh.version, mh.mipmapLevel });
+            rec("alpha.bitmap", 'B', c + sizeof(HeaderBase) + sizeof(MipmapHeader), nbytes);
+        } else {
+            recInts("alpha.chunk_bbox", {});
+            rec("alpha.bitmap", 'B', NULL, 0);
+        }
+    }
+
+    void runGradient(Image* output, double* secs, bool dumpPerPass) {
+        static const int order[7][2] = { {4,4},{4,3},{3,4},{3,3},{3,2},{2,3},{2,2} };   // EC.cpp:9057-9093
+        for (int k = 0; k < 7; k++) {
+            int sx = order[k][0], sy = order[k][1];
+            size_t p0 = tell(); size_t cap0 = g_rgbCaptured.size();
+            double t0 = now();
+            int done = FittingQuadSmooth(3, original->GetPlane(0), original->GetPlane(1), original->GetPlane(2), output, false, sx, sy);
+            *secs += now() - t0;
+            size_t p1 = tell();
+            char nm[32];
+            u32 bw, bh, bits; HeaderGradientTile::getSwizzleSize(sx, sy, bw, bh, bits);
+            int W = original->GetWidth(), H = original->GetHeight();
+            size_t bitmapBytes = (size_t)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * bits / 8;
+            std::vector<u8> bitmap(bitmapBytes, 0);
+            int bbox[4] = { 0, 0, 0, 0 }; int wrote = 0;
+            if (p1 > p0) {   // 'GTIL' chunk
+                const u8* c = (const u8*)memBuf + p0;
+                HeaderGradientTile hg; memcpy(&hg, c + sizeof(HeaderBase), sizeof hg);
+                bitmap = unzstd(c + sizeof(HeaderBase) + sizeof hg, hg.streamBitmapSize, bitmapBytes);
+                bbox[0] = hg.bbox.x; bbox[1] = hg.bbox.y; bbox[2] = hg.bbox.w; bbox[3] = hg.bbox.h;
+                wrote = 1;
+                snprintf(nm, sizeof nm, "grad%d.hdr", k);
+                recInts(nm, { (int)hg.streamRGBSizeUncompressed, hg.colorCompression, hg.format, hg.plane });
+            }
+            snprintf(nm, sizeof nm, "grad%d.tiledone", k); recInts(nm, { done, wrote });
+            snprintf(nm, sizeof nm, "grad%d.bbox", k);     rec(nm, 'i', bbox, 4);
+            snprintf(nm, sizeof nm, "grad%d.bitmap", k);   rec(nm, 'B', bitmap.data(), bitmap.size());
+            snprintf(nm, sizeof nm, "grad%d.rgb", k);
+            if (g_rgbCaptured.size() > cap0) rec(nm, 'B', g_rgbCaptured.back().data(), g_rgbCaptured.back().size());
+            else rec(nm, 'B', NULL, 0);
+            if (dumpPerPass) { snprintf(nm, sizeof nm, "grad%d.smoothMap", k); recPlane(nm, smoothMap); }
+        }
+        recPlane("state.smoothMap", smoothMap);
+        recPlane("state.mipmapMask", mipmapMask);
+        for (int c = 0; c < 3; c++) {
+            char nm[32];
+            snprintf(nm, sizeof nm, "state.mapSmoothTile%d", c); recPlane(nm, mapSmoothTile->GetPlane(c));
+            snprintf(nm, sizeof nm, "state.mappedRGB%d", c);     recPlane(nm, mappedRGB->GetPlane(c));
+            snprintf(nm, sizeof nm, "state.recon%d", c);         recPlane(nm, output->GetPlane(c));
+        }
+    }
+
+    void ensureGradState(Image* output) {   // R2/R1 without a preceding gradient stage
+        if (!smoothMap) {
+            CheckMipmapMask();
+            int W = original->GetWidth(), H = original->GetHeight();
+            smoothMap = new Plane(W, H); smoothMap->Clear();
+            mapSmoothTile = Image::CreateImage(W, H, 3, true);
+            mappedRGB = Image::CreateImage(W + 1, H + 1, 3, true);
+            (void)output;
+        }
+    }
+
+    void runR2(Image* output, double* secs) {
+        int W = original->GetWidth(), H = original->GetHeight();
+        std::vector<u8> stream((size_t)W * H * 3 + 64);
+        // EC.cpp:8217: the 100000-byte global overflows beyond 33 333 tile records
+        size_t typeCap = (size_t)(W / 8 + 1) * (H / 8 + 1) * 9 + 64;
+        streamType = new u8[typeCap]; pType = streamType;
+        u8* p = stream.data();
+        Image* debug = Image::CreateImage(W, H, 3, true);
+        for (int c = 0; c < 3; c++) {
+            u8* p0 = p; u8* t0p = pType;
+            double t0 = now();
+            p = DynamicTileCompressor(p, original->GetPlane(c), mapSmoothTile->GetPlane(c), debug->GetPlane(c));   // EC.cpp:9451-9460
+            *secs += now() - t0;
+            char nm[32];
+            snprintf(nm, sizeof nm, "r2.idx%d", c);   rec(nm, 'B', p0, p - p0);
+            snprintf(nm, sizeof nm, "r2.type%d", c);  rec(nm, 'B', t0p, pType - t0p);
+            snprintf(nm, sizeof nm, "r2.debug%d", c); recPlane(nm, debug->GetPlane(c));
+        }
+        (void)output;
+    }
+
+    void runR1(bool mode3BitOnly, double* secs) {
+        int W = original->GetWidth(), H = original->GetHeight();
+        DynamicTileEncoderTable();
+        for (int c = 0; c < 3; c++) {
+            Plane* dst = new Plane(W, H);
+            BoundingBox all = dst->GetRect(); dst->Fill(all, -1);
+            size_t p0 = tell();
+            double t0 = now();
+            int ret = DynamicTileEncode(mode3BitOnly, original->GetPlane(c), dst, false, false, false, false);
+            *secs += now() - t0;
+            size_t p1 = tell();
+            const u8* ch = (const u8*)memBuf + p0;
+            if (p1 <= p0) { fprintf(stderr, "yaik_ref: no PLNT chunk\n"); abort(); }
+            PlaneTile pt; memcpy(&pt, ch + sizeof(HeaderBase), sizeof pt);
+            const u8* z0 = ch + sizeof(HeaderBase) + sizeof(PlaneTile);
+            std::vector<u8> defs = unzstd(z0, pt.streamSizeTileMap, (size_t)(W / 8) * (H / 8) * 2 + 16);
+            std::vector<u8> nib  = unzstd(z0 + pt.streamSizeTileMap, pt.streamSizeTileStream, (size_t)(W / 8) * (H / 8) * 32 + 16);
+            char nm[32];
+            snprintf(nm, sizeof nm, "r1.defs%d", c);    rec(nm, 'H', defs.data(), defs.size() / 2);
+            snprintf(nm, sizeof nm, "r1.nibbles%d", c); rec(nm, 'B', nib.data(), nib.size());
+            snprintf(nm, sizeof nm, "r1.hdr%d", c);
+            recInts(nm, { pt.bbox.x, pt.bbox.y, pt.bbox.w, pt.bbox.h, (int)pt.expectedSizeTileStream, pt.version, pt.format, ret });
+            snprintf(nm, sizeof nm, "r1.dst%d", c);     recPlane(nm, dst);
+        }
+    }
+};
+
+int main(int argc, char** argv) {
+    if (argc < 3) { fprintf(stderr, "usage: %s in out [alpha] [grad] [r2] [r1] [r1_3bit] [reps=N] [perpass]\n", argv[0]); return 2; }
+    bool doAlpha = false, doGrad = false, doR2 = false, doR1 = false, r1_3bit = false, perPass = false;
+    int reps = 1;
+    for (int i = 3; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "alpha") doAlpha = true; else if (a == "grad") doGrad = true; else if (a == "r2") doR2 = true;
+        else if (a == "r1") doR1 = true; else if (a == "r1_3bit") { doR1 = true; r1_3bit = true; }
+        else if (a == "perpass") perPass = true;
+        else if (a.rfind("reps=", 0) == 0) reps = atoi(a.c_str() + 5);
+        else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
+    }
+    FILE* fi = fopen(argv[1], "rb");
+    if (!fi) { perror(argv[1]); return 1; }
+    char magic[4]; int hdr[3];
+    if (fread(magic, 1, 4, fi) != 4 || memcmp(magic, "YKIN", 4) || fread(hdr, 4, 3, fi) != 3) { fprintf(stderr, "bad input\n"); return 1; }
+    int W = hdr[0], H = hdr[1], NP = hdr[2];
+    std::vector<u8> px((size_t)W * H * NP);
+    if (fread(px.data(), 1, px.size(), fi) != px.size()) { fprintf(stderr, "short input\n"); return 1; }
+    fclose(fi);
+    // absolute output path before chdir
+    std::string outPath = argv[2];
+    if (outPath[0] != '/') { char cwd[4096]; if (getcwd(cwd, sizeof cwd)) outPath = std::string(cwd) + "/" + outPath; }
+    g_out = fopen(outPath.c_str(), "wb");
+    if (!g_out) { perror(outPath.c_str()); return 1; }
+
+    // the reference printf()s per accepted tile (EC.cpp:4216, 8507) and writes debug PNGs into the cwd
+    char tmpl[] = "/tmp/yaik_ref_XXXXXX";
+    char* dir = mkdtemp(tmpl);
+    if (!dir || chdir(dir) != 0) { perror("mkdtemp/chdir"); return 1; }
+    if (!freopen("/dev/null", "w", stdout)) { perror("freopen"); return 1; }
+
+    double tAlpha = 0, tGrad = 0, tR2 = 0, tR1 = 0;
+    for (int r = 0; r < reps; r++) {
+        bool last = (r == reps - 1);
+        FILE* keep = g_out;
+        if (!last) g_out = fopen("/dev/null", "wb");
+        Probe* ctx = new Probe();
+        Image* img = Image::CreateImage(W, H, NP, false);
+        for (int c = 0; c < NP; c++) {
+            int* d = img->GetPlane(c)->GetPixels(); const u8* s = px.data() + (size_t)c * W * H;
+            for (size_t i = 0; i < (size_t)W * H; i++) d[i] = s[i];
+        }
+        ctx->SetImageToEncode(img);
+        ctx->openOut();
+        Image* output = Image::CreateImage(W, H, 3, true);
+        if (doAlpha && NP == 4) ctx->runAlpha(&tAlpha);
+        if (doGrad) ctx->runGradient(output, &tGrad, perPass);
+        if (doR2 || doR1) ctx->ensureGradState(output);
+        if (doR2) ctx->runR2(output, &tR2);
+        if (doR1) ctx->runR1(r1_3bit, &tR1);
+        if (!last) { fclose(g_out); g_out = keep; }
+        // leak everything like the reference does (README.md:48-50); process exits soon
+    }
+    double times[6] = { tAlpha / reps, tGrad / reps, tR2 / reps, tR1 / reps, g_paletteSeconds / reps, (double)reps };
+    rec("time.seconds", 'd', times, 6);
+    recInts("meta", { W, H, NP });
+    fclose(g_out);
+    std::string rm = std::string("rm -rf '") + dir + "'";
+    if (system(rm.c_str()) != 0) {}
+    return 0;
+}

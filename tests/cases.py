@@ -1,0 +1,79 @@
+"""Seeded parity cases shared by the oracle-vs-reference tests, the golden-vector generator and the GPU
+parity tests.  Each entry returns (planes int32 [C][H][W], stages) — stages name what the reference
+harness can run on that size (SURVEY.md hazards 7 and 11: alpha needs pow2 squares >= 16, R2 needs
+multiples of 8, R1 needs >= 32)."""
+import numpy as np
+
+from yaik_b200.synth import make_image, SEED_BASE, _rand
+
+
+def _noise(w, h, c, seed, lo=0, hi=255):
+    n = w * h * c
+    v = (_rand(seed, 99, np.arange(n, dtype=np.uint64)) >> np.uint64(33)).astype(np.int64) % (hi - lo + 1) + lo
+    return v.reshape(c, h, w).astype(np.int32)
+
+
+def _smooth_noisy(w, h, seed, amp):
+    """Global bilinear ramp + small noise: many tiles sit near the +-3 tolerance, so the 6 variants, the
+    top-left-only eligibility and overlapping 16x8 / 8x16 (8x4 / 4x8) tiles are all exercised."""
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    out = np.empty((3, h, w), np.int64)
+    for c in range(3):
+        k = (_rand(seed, c, np.arange(4, dtype=np.uint64)) >> np.uint64(33)).astype(np.int64) % 256
+        top = k[0] * (w - xx) + k[1] * xx
+        bot = k[2] * (w - xx) + k[3] * xx
+        out[c] = (top * (h - yy) + bot * yy) // (w * h)
+    out += _noise(w, h, 3, seed + 7, 0, 2 * amp) - amp
+    return np.clip(out, 0, 255).astype(np.int32)
+
+
+def _with_alpha(rgb, alpha):
+    c, h, w = rgb.shape
+    out = np.empty((4, h, w), np.int32)
+    out[:3] = rgb[:3]
+    out[3] = alpha
+    return out
+
+
+def _alpha_island(w, h, x0, y0, x1, y1, holes=()):
+    a = np.zeros((h, w), np.int32)
+    a[y0:y1, x0:x1] = 255
+    for (hx0, hy0, hx1, hy1) in holes:
+        a[hy0:hy1, hx0:hx1] = 0
+    return a
+
+
+ALL = ("alpha", "grad", "r2", "r1")
+
+SMALL_CASES = {
+    # synthetic illustration-like content
+    "synth128_rgb": lambda: (make_image(128, 128, 3, SEED_BASE + 11), ("grad", "r2", "r1")),
+    "synth256_rgba": lambda: (make_image(256, 256, 4, SEED_BASE + 12), ALL),
+    "synth256_rgb_3bit": lambda: (make_image(256, 256, 3, SEED_BASE + 13), ("grad", "r1_3bit")),
+    # near-tolerance ramps: overlaps between non-nesting tile shapes, all six variants
+    "ramp64_a2": lambda: (_smooth_noisy(64, 64, 21, 2), ("grad", "r2", "r1")),
+    "ramp128_a3": lambda: (_smooth_noisy(128, 128, 22, 3), ("grad", "r2", "r1")),
+    "ramp128_a4": lambda: (_smooth_noisy(128, 128, 23, 4), ("grad", "r2", "r1")),
+    "ramp_192x136_a3": lambda: (_smooth_noisy(192, 136, 24, 3), ("grad", "r2", "r1")),   # partial swizzle blocks
+    "ramp_72x40_a3": lambda: (_smooth_noisy(72, 40, 25, 3), ("grad", "r2", "r1")),
+    # extremes
+    "flat64": lambda: (np.full((3, 64, 64), 77, np.int32), ("grad", "r2", "r1")),
+    "flat_255": lambda: (np.full((3, 64, 64), 255, np.int32), ("grad", "r2", "r1")),
+    "noise64": lambda: (_noise(64, 64, 3, 31), ("grad", "r2", "r1")),
+    "noise_lowamp96": lambda: (_noise(96, 96, 3, 32, 100, 108), ("grad", "r2", "r1")),
+    "noise_delta1": lambda: (_noise(64, 64, 3, 33, 0, 3), ("grad", "r2", "r1")),      # R2 delta==1 -> index -1 quirk
+    "noise_hi": lambda: (_noise(64, 64, 3, 34, 250, 255), ("grad", "r2", "r1")),      # R2 clamp 254, R1 base clamp 224
+    # mip tail (SURVEY.md hazard 11)
+    "mip32_rgba": lambda: (make_image(32, 32, 4, SEED_BASE + 14), ALL),
+    "mip16_rgba": lambda: (make_image(16, 16, 4, SEED_BASE + 15, holes=0), ("alpha", "grad", "r2")),
+    "mip8_rgb": lambda: (_smooth_noisy(8, 8, 26, 2), ("grad", "r2")),
+    "mip4_rgb": lambda: (_smooth_noisy(4, 4, 27, 1), ("grad",)),
+    # alpha: bbox smaller than the image (MIPM chunk written), holes inside, R1 constraint quirks
+    "alpha_island128": lambda: (_with_alpha(make_image(128, 128, 3, SEED_BASE + 16),
+                                            _alpha_island(128, 128, 16, 32, 100, 90, [(48, 48, 80, 64)])), ALL),
+    "alpha_island256": lambda: (_with_alpha(_smooth_noisy(256, 256, 28, 3),
+                                            _alpha_island(256, 256, 64, 16, 250, 200, [(96, 32, 160, 96), (170, 100, 171, 101)])), ALL),
+    "alpha_full_reset64": lambda: (_with_alpha(_noise(64, 64, 3, 35, 90, 99),
+                                               _alpha_island(64, 64, 0, 0, 64, 64, [(16, 16, 48, 32)])), ALL),
+    "alpha_corner_only": lambda: (_with_alpha(_smooth_noisy(64, 64, 29, 3), _alpha_island(64, 64, 40, 40, 64, 64)), ALL),
+}

@@ -1,0 +1,88 @@
+"""Pins the C oracle (oracle/yaik_oracle.c) against the compiled, UNMODIFIED reference (oracle/_ref,
+built from /root/reference by oracle/Makefile).  Skipped where the reference build is absent (GPU box:
+there the committed golden vectors in tests/golden/ pin the oracle instead, see test_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle_py import Oracle, PASS_ORDER
+from refrun import have_ref, run_ref
+from yaik_b200.synth import make_image, SEED_BASE
+import cases
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+def check_against_ref(planes, stages):
+    ref = run_ref(planes, stages)
+    o = Oracle(planes)
+    c, h, w = planes.shape
+    if "alpha" in stages and c == 4:
+        a = o.alpha()
+        assert a is not None
+        assert a["bound"] == list(ref["alpha.bound"])
+        assert a["remaining"] == int(ref["alpha.remaining"][0])
+        assert np.array_equal(a["bitmap"], ref["alpha.bitmap"])
+        if a["wrote"]:
+            assert a["chunk_bbox"] == list(ref["alpha.chunk_bbox"][:4])
+        else:
+            assert ref["alpha.chunk_bbox"].size == 0
+        if "grad" not in stages:
+            assert np.array_equal(o.state(1), ref["alpha.mask"])
+    if "grad" in stages:
+        for k, (sx, sy) in enumerate(PASS_ORDER):
+            if (1 << sx) > w or (1 << sy) > h:
+                # the reference still runs the pass (no tile fits); nothing is accepted
+                pass
+            g = o.gradient_pass(sx, sy)
+            assert g["tiledone"] == int(ref[f"grad{k}.tiledone"][0]), (k, sx, sy)
+            assert np.array_equal(g["rgb"], ref[f"grad{k}.rgb"]), (k, "rgb")
+            if int(ref[f"grad{k}.tiledone"][1]):     # chunk written: bitmap recoverable from the GTIL chunk
+                assert np.array_equal(g["bitmap"], ref[f"grad{k}.bitmap"]), (k, "bitmap")
+                mnx, mny, mxx, mxy = g["bbox"]
+                assert [mnx, mny, mxx - mnx, mxy - mnx] == list(ref[f"grad{k}.bbox"])      # EC.cpp:4258 (maxY - minX)
+            else:
+                assert g["rgb"].size == 0 or not (g["bbox"][2] > g["bbox"][0] and g["bbox"][3] > g["bbox"][1])
+        assert np.array_equal(o.state(0), ref["state.smoothMap"])
+        assert np.array_equal(o.state(1), ref["state.mipmapMask"])
+        for n in range(3):
+            assert np.array_equal(o.state(2 + n), ref[f"state.mapSmoothTile{n}"])
+            assert np.array_equal(o.state(5 + n), ref[f"state.mappedRGB{n}"])
+            assert np.array_equal(o.state(8 + n), ref[f"state.recon{n}"])
+    if "r2" in stages:
+        for n in range(3):
+            r = o.range1d(n, want_debug=True)
+            assert np.array_equal(r["idx"], ref[f"r2.idx{n}"]), n
+            assert np.array_equal(r["type"], ref[f"r2.type{n}"]), n
+            assert np.array_equal(r["debug"].ravel(), ref[f"r2.debug{n}"]), n
+    if "r1" in stages or "r1_3bit" in stages:
+        for n in range(3):
+            r = o.range_dyn(n, mode3="r1_3bit" in stages, want_dst=True)
+            assert np.array_equal(r["defs"], ref[f"r1.defs{n}"]), n
+            assert np.array_equal(r["nibbles"], ref[f"r1.nibbles{n}"]), n
+            assert r["constraint"] == list(ref[f"r1.hdr{n}"][:4])
+            assert np.array_equal(r["dst"].ravel(), ref[f"r1.dst{n}"]), n
+    o.close()
+
+
+@pytest.mark.parametrize("name", list(cases.SMALL_CASES))
+def test_oracle_matches_reference(name):
+    planes, stages = cases.SMALL_CASES[name]()
+    check_against_ref(planes, stages)
+
+
+def test_oracle_matches_reference_512_rgb():
+    """BASELINE.json configs[0]: the reference's own CPU-runnable case."""
+    check_against_ref(make_image(512, 512, 3, SEED_BASE + 0), ("grad", "r2", "r1"))
+
+
+def test_dyn_tables_match_reference_for_all_min_max():
+    """All 256x256 (min,max) LUTs agree with what the reference emits is checked indirectly through R1
+    streams above; here: the table builder is total and monotone on the valid domain."""
+    from oracle_py import dyn_table
+    for mn in (0, 1, 17, 100, 223, 224, 225, 255):
+        for mx in range(mn, 256, 7):
+            for mode in range(6):
+                lut, b, r = dyn_table(mn, mx, mode)
+                assert len(lut) == (16 if mode < 3 else 8)
+                assert 0 <= b < 64 and 0 <= r < 128
+                assert all(lut[i] <= lut[i + 1] for i in range(len(lut) - 1))
