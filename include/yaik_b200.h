@@ -1,0 +1,162 @@
+/* yaik_b200 — C ABI of the B200-native YAIK encoder-analysis stage.
+ *
+ * The reference (KLab/YAIK) has no plugin/FFI layer: the boundary is four member functions of
+ * `struct EncoderContext` called from `EncoderContext::Convert()` plus two global buffers.  Each entry
+ * point below names the reference interface it replaces (paths under the reference tree; "EC.cpp" =
+ * encoder/EncoderContext.cpp).  The host-side C++ mirror of that class (yaik_b200/host/EncoderContext.h)
+ * and the ctypes binding (yaik_b200/capi.py) call nothing but these symbols.
+ *
+ * Conventions: plain pointers and sizes; every call returns 0 (YK_OK) or a negative YK_ERR_* code; no
+ * exceptions cross the boundary; the caller owns every host buffer; a context is used from one thread at
+ * a time, distinct contexts are independent (one per GPU / per stream).  There is NO CPU fallback: without
+ * a CUDA device every compute entry point fails with YK_ERR_CUDA.
+ *
+ * Domain (SURVEY.md §8c hazards 7, 11): planes are int32 with samples 0..255 (the reference's
+ * `Plane`, encoder/framework.h:74-127, as filled by Image::LoadPNG, Image.cpp:200-229); width and height
+ * are multiples of 4 (the reference's loader demands multiples of 8; 4x4 is the last mip level).  A sample
+ * outside 0..255 makes the analysis return YK_ERR_RANGE (the reference indexes a 256-bin histogram with it,
+ * EC.cpp:8445).  Only the 3-plane RGB form of FittingQuadSmooth (PlaneBit == 7) is provided.
+ */
+#ifndef YAIK_B200_H
+#define YAIK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YK_OK                0
+#define YK_ERR_CUDA         -1   /* CUDA runtime error (yk_last_cuda_error() has the text) */
+#define YK_ERR_ARG          -2   /* bad argument / size outside the domain */
+#define YK_ERR_CAPACITY     -3   /* image or batch larger than the context was created for */
+#define YK_ERR_RANGE        -4   /* a sample outside 0..255 was found */
+#define YK_ERR_STATE        -5   /* call order: stage not run yet / no image set */
+#define YK_ERR_UNSUPPORTED  -6   /* variant of the reference call that this path does not provide */
+#define YK_ERR_NOMEM        -7
+
+/* gradient pass ids in the order EncoderContext::Convert() runs them (EC.cpp:9057-9093):
+ * (shX,shY) = (4,4) (4,3) (3,4) (3,3) (3,2) (2,3) (2,2)  i.e. 16x16 16x8 8x16 8x8 8x4 4x8 4x4 */
+#define YK_NUM_PASSES 7
+
+typedef struct yk_ctx yk_ctx;
+
+int         yk_abi_version(void);
+const char* yk_error_string(int code);
+const char* yk_last_cuda_error(void);
+int         yk_device_count(int* count);
+
+/* One context per GPU (or per stream).  Owns the device planes of `maxSlots` images of up to maxW x maxH
+ * (a "slot" holds one image and every result of its analysis; batches are slots 0..n-1 of the same size),
+ * the compact state masks, the result streams and pinned staging.  Replaces the EncoderContext
+ * constructor/Release pair for this stage (EncoderContext.h:185-232). */
+int  yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPlanes, int maxSlots);
+void yk_destroy(yk_ctx* ctx);
+
+/* Work is enqueued on this cudaStream_t (default: a stream the context creates).  Lets a caller time the
+ * path with its own CUDA events or order it against its own copies. */
+int  yk_set_stream(yk_ctx* ctx, void* cudaStream);
+int  yk_sync(yk_ctx* ctx);
+
+/* Pinned host memory for Plane::pixels so uploads run at full PCIe rate (Plane ctor, framework.h:76). */
+void* yk_host_alloc(size_t bytes);
+void  yk_host_free(void* p);
+
+/* EncoderContext::SetImageToEncode / LoadImagePNG hand-off (EncoderContext.h:230, EC.cpp:1235):
+ * copies Plane::GetPixels() of nPlanes (3 = RGB, 4 = RGBA) planes host -> device into `slot` and resets
+ * the slot's analysis state (the reference allocates its state planes lazily per image, EC.cpp:3739-3749). */
+int  yk_set_image(yk_ctx* ctx, int slot, const int32_t* const* planes, int nPlanes, int w, int h);
+/* Same, planes already resident in device memory (borrowed, not copied; row pitch == w). */
+int  yk_set_image_device(yk_ctx* ctx, int slot, const int32_t* const* devPlanes, int nPlanes, int w, int h);
+/* Device pointer of plane `p` of `slot` (so a caller can fill it in place); NULL on error. */
+int32_t* yk_device_plane(yk_ctx* ctx, int slot, int p);
+int  yk_reset_state(yk_ctx* ctx, int slot);
+
+/* ---- the fused hot path -------------------------------------------------------------------------------
+ * Runs, for slots [slot0, slot0+nSlots) (all the same size), on the device, leaving results in HBM:
+ *   YK_STAGE_ALPHA     MipPrefilter(true)                          EC.cpp:1257-1427 (quadRecursion 357-430)
+ *   YK_STAGE_GRADIENT  the 7 FittingQuadSmooth passes in Convert()'s order   EC.cpp:3710-4235, 9057-9093
+ *   YK_STAGE_RANGE1D   DynamicTileCompressor for R, G, B            EC.cpp:8398-8522
+ *   YK_STAGE_RANGEDYN  DynamicTileEncode (full-resolution planes)   EC.cpp:4365-4503
+ * The per-stage getters below copy the named results to host buffers. */
+#define YK_STAGE_ALPHA     1
+#define YK_STAGE_GRADIENT  2
+#define YK_STAGE_RANGE1D   4
+#define YK_STAGE_RANGEDYN  8
+#define YK_STAGE_RANGEDYN3 16   /* DynamicTileEncode(mode3BitOnly = true) instead of the 6-mode search */
+int  yk_analyze(yk_ctx* ctx, int slot0, int nSlots, int stages, int rejectFactor);
+
+/* ---- stage-by-stage entry points (what the patched member bodies call) ------------------------------- */
+
+/* void EncoderContext::MipPrefilter(bool active)  — EncoderContext.h:332, EC.cpp:1257.
+ * bitmap: ceil(tw*th/8) bytes of the kept-tile bbox, bit i (row-major, LSB first) = tile kept (EC.cpp:1317-1327);
+ * boundPx = boundX0,boundY0,boundX1,boundY1; wroteChunk = 1 when the reference would write the 'MIPM'
+ * chunk (bbox != full image, EC.cpp:1294), chunkBBoxTiles = MipmapHeader.bbox {x,y,w,h} in 16-px tiles.
+ * Outside the reference's own domain (w == h == 2^k >= 16) the same per-16x16 rule is applied.
+ * Runs the stage if yk_analyze has not already. */
+int  yk_alpha_reject(yk_ctx* ctx, int slot, uint8_t* bitmap, int bitmapCap, int* bitmapBytes, int boundPx[4],
+                     int* remainingPixels, int* wroteChunk, int chunkBBoxTiles[4]);
+
+/* void EncoderContext::PrepareQuadSmooth()  — EncoderContext.h:327, EC.cpp:2796 (an empty stub in the
+ * reference; its state is created lazily in FittingQuadSmooth).  Here: runs all 7 passes in one fused
+ * launch sequence so the FittingQuadSmooth calls that follow only fetch their results. */
+int  yk_prepare_quad_smooth(yk_ctx* ctx, int slot, int rejectFactor);
+
+/* int EncoderContext::FittingQuadSmooth(rejectFactor, R, G, B, testOutput, false, shX, shY)
+ *   — EncoderContext.h:329, EC.cpp:3710; the part before the host tail (EC.cpp:3810-4235).
+ * bitmap  = pFillBitMap (getBitmapSwizzleSize()/8 bytes, swizzled bit order, EC.cpp:3770-3777, 4026)
+ * rgb     = rgbStream handed to PaletteCompressor (EC.cpp:4115-4132, 4279), *rgbBytes its length
+ * bbox    = minX,minY,maxX,maxY of accepted tiles (EC.cpp:4039-4042; {w,h,0,0} when none)
+ * tileDone = the function's return value.
+ * If the pass was already produced by yk_prepare_quad_smooth/yk_analyze with the same rejectFactor and it
+ * is the next pass in Convert()'s order, results are fetched; otherwise the single pass is run on the
+ * current state (any order of calls is legal, as in the reference). */
+int  yk_gradient_pass(yk_ctx* ctx, int slot, int rejectFactor, int shX, int shY,
+                      uint8_t* bitmap, int bitmapCap, int* bitmapBytes,
+                      uint8_t* rgb, int rgbCap, int* rgbBytes, int bbox[4], int* tileDone);
+
+/* u8* EncoderContext::DynamicTileCompressor(stream, src = plane, map = mapSmoothTile[plane], debug)
+ *   — EncoderContext.h:236, EC.cpp:8398; globals streamType/pType (EC.cpp:8217-8218) become `type`.
+ * idx: index bytes 0..16 appended for this plane; type: {color0, minCol, delta} per coded tile. */
+int  yk_range1d(yk_ctx* ctx, int slot, int plane, uint8_t* idx, int idxCap, int* idxBytes,
+                uint8_t* type, int typeCap, int* typeBytes);
+
+/* int EncoderContext::DynamicTileEncode(mode3BitOnly, plane, dst, false, false, false, false)
+ *   — EncoderContext.h:370, EC.cpp:4365; the part before the ZSTD tail (EC.cpp:4365-4503).
+ * nibbles: packed 4-bit codes, low nibble first, continuous across tiles (EC.cpp:1174-1190), *nNibbles codes;
+ * defs: EncodeTileType(type, range7, base6) u16 per tile with >= 1 valid pixel (include/YAIK_private.h:358);
+ * constraint: PlaneTile.bbox {x,y,w,h} (EC.cpp:4386-4391); dst (optional, w*h int32): written only at
+ * valid pixels with the decoded value, as the reference does (EC.cpp:4448-4457). */
+int  yk_range_dyn(yk_ctx* ctx, int slot, int plane, int mode3BitOnly, uint8_t* nibbles, int nibCap, int* nNibbles,
+                  uint16_t* defs, int defsCap, int* nDefs, int constraint[4], int32_t* dst);
+
+/* Expands the compact device state into the reference's int32 state planes so later reference stages
+ * (3D LUT search, debug PNGs) keep working: smoothMap, mapSmoothTile[3] (w*h each), mappedRGB[3]
+ * ((w+1)*(h+1) each), mipmapMask, recon = testOutput planes (w*h each) — EncoderContext.h:300-323.
+ * Any pointer may be NULL. */
+int  yk_download_state(yk_ctx* ctx, int slot, int32_t* smoothMap, int32_t* const* mapSmoothTile,
+                       int32_t* const* mappedRGB, int32_t* mipmapMask, int32_t* const* recon);
+
+/* Bytes of result streams the last yk_analyze left in HBM for `slot` (for the roofline's algorithmic
+ * byte count): [0] bitmaps, [1] rgb streams, [2] R2 idx, [3] R2 type, [4] alpha tile bitmap, [5] R1. */
+int  yk_result_bytes(yk_ctx* ctx, int slot, long long out[6]);
+/* Number of kernel launches enqueued by this context since creation. */
+long long yk_launch_count(yk_ctx* ctx);
+
+/* ---- multi-GPU: tile-row strips of one large image ------------------------------------
+ * A strip context holds rows [y0, y0+h) of an image of height imgH (h a multiple of 64 except for the last
+ * strip).  It needs (i) one pixel row below the strip (the clamped bottom corners of its last tile row) and
+ * (ii) per pass the accept bits of the neighbours' adjacent tile rows, so both sides agree on who owns the
+ * boundary lattice row.  Both are plain device buffers that the neighbour fills over NVLink P2P
+ * (cudaMemcpyPeer / cudaIpc*), no collective. */
+int  yk_strip_config(yk_ctx* ctx, int slot, int imgH, int y0);
+int  yk_strip_halo_ptrs(yk_ctx* ctx, int slot, void** pixelRowBelow /* 3*w int32 */, size_t* pixelRowBytes,
+                        void** acceptOut /* this strip's boundary bits */, void** acceptAbove, void** acceptBelow,
+                        size_t* acceptBytes);
+int  yk_strip_phase(yk_ctx* ctx, int slot, int phase, int rejectFactor);  /* 0 = accept phase, 1 = emission phase */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -27,6 +27,17 @@ def _smooth_noisy(w, h, seed, amp):
     return np.clip(out, 0, 255).astype(np.int32)
 
 
+def _patchy(w, h, seed, cell=8, maxamp=3):
+    """Ramp whose noise amplitude changes per `cell` block (0..maxamp): acceptance at every tile size."""
+    base = _smooth_noisy(w, h, seed, 0).astype(np.int64)
+    by, bx = np.meshgrid(np.arange(h) // cell, np.arange(w) // cell, indexing="ij")
+    amp = (_rand(seed, 5, (by * 4096 + bx).astype(np.uint64).ravel()) >> np.uint64(33)).astype(np.int64).reshape(h, w) % (maxamp + 1)
+    amp = np.where((_rand(seed, 6, ((by // 4) * 4096 + bx // 4).astype(np.uint64).ravel()) >> np.uint64(60)).reshape(h, w) < 9, 0, amp)
+    nz = _noise(w, h, 3, seed + 3, 0, 2 * maxamp).astype(np.int64) - maxamp
+    nz = np.clip(nz, -amp, amp)
+    return np.clip(base + nz, 0, 255).astype(np.int32)
+
+
 def _with_alpha(rgb, alpha):
     c, h, w = rgb.shape
     out = np.empty((4, h, w), np.int32)
@@ -52,10 +63,10 @@ SMALL_CASES = {
     "synth256_rgb_3bit": lambda: (make_image(256, 256, 3, SEED_BASE + 13), ("grad", "r1_3bit")),
     # near-tolerance ramps: overlaps between non-nesting tile shapes, all six variants
     "ramp64_a2": lambda: (_smooth_noisy(64, 64, 21, 2), ("grad", "r2", "r1")),
-    "ramp128_a3": lambda: (_smooth_noisy(128, 128, 22, 3), ("grad", "r2", "r1")),
-    "ramp128_a4": lambda: (_smooth_noisy(128, 128, 23, 4), ("grad", "r2", "r1")),
-    "ramp_192x136_a3": lambda: (_smooth_noisy(192, 136, 24, 3), ("grad", "r2", "r1")),   # partial swizzle blocks
-    "ramp_72x40_a3": lambda: (_smooth_noisy(72, 40, 25, 3), ("grad", "r2", "r1")),
+    "ramp128_a1": lambda: (_smooth_noisy(128, 128, 22, 1), ("grad", "r2", "r1")),
+    "patchy128": lambda: (_patchy(128, 128, 23), ("grad", "r2", "r1")),
+    "patchy_192x136": lambda: (_patchy(192, 136, 24, 4, 4), ("grad", "r2", "r1")),   # partial swizzle blocks
+    "patchy_72x40": lambda: (_patchy(72, 40, 25, 4, 3), ("grad", "r2", "r1")),
     # extremes
     "flat64": lambda: (np.full((3, 64, 64), 77, np.int32), ("grad", "r2", "r1")),
     "flat_255": lambda: (np.full((3, 64, 64), 255, np.int32), ("grad", "r2", "r1")),
@@ -71,9 +82,9 @@ SMALL_CASES = {
     # alpha: bbox smaller than the image (MIPM chunk written), holes inside, R1 constraint quirks
     "alpha_island128": lambda: (_with_alpha(make_image(128, 128, 3, SEED_BASE + 16),
                                             _alpha_island(128, 128, 16, 32, 100, 90, [(48, 48, 80, 64)])), ALL),
-    "alpha_island256": lambda: (_with_alpha(_smooth_noisy(256, 256, 28, 3),
+    "alpha_island256": lambda: (_with_alpha(_patchy(256, 256, 28),
                                             _alpha_island(256, 256, 64, 16, 250, 200, [(96, 32, 160, 96), (170, 100, 171, 101)])), ALL),
     "alpha_full_reset64": lambda: (_with_alpha(_noise(64, 64, 3, 35, 90, 99),
                                                _alpha_island(64, 64, 0, 0, 64, 64, [(16, 16, 48, 32)])), ALL),
-    "alpha_corner_only": lambda: (_with_alpha(_smooth_noisy(64, 64, 29, 3), _alpha_island(64, 64, 40, 40, 64, 64)), ALL),
+    "alpha_corner_only": lambda: (_with_alpha(_patchy(64, 64, 29, 4, 3), _alpha_island(64, 64, 40, 40, 64, 64)), ALL),
 }

@@ -1,0 +1,76 @@
+"""Shared parity checker: the C-ABI path (CUDA library on the GPU box, or the CPU-emulated build of the same
+sources for kernel-logic tests here) against the C oracle on the same input.  Bit-exact or fail."""
+import numpy as np
+
+from oracle_py import Oracle, PASS_ORDER
+from yaik_b200 import capi
+
+
+def _eq(a, b, what):
+    a = np.asarray(a); b = np.asarray(b)
+    if a.shape != b.shape or not np.array_equal(a, b):
+        n = min(a.size, b.size)
+        diff = np.nonzero(a.ravel()[:n] != b.ravel()[:n])[0]
+        first = int(diff[0]) if diff.size else n
+        raise AssertionError(f"{what}: sizes {a.size} vs {b.size}, first difference at {first} "
+                             f"(got {a.ravel()[first:first + 8].tolist()} want {b.ravel()[first:first + 8].tolist()}), {diff.size} differ")
+
+
+def check_image(ctx: "capi.Context", planes: np.ndarray, stages, *, fused=True, state=True, slot=0):
+    """stages as in tests/cases.py.  fused=True: one yk_analyze then getters; False: stage-by-stage calls."""
+    c, h, w = planes.shape
+    o = Oracle(planes)
+    ctx.set_image(planes, slot)
+    do_alpha = "alpha" in stages and c == 4
+    do_grad = "grad" in stages
+    do_r2 = "r2" in stages
+    if fused:
+        st = (capi.STAGE_ALPHA if do_alpha else 0) | (capi.STAGE_GRADIENT if do_grad else 0) | (capi.STAGE_RANGE1D if do_r2 else 0)
+        ctx.analyze(st, slot0=slot)
+    if do_alpha:
+        want = o.alpha()
+        if want is not None:
+            got = ctx.alpha_reject(slot)
+            assert got["bound"] == want["bound"], ("alpha bound", got["bound"], want["bound"])
+            assert got["remaining"] == want["remaining"]
+            assert got["wrote"] == want["wrote"]
+            assert got["chunk_bbox"] == want["chunk_bbox"]
+            _eq(got["bitmap"], want["bitmap"], "alpha bitmap")
+    if do_grad:
+        for k, (sx, sy) in enumerate(PASS_ORDER):
+            want = o.gradient_pass(sx, sy)
+            got = ctx.gradient_pass(sx, sy, slot)
+            assert got["tiledone"] == want["tiledone"], (f"pass {k} tileDone", got["tiledone"], want["tiledone"])
+            _eq(got["bitmap"], want["bitmap"], f"pass {k} bitmap")
+            assert got["bbox"] == want["bbox"], (f"pass {k} bbox", got["bbox"], want["bbox"])
+            _eq(got["rgb"], want["rgb"], f"pass {k} rgbStream")
+    if do_r2:
+        for n in range(3):
+            want = o.range1d(n)
+            got = ctx.range1d(n, slot)
+            _eq(got["type"], want["type"], f"R2 type plane {n}")
+            _eq(got["idx"], want["idx"], f"R2 idx plane {n}")
+    if state and do_grad:
+        s = ctx.download_state(slot)
+        _eq(s["smoothMap"].ravel(), o.state(0), "smoothMap")
+        _eq(s["mipmapMask"].ravel(), o.state(1), "mipmapMask")
+        for n in range(3):
+            _eq(s["mapSmoothTile"][n].ravel(), o.state(2 + n), f"mapSmoothTile{n}")
+            _eq(s["mappedRGB"][n].ravel(), o.state(5 + n), f"mappedRGB{n}")
+            _eq(s["recon"][n].ravel(), o.state(8 + n), f"recon{n}")
+    if "r1" in stages or "r1_3bit" in stages:
+        for n in range(3):
+            want = o.range_dyn(n, mode3="r1_3bit" in stages, want_dst=True)
+            try:
+                got = ctx.range_dyn(n, mode3="r1_3bit" in stages, slot=slot, want_dst=True)
+            except capi.YaikError as e:
+                if e.code == -6:
+                    import pytest
+                    pytest.skip("R1 (DynamicTileEncode) not built yet; alpha/gradient/R2 matched")
+                raise
+            assert got["constraint"] == want["constraint"]
+            _eq(got["defs"], want["defs"], f"R1 defs plane {n}")
+            assert got["n_nibbles"] == want["n_nibbles"]
+            _eq(got["nibbles"], want["nibbles"], f"R1 nibbles plane {n}")
+            _eq(got["dst"], want["dst"], f"R1 dst plane {n}")
+    o.close()

@@ -1,0 +1,128 @@
+"""GPU parity tests proper (-m gpu): the CUDA library through the C ABI against the C oracle, bit-exact, on the
+seeded cases (all edge cases the oracle was pinned on), on BASELINE.json config sizes, and through
+size-independent properties at the full sizes.  Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+import cases
+from parity import check_image
+from yaik_b200 import capi
+from yaik_b200.synth import make_image, mip_chain, SEED_BASE
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return capi.load_library()        # raises if libyaik_b200.so is missing: no fallback
+
+
+@pytest.fixture(scope="module")
+def ctx(lib):
+    c = capi.Context(1024, 1024, planes=4, slots=2, lib=lib)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", list(cases.SMALL_CASES))
+def test_small_cases_fused(ctx, name):
+    planes, stages = cases.SMALL_CASES[name]()
+    check_image(ctx, planes, stages, fused=True)
+
+
+@pytest.mark.parametrize("name", ["patchy128", "patchy_192x136", "alpha_island128", "ramp64_a2"])
+def test_small_cases_stage_by_stage(ctx, name):
+    planes, stages = cases.SMALL_CASES[name]()
+    check_image(ctx, planes, stages, fused=False)
+
+
+def test_config0_512_rgb(ctx):
+    """BASELINE.json configs[0]: 512x512 RGB illustration-like image, gradient + range stages."""
+    check_image(ctx, make_image(512, 512, 3, SEED_BASE + 0), ("grad", "r2", "r1"))
+
+
+def test_1024_rgba_full_compare(ctx):
+    """One texture of BASELINE.json configs[2] (256 x 1024x1024 RGBA): full comparison with the oracle."""
+    check_image(ctx, make_image(1024, 1024, 4, SEED_BASE + 2), ("alpha", "grad", "r2"))
+
+
+def test_batch_equals_single(lib):
+    """configs[2] shape: a batch launch over slots gives exactly what one-image launches give."""
+    imgs = [make_image(256, 256, 4, SEED_BASE + 100 + i) for i in range(4)]
+    cb = capi.Context(256, 256, planes=4, slots=4, lib=lib)
+    cs = capi.Context(256, 256, planes=4, slots=1, lib=lib)
+    try:
+        for i, im in enumerate(imgs):
+            cb.set_image(im, i)
+        cb.analyze(capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D, slot0=0, n_slots=4)
+        for i, im in enumerate(imgs):
+            cs.set_image(im, 0)
+            cs.analyze(capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D)
+            for sx, sy in capi.PASS_ORDER:
+                a, b = cb.gradient_pass(sx, sy, slot=i), cs.gradient_pass(sx, sy)
+                assert a["tiledone"] == b["tiledone"] and a["bbox"] == b["bbox"]
+                assert np.array_equal(a["bitmap"], b["bitmap"]) and np.array_equal(a["rgb"], b["rgb"])
+            for p in range(3):
+                a, b = cb.range1d(p, slot=i), cs.range1d(p)
+                assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["type"], b["type"])
+    finally:
+        cb.close(); cs.close()
+
+
+def test_config1_2048_rgba_properties(lib):
+    """BASELINE.json configs[1] at full size: oracle comparison of every stream plus size-independent properties
+    (bitmap popcount == TileDone, claimed cells == union of accepted tiles, R2 length == 16 bytes per unclaimed
+    cell, idempotence of a second run)."""
+    planes = make_image(2048, 2048, 4, SEED_BASE + 1)
+    c = capi.Context(2048, 2048, planes=4, slots=1, lib=lib)
+    try:
+        check_image(c, planes, ("alpha", "grad", "r2"), state=False)
+        c.set_image(planes)
+        c.analyze(capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D)
+        first = [c.gradient_pass(sx, sy) for sx, sy in capi.PASS_ORDER]
+        for g in first:
+            assert int(np.unpackbits(g["bitmap"]).sum()) == g["tiledone"]
+        st = c.download_state(recon=False)
+        claimed = (st["smoothMap"] != 0)
+        cells = claimed.reshape(512, 4, 512, 4)
+        assert (cells.all(axis=(1, 3)) | ~cells.any(axis=(1, 3))).all()          # claims are whole 4x4 cells
+        r = c.range1d(0)
+        assert r["idx"].size == int((~claimed).sum())
+        assert r["idx"].max() <= 16
+        c.set_image(planes)
+        c.analyze(capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D)
+        for g, (sx, sy) in zip(first, capi.PASS_ORDER):
+            h = c.gradient_pass(sx, sy)
+            assert np.array_equal(g["bitmap"], h["bitmap"]) and np.array_equal(g["rgb"], h["rgb"])
+    finally:
+        c.close()
+
+
+def test_config4_mip_chain(lib):
+    """BASELINE.json configs[4]: RGBA mip chain down to 4x4 (small-tile and alpha-rejection paths); levels run the
+    stages the reference itself supports at that size (SURVEY.md hazards 7, 11)."""
+    chain = mip_chain(512, SEED_BASE + 4)
+    c = capi.Context(512, 512, planes=4, slots=1, lib=lib)
+    try:
+        for lvl in chain:
+            s = lvl.shape[1]
+            stages = ["grad"]
+            if s >= 16 and lvl[3].any():
+                stages.append("alpha")
+            if s >= 8:
+                stages.append("r2")
+            if s >= 32:
+                stages.append("r1")
+            check_image(c, lvl, tuple(stages))
+    finally:
+        c.close()
+
+
+def test_out_of_range_sample_is_reported(ctx):
+    planes = make_image(64, 64, 3, SEED_BASE + 7).copy()
+    planes[1, 10, 10] = 300
+    ctx.set_image(planes)
+    ctx.analyze(capi.STAGE_GRADIENT)
+    with pytest.raises(capi.YaikError) as e:
+        ctx.gradient_pass(4, 4)
+    assert e.value.code == -4

@@ -1,0 +1,519 @@
+// yaik_b200 — the extern "C" layer declared in include/yaik_b200.h: context/slot management, launch sequencing and
+// result download.  Host code is C++; all device work goes through the launch wrappers of yk_kernels.cu.
+// There is no CPU path here: every compute entry point needs a CUDA device.
+#include "../../include/yaik_b200.h"
+#include "yk_internal.h"
+
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_lastCuda;
+
+#define CK(call)                                                                            \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            g_lastCuda = std::string(#call) + ": " + cudaGetErrorString(e__);               \
+            return YK_ERR_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+static const YkPassGeom kGeom[YK_NPASS] = YK_PASS_TABLE;
+
+static int pass_id(int shX, int shY) {
+    for (int i = 0; i < YK_NPASS; i++) if (kGeom[i].shx == shX && kGeom[i].shy == shY) return i;
+    return -1;
+}
+
+struct YkSlotHost {
+    YkSlotDev d;
+    bool haveImage = false, borrowed = false, dirty = true;
+    int32_t* owned[4] = { 0, 0, 0, 0 };
+    // what is valid on the device for the current image
+    bool k1Ran = false;          // r2Seg / latRGB are current
+    bool alphaRan = false, alphaFetched = false;
+    bool prepared = false;       // fused 7-pass cascade results present
+    int  preparedReject = 0, nextPass = 0;
+    bool r2Valid = false;
+    bool pendingHarvest = false; // a run's header has not been copied back yet
+    int  lastRunPasses = 0;      // bit p: pass p was in the last run; bit 8: alpha
+    int  rangeErr = 0;
+    int  hdr[YK_HD_INTS];        // harvested copy: per-pass stats of the run that produced them, alpha box, R2 totals
+    long long resultBytes[6] = { 0, 0, 0, 0, 0, 0 };
+    // alpha results (host)
+    int bound[4] = { 0, 0, 0, 0 }, remaining = 0, wroteChunk = 0, chunkBBox[4] = { 0, 0, 0, 0 };
+    std::vector<uint8_t> alphaBitmap;
+    void* devAllocs[64]; int nAllocs = 0;
+};
+
+struct yk_ctx {
+    int device = 0, maxW = 0, maxH = 0, maxPlanes = 0, maxSlots = 0;
+    cudaStream_t stream = 0; bool ownStream = false;
+    YkSlotDev* slotsDev = nullptr;
+    std::vector<YkSlotHost> slots;
+    uint8_t* zeroArea = nullptr; size_t zeroStride = 0;
+    int* lutDev = nullptr;       // R1 tables
+    long long launches = 0;
+    size_t planeCap = 0;
+};
+
+extern "C" int yk_abi_version(void) { return 1; }
+
+extern "C" const char* yk_error_string(int code) {
+    switch (code) {
+    case YK_OK: return "ok";
+    case YK_ERR_CUDA: return "CUDA error";
+    case YK_ERR_ARG: return "bad argument";
+    case YK_ERR_CAPACITY: return "capacity exceeded";
+    case YK_ERR_RANGE: return "sample outside 0..255";
+    case YK_ERR_STATE: return "wrong call order / no image";
+    case YK_ERR_UNSUPPORTED: return "unsupported variant";
+    case YK_ERR_NOMEM: return "out of memory";
+    default: return "unknown";
+    }
+}
+extern "C" const char* yk_last_cuda_error(void) { return g_lastCuda.c_str(); }
+
+extern "C" int yk_device_count(int* count) {
+    if (!count) return YK_ERR_ARG;
+    *count = 0;
+    CK(cudaGetDeviceCount(count));
+    return YK_OK;
+}
+
+extern "C" void* yk_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void yk_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+template <class T> static int dev_alloc(YkSlotHost& s, T** out, size_t count) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (count ? count : 1) * sizeof(T) + 64));
+    if (s.nAllocs < 64) s.devAllocs[s.nAllocs++] = p;
+    *out = (T*)p;
+    return YK_OK;
+}
+
+extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPlanes, int maxSlots) {
+    if (!out || maxW < 4 || maxH < 4 || (maxW & 3) || (maxH & 3) || maxPlanes < 3 || maxPlanes > 4 || maxSlots < 1) return YK_ERR_ARG;
+    if (maxW > 32764 || maxH > 32764) return YK_ERR_ARG;      // BoundingBox is s16 in the stream headers (YAIK_private.h:15-20)
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return YK_ERR_ARG;
+    CK(cudaSetDevice(device));
+    yk_ctx* c = new yk_ctx();
+    c->device = device; c->maxW = maxW; c->maxH = maxH; c->maxPlanes = maxPlanes; c->maxSlots = maxSlots;
+    c->slots.resize(maxSlots);
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->ownStream = true;
+    CK(cudaMalloc((void**)&c->slotsDev, sizeof(YkSlotDev) * maxSlots));
+    const size_t W = maxW, H = maxH;
+    const size_t nbx = (W + 63) / 64, latW = W / 4 + 1, latH = H / 4 + 1, cw = (latW + 31) / 32 + 1;
+    c->planeCap = W * H;
+    // zero area per slot: header ints + cornerNew
+    c->zeroStride = ((YK_HD_INTS * sizeof(int) + latH * cw * 4 + 255) / 256) * 256;
+    CK(cudaMalloc((void**)&c->zeroArea, c->zeroStride * maxSlots));
+    CK(cudaMemset(c->zeroArea, 0, c->zeroStride * maxSlots));
+    for (int i = 0; i < maxSlots; i++) {
+        YkSlotHost& s = c->slots[i];
+        memset(&s.d, 0, sizeof s.d);
+        int rc;
+        for (int p = 0; p < maxPlanes; p++) if ((rc = dev_alloc(s, &s.owned[p], W * H))) return rc;
+        if ((rc = dev_alloc(s, &s.d.cellMask, (H / 4 + 1) * nbx))) return rc;
+        if ((rc = dev_alloc(s, &s.d.cornerMask, latH * cw))) return rc;
+        s.d.hdr = (int*)(c->zeroArea + c->zeroStride * i);
+        s.d.cornerNew = (uint32_t*)(c->zeroArea + c->zeroStride * i + YK_HD_INTS * sizeof(int));
+        if ((rc = dev_alloc(s, &s.d.alphaKept, ((H + 15) / 16) * ((W + 15) / 16)))) return rc;
+        for (int p = 0; p < YK_NPASS; p++) {
+            const YkPassGeom& g = kGeom[p];
+            size_t nu = ((W + g.bw - 1) / g.bw) * ((H + g.bh - 1) / g.bh);
+            if ((rc = dev_alloc(s, &s.d.bitmap[p], nu * g.bits / 8))) return rc;
+            if ((rc = dev_alloc(s, &s.d.emitMask[p], nu * g.bits))) return rc;
+            if ((rc = dev_alloc(s, &s.d.unitOff[p], nu))) return rc;
+            if ((rc = dev_alloc(s, &s.d.rgb[p], 3 * ((W >> g.shx) + 1) * ((H >> g.shy) + 1)))) return rc;
+        }
+        if ((rc = dev_alloc(s, &s.d.latRGB, latW * latH * 3))) return rc;
+        if ((rc = dev_alloc(s, &s.d.r2Seg, (H / 8 + 1) * nbx))) return rc;
+        if ((rc = dev_alloc(s, &s.d.r2SegTiles, (H / 8 + 1) * nbx))) return rc;
+        for (int p = 0; p < 3; p++) {
+            if ((rc = dev_alloc(s, &s.d.r2Idx[p], W * H))) return rc;
+            if ((rc = dev_alloc(s, &s.d.r2Type[p], 3 * (W / 8 + 1) * (H / 8 + 1)))) return rc;
+        }
+        size_t nblk = (W / 8) * (H / 8 + 1) + 1;
+        if ((rc = dev_alloc(s, &s.d.r1Cnt, nblk))) return rc;
+        if ((rc = dev_alloc(s, &s.d.r1Def, nblk))) return rc;
+        for (int p = 0; p < 3; p++) {
+            if ((rc = dev_alloc(s, &s.d.r1Nib[p], (W / 8) * (H / 8) * 8 + 4))) return rc;
+            if ((rc = dev_alloc(s, &s.d.r1Defs[p], (W / 8) * (H / 8) + 4))) return rc;
+        }
+    }
+    *out = c;
+    return YK_OK;
+}
+
+extern "C" void yk_destroy(yk_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& s : c->slots) for (int i = 0; i < s.nAllocs; i++) cudaFree(s.devAllocs[i]);
+    cudaFree(c->slotsDev); cudaFree(c->zeroArea);
+    if (c->lutDev) cudaFree(c->lutDev);
+    if (c->ownStream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int yk_set_stream(yk_ctx* c, void* st) {
+    if (!c) return YK_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->ownStream) { cudaStreamDestroy(c->stream); c->ownStream = false; }
+    c->stream = (cudaStream_t)st;
+    return YK_OK;
+}
+extern "C" int yk_sync(yk_ctx* c) {
+    if (!c) return YK_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return YK_OK;
+}
+extern "C" long long yk_launch_count(yk_ctx* c) { return c ? c->launches : 0; }
+
+static int slot_ok(yk_ctx* c, int slot) { return c && slot >= 0 && slot < c->maxSlots; }
+
+static int configure_slot(yk_ctx* c, int slot, int nPlanes, int w, int h) {
+    if (nPlanes < 3 || nPlanes > 4 || w < 4 || h < 4 || (w & 3) || (h & 3)) return YK_ERR_ARG;
+    if (w > c->maxW || h > c->maxH || (size_t)w * h > c->planeCap || nPlanes > c->maxPlanes) return YK_ERR_CAPACITY;
+    YkSlotHost& s = c->slots[slot];
+    s.d.w = w; s.d.h = h; s.d.nPlanes = nPlanes;
+    s.d.nbx = (w + 63) / 64; s.d.nby = (h + 63) / 64;
+    s.d.imgH = h; s.d.y0 = 0;
+    s.d.latW = w / 4 + 1; s.d.latH = h / 4 + 1;
+    s.d.cornerWords = (s.d.latW + 31) / 32 + 1;
+    for (int p = 0; p < 3; p++) s.d.rowBelow[p] = nullptr;
+    s.haveImage = true;
+    return YK_OK;
+}
+
+extern "C" int yk_reset_state(yk_ctx* c, int slot) {
+    if (!slot_ok(c, slot)) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(s.d.cellMask, 0, (size_t)(s.d.h / 4 + 1) * s.d.nbx * sizeof(uint16_t), c->stream));
+    CK(cudaMemsetAsync(s.d.cornerMask, 0, (size_t)s.d.latH * s.d.cornerWords * 4, c->stream));
+    s.d.alphaReset = 0; s.d.alphaValid = 0;
+    s.k1Ran = s.alphaRan = s.alphaFetched = s.prepared = s.r2Valid = s.pendingHarvest = false;
+    s.nextPass = 0; s.dirty = true; s.rangeErr = 0; s.lastRunPasses = 0;
+    memset(s.hdr, 0, sizeof s.hdr);
+    return YK_OK;
+}
+
+extern "C" int yk_set_image(yk_ctx* c, int slot, const int32_t* const* planes, int nPlanes, int w, int h) {
+    if (!slot_ok(c, slot) || !planes) return YK_ERR_ARG;
+    int rc = configure_slot(c, slot, nPlanes, w, h);
+    if (rc) return rc;
+    YkSlotHost& s = c->slots[slot];
+    CK(cudaSetDevice(c->device));
+    for (int p = 0; p < nPlanes; p++) {
+        if (!planes[p]) return YK_ERR_ARG;
+        CK(cudaMemcpyAsync(s.owned[p], planes[p], (size_t)w * h * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        s.d.plane[p] = s.owned[p];
+    }
+    for (int p = nPlanes; p < 4; p++) s.d.plane[p] = nullptr;
+    s.borrowed = false;
+    return yk_reset_state(c, slot);
+}
+
+extern "C" int yk_set_image_device(yk_ctx* c, int slot, const int32_t* const* devPlanes, int nPlanes, int w, int h) {
+    if (!slot_ok(c, slot) || !devPlanes) return YK_ERR_ARG;
+    int rc = configure_slot(c, slot, nPlanes, w, h);
+    if (rc) return rc;
+    YkSlotHost& s = c->slots[slot];
+    for (int p = 0; p < nPlanes; p++) {
+        if (!devPlanes[p] || ((uintptr_t)devPlanes[p] & 15)) return YK_ERR_ARG;
+        s.d.plane[p] = devPlanes[p];
+    }
+    for (int p = nPlanes; p < 4; p++) s.d.plane[p] = nullptr;
+    s.borrowed = true;
+    return yk_reset_state(c, slot);
+}
+
+extern "C" int32_t* yk_device_plane(yk_ctx* c, int slot, int p) {
+    if (!slot_ok(c, slot) || p < 0 || p >= c->maxPlanes) return nullptr;
+    return c->slots[slot].owned[p];
+}
+
+static int upload_slots(yk_ctx* c, int slot0, int nSlots) {
+    for (int i = slot0; i < slot0 + nSlots; i++) {
+        YkSlotHost& s = c->slots[i];
+        if (s.dirty) {
+            CK(cudaMemcpyAsync(c->slotsDev + i, &s.d, sizeof(YkSlotDev), cudaMemcpyHostToDevice, c->stream));
+            s.dirty = false;
+        }
+    }
+    return YK_OK;
+}
+
+static int check_batch(yk_ctx* c, int slot0, int nSlots) {
+    if (!c || nSlots < 1 || slot0 < 0 || slot0 + nSlots > c->maxSlots) return YK_ERR_ARG;
+    const YkSlotHost& a = c->slots[slot0];
+    for (int i = slot0; i < slot0 + nSlots; i++) {
+        const YkSlotHost& s = c->slots[i];
+        if (!s.haveImage) return YK_ERR_STATE;
+        if (s.d.w != a.d.w || s.d.h != a.d.h) return YK_ERR_ARG;
+    }
+    return YK_OK;
+}
+
+// Copy back the header of the last run (one sync) and keep what that run produced: the stats of its passes, the
+// alpha box if it ran the alpha stage, the R2 totals (the scan always refreshes them).
+static int fetch_hdr(yk_ctx* c, YkSlotHost& s) {
+    if (s.pendingHarvest) {
+        int tmp[YK_HD_INTS];
+        CK(cudaMemcpyAsync(tmp, s.d.hdr, sizeof tmp, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        s.pendingHarvest = false;
+        if (tmp[YK_HD_ERR] & 1) s.rangeErr = 1;
+        for (int p = 0; p < YK_NPASS; p++)
+            if (s.lastRunPasses & (1 << p)) memcpy(s.hdr + YK_HD_PASS0 + p * YK_ST_STRIDE, tmp + YK_HD_PASS0 + p * YK_ST_STRIDE, YK_ST_STRIDE * sizeof(int));
+        if (s.lastRunPasses & 256) memcpy(s.hdr + YK_HD_ALPHA_MINX, tmp + YK_HD_ALPHA_MINX, 5 * sizeof(int));
+        s.hdr[YK_HD_R2_CHUNKS] = tmp[YK_HD_R2_CHUNKS]; s.hdr[YK_HD_R2_TILES] = tmp[YK_HD_R2_TILES];
+    }
+    return s.rangeErr ? YK_ERR_RANGE : YK_OK;
+}
+
+// Enqueue analysis kernels for a run (list of gradient passes, optional alpha), then the emission + scan + R2 tail.
+static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEmit, bool doR2) {
+    int rc = check_batch(c, slot0, nSlots);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    const YkSlotHost& a = c->slots[slot0];
+    const int nRegions = a.d.nbx * a.d.nby;
+    for (int i = slot0; i < slot0 + nSlots; i++)            // the header is about to be cleared: keep the previous run's numbers
+        if (c->slots[i].pendingHarvest) { rc = fetch_hdr(c, c->slots[i]); if (rc && rc != YK_ERR_RANGE) return rc; }
+    CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * slot0, 0, c->zeroStride * nSlots, c->stream));
+    if ((rc = upload_slots(c, slot0, nSlots))) return rc;
+    yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++;
+    if (doEmit && run.nPasses > 0) { yk_launch_emit_count(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
+    yk_launch_scan(c->slotsDev, slot0, nSlots, run, c->stream); c->launches++;
+    if (doEmit && run.nPasses > 0) { yk_launch_emit_write(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
+    if (doR2) { yk_launch_range1d(c->slotsDev, slot0, nSlots, nRegions, c->stream); c->launches++; }
+    CK(cudaGetLastError());
+    for (int i = slot0; i < slot0 + nSlots; i++) {
+        YkSlotHost& s = c->slots[i];
+        s.k1Ran = true; s.pendingHarvest = true; s.lastRunPasses = (run.doAlpha ? 256 : 0);
+        for (int p = 0; p < run.nPasses; p++) s.lastRunPasses |= 1 << run.passId[p];
+        if (run.doAlpha && s.d.nPlanes == 4) { s.alphaRan = true; s.alphaFetched = false; }
+        if (run.nPasses > 0) s.r2Valid = false;
+        if (doR2) s.r2Valid = true;
+    }
+    return YK_OK;
+}
+
+extern "C" int yk_analyze(yk_ctx* c, int slot0, int nSlots, int stages, int rejectFactor) {
+    if (!c || rejectFactor < 0 || rejectFactor > 64) return YK_ERR_ARG;
+    if (stages & (YK_STAGE_RANGEDYN | YK_STAGE_RANGEDYN3)) return YK_ERR_UNSUPPORTED;   // R1 is driven per plane through yk_range_dyn
+    YkRun run; memset(&run, 0, sizeof run);
+    run.rejectFactor = rejectFactor;
+    run.doAlpha = (stages & YK_STAGE_ALPHA) ? 1 : 0;
+    if (stages & YK_STAGE_GRADIENT) { run.nPasses = YK_NPASS; for (int i = 0; i < YK_NPASS; i++) run.passId[i] = i; }
+    int rc = check_batch(c, slot0, nSlots);
+    if (rc) return rc;
+    if (stages & YK_STAGE_GRADIENT)
+        for (int i = slot0; i < slot0 + nSlots; i++) if (c->slots[i].prepared || c->slots[i].nextPass) return YK_ERR_STATE;   // needs a fresh state
+    rc = enqueue(c, slot0, nSlots, run, true, (stages & YK_STAGE_RANGE1D) != 0);
+    if (rc) return rc;
+    if (stages & YK_STAGE_GRADIENT)
+        for (int i = slot0; i < slot0 + nSlots; i++) { c->slots[i].prepared = true; c->slots[i].preparedReject = rejectFactor; c->slots[i].nextPass = 0; }
+    return YK_OK;
+}
+
+extern "C" int yk_prepare_quad_smooth(yk_ctx* c, int slot, int rejectFactor) {
+    return yk_analyze(c, slot, 1, YK_STAGE_GRADIENT, rejectFactor);
+}
+
+// ---- alpha ------------------------------------------------------------------------------------------------
+static int alpha_finish(yk_ctx* c, YkSlotHost& s) {
+    if (s.alphaFetched) return YK_OK;
+    int rc = fetch_hdr(c, s);
+    if (rc) return rc;
+    const int w = s.d.w, h = s.d.h, big = INT_MAX / 2;
+    const int tw = (w + 15) / 16, th = (h + 15) / 16;
+    if (s.hdr[YK_HD_ALPHA_KEPT] == 0) return YK_ERR_ARG;        // fully transparent: outside the reference's domain (sentinel bbox)
+    const int L = w - s.hdr[YK_HD_ALPHA_MINX], T = big - s.hdr[YK_HD_ALPHA_MINY];
+    const int R = s.hdr[YK_HD_ALPHA_MAXX], B = s.hdr[YK_HD_ALPHA_MAXY];
+    s.bound[0] = L; s.bound[1] = T; s.bound[2] = R; s.bound[3] = B;
+    s.alphaBitmap.clear();
+    if (L != 0 || T != 0 || R != w || B != s.d.imgH) {           // EC.cpp:1294
+        std::vector<uint8_t> kept((size_t)tw * th);
+        CK(cudaMemcpyAsync(kept.data(), s.d.alphaKept, kept.size(), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        const int bx0 = L >> 4, bx1 = (R + 15) >> 4, by0 = T >> 4, by1 = (B + 15) >> 4;
+        const int tWB = bx1 - bx0, tHB = by1 - by0;
+        s.alphaBitmap.assign((size_t)(tWB * tHB + 7) / 8, 0);
+        int bit = 0, rem = 0;
+        for (int y = 0; y < tHB; y++)
+            for (int x = 0; x < tWB; x++, bit++)
+                if (kept[(size_t)(y + by0) * tw + x + bx0]) { s.alphaBitmap[bit >> 3] |= (uint8_t)(1 << (bit & 7)); rem += 256; }   // EC.cpp:1317-1327
+        s.remaining = rem; s.wroteChunk = 1;
+        s.chunkBBox[0] = bx0; s.chunkBBox[1] = by0; s.chunkBBox[2] = tWB; s.chunkBBox[3] = tHB;
+        s.d.alphaReset = 0;
+    } else {
+        s.remaining = R * B; s.wroteChunk = 0; s.d.alphaReset = 1;     // EC.cpp:1400-1403
+    }
+    s.d.alphaValid = 1; s.dirty = true; s.alphaFetched = true;
+    return YK_OK;
+}
+
+extern "C" int yk_alpha_reject(yk_ctx* c, int slot, uint8_t* bitmap, int bitmapCap, int* bitmapBytes, int boundPx[4],
+                               int* remainingPixels, int* wroteChunk, int chunkBBoxTiles[4]) {
+    if (!slot_ok(c, slot)) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    if (s.d.nPlanes != 4) return YK_ERR_ARG;
+    if (!s.alphaRan) {
+        YkRun run; memset(&run, 0, sizeof run); run.doAlpha = 1; run.rejectFactor = 3;
+        int rc = enqueue(c, slot, 1, run, false, false);
+        if (rc) return rc;
+    }
+    int rc = alpha_finish(c, s);
+    if (rc) return rc;
+    if ((int)s.alphaBitmap.size() > bitmapCap) return YK_ERR_CAPACITY;
+    if (bitmap && !s.alphaBitmap.empty()) memcpy(bitmap, s.alphaBitmap.data(), s.alphaBitmap.size());
+    if (bitmapBytes) *bitmapBytes = (int)s.alphaBitmap.size();
+    if (boundPx) memcpy(boundPx, s.bound, sizeof s.bound);
+    if (remainingPixels) *remainingPixels = s.remaining;
+    if (wroteChunk) *wroteChunk = s.wroteChunk;
+    if (chunkBBoxTiles) memcpy(chunkBBoxTiles, s.chunkBBox, sizeof s.chunkBBox);
+    return YK_OK;
+}
+
+// ---- gradient ---------------------------------------------------------------------------------------------
+extern "C" int yk_gradient_pass(yk_ctx* c, int slot, int rejectFactor, int shX, int shY,
+                                uint8_t* bitmap, int bitmapCap, int* bitmapBytes,
+                                uint8_t* rgb, int rgbCap, int* rgbBytes, int bbox[4], int* tileDone) {
+    if (!slot_ok(c, slot)) return YK_ERR_ARG;
+    const int pid = pass_id(shX, shY);
+    if (pid < 0 || rejectFactor < 0 || rejectFactor > 64) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    int rc;
+    if (s.prepared) {
+        // results of the fused cascade are only what the reference would compute if the passes are consumed in
+        // Convert()'s order with the same rejectFactor
+        if (pid != s.nextPass || rejectFactor != s.preparedReject) return YK_ERR_STATE;
+        s.nextPass++;
+    } else {
+        YkRun run; memset(&run, 0, sizeof run);
+        run.nPasses = 1; run.passId[0] = pid; run.rejectFactor = rejectFactor;
+        if ((rc = enqueue(c, slot, 1, run, true, false))) return rc;
+        s.nextPass = -1;
+    }
+    if ((rc = fetch_hdr(c, s))) return rc;
+    const YkPassGeom& g = kGeom[pid];
+    const int w = s.d.w, h = s.d.h;
+    const int nb = ((w + g.bw - 1) / g.bw) * ((h + g.bh - 1) / g.bh) * g.bits / 8;
+    const int* st = s.hdr + YK_HD_PASS0 + pid * YK_ST_STRIDE;
+    const int nrgb = st[YK_ST_RGBBYTES];
+    if (nb > bitmapCap || nrgb > rgbCap) return YK_ERR_CAPACITY;
+    CK(cudaSetDevice(c->device));
+    if (bitmap) CK(cudaMemcpyAsync(bitmap, s.d.bitmap[pid], nb, cudaMemcpyDeviceToHost, c->stream));
+    if (rgb && nrgb) CK(cudaMemcpyAsync(rgb, s.d.rgb[pid], nrgb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (bitmapBytes) *bitmapBytes = nb;
+    if (rgbBytes) *rgbBytes = nrgb;
+    if (tileDone) *tileDone = st[YK_ST_TILEDONE];
+    if (bbox) {
+        bbox[0] = w - st[YK_ST_MINX];
+        bbox[1] = st[YK_ST_MINY] ? INT_MAX / 2 - st[YK_ST_MINY] : s.d.imgH;
+        bbox[2] = st[YK_ST_MAXX]; bbox[3] = st[YK_ST_MAXY];
+    }
+    return YK_OK;
+}
+
+// ---- range R2 ---------------------------------------------------------------------------------------------
+extern "C" int yk_range1d(yk_ctx* c, int slot, int plane, uint8_t* idx, int idxCap, int* idxBytes,
+                          uint8_t* type, int typeCap, int* typeBytes) {
+    if (!slot_ok(c, slot) || plane < 0 || plane > 2) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    if ((s.d.w & 7) || (s.d.h & 7)) return YK_ERR_ARG;          // the reference's own domain (SURVEY.md hazard 11)
+    int rc;
+    if (!s.r2Valid) {
+        YkRun run; memset(&run, 0, sizeof run); run.rejectFactor = 3;      // no gradient pass: refresh segments, scan, code
+        if ((rc = enqueue(c, slot, 1, run, false, true))) return rc;
+    }
+    if ((rc = fetch_hdr(c, s))) return rc;
+    const long long ni = 16ll * s.hdr[YK_HD_R2_CHUNKS], nt = 3ll * s.hdr[YK_HD_R2_TILES];
+    if (ni > idxCap || nt > typeCap) return YK_ERR_CAPACITY;
+    CK(cudaSetDevice(c->device));
+    if (idx && ni) CK(cudaMemcpyAsync(idx, s.d.r2Idx[plane], (size_t)ni, cudaMemcpyDeviceToHost, c->stream));
+    if (type && nt) CK(cudaMemcpyAsync(type, s.d.r2Type[plane], (size_t)nt, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (idxBytes) *idxBytes = (int)ni;
+    if (typeBytes) *typeBytes = (int)nt;
+    return YK_OK;
+}
+
+// ---- compat state download --------------------------------------------------------------------------------
+extern "C" int yk_download_state(yk_ctx* c, int slot, int32_t* smoothMap, int32_t* const* mapSmoothTile,
+                                 int32_t* const* mappedRGB, int32_t* mipmapMask, int32_t* const* recon) {
+    if (!slot_ok(c, slot)) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    CK(cudaSetDevice(c->device));
+    if (s.alphaRan && !s.alphaFetched) { int rc = alpha_finish(c, s); if (rc) return rc; }
+    int rc = upload_slots(c, slot, 1);
+    if (rc) return rc;
+    const size_t n = (size_t)s.d.w * s.d.h, n1 = (size_t)(s.d.w + 1) * (s.d.h + 1);
+    int32_t *dSmooth = nullptr, *dMask = nullptr, *dMapped = nullptr, *dRec = nullptr;
+    const bool wantSmooth = smoothMap || mapSmoothTile, wantRec = recon != nullptr;
+    if (wantSmooth) CK(cudaMalloc((void**)&dSmooth, n * 4));
+    if (mipmapMask) CK(cudaMalloc((void**)&dMask, n * 4));
+    if (mappedRGB) CK(cudaMalloc((void**)&dMapped, n1 * 4));
+    if (wantRec) CK(cudaMalloc((void**)&dRec, 3 * n * 4));
+    yk_launch_state(c->slotsDev, slot, s.d.nbx * s.d.nby, dSmooth, dMask, dMapped, dRec, dRec ? dRec + n : nullptr, dRec ? dRec + 2 * n : nullptr, c->stream);
+    c->launches++;
+    CK(cudaGetLastError());
+    if (smoothMap) CK(cudaMemcpyAsync(smoothMap, dSmooth, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (mapSmoothTile) for (int p = 0; p < 3; p++) if (mapSmoothTile[p]) CK(cudaMemcpyAsync(mapSmoothTile[p], dSmooth, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (mipmapMask) CK(cudaMemcpyAsync(mipmapMask, dMask, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (mappedRGB) for (int p = 0; p < 3; p++) if (mappedRGB[p]) CK(cudaMemcpyAsync(mappedRGB[p], dMapped, n1 * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (recon) for (int p = 0; p < 3; p++) if (recon[p]) CK(cudaMemcpyAsync(recon[p], dRec + p * n, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(dSmooth); cudaFree(dMask); cudaFree(dMapped); cudaFree(dRec);
+    return YK_OK;
+}
+
+extern "C" int yk_result_bytes(yk_ctx* c, int slot, long long out[6]) {
+    if (!slot_ok(c, slot) || !out) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    int rc = fetch_hdr(c, s);
+    if (rc) return rc;
+    const int w = s.d.w, h = s.d.h;
+    long long bm = 0, rgb = 0;
+    for (int p = 0; p < YK_NPASS; p++) {
+        const YkPassGeom& g = kGeom[p];
+        bm += (long long)((w + g.bw - 1) / g.bw) * ((h + g.bh - 1) / g.bh) * g.bits / 8;
+        rgb += s.hdr[YK_HD_PASS0 + p * YK_ST_STRIDE + YK_ST_RGBBYTES];
+    }
+    out[0] = bm; out[1] = rgb;
+    out[2] = 3ll * 16 * s.hdr[YK_HD_R2_CHUNKS]; out[3] = 3ll * 3 * s.hdr[YK_HD_R2_TILES];
+    out[4] = s.d.nPlanes == 4 ? ((long long)((w + 15) / 16) * ((h + 15) / 16) + 7) / 8 : 0;
+    out[5] = 0;
+    return YK_OK;
+}
+
+// ---- not built yet (declared so the boundary is complete; see DESIGN.md "status") --------------------------
+extern "C" int yk_range_dyn(yk_ctx*, int, int, int, uint8_t*, int, int*, uint16_t*, int, int*, int*, int32_t*) { return YK_ERR_UNSUPPORTED; }
+extern "C" int yk_strip_config(yk_ctx*, int, int, int) { return YK_ERR_UNSUPPORTED; }
+extern "C" int yk_strip_halo_ptrs(yk_ctx*, int, void**, size_t*, void**, void**, void**, size_t*) { return YK_ERR_UNSUPPORTED; }
+extern "C" int yk_strip_phase(yk_ctx*, int, int, int) { return YK_ERR_UNSUPPORTED; }

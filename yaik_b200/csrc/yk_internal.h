@@ -1,0 +1,93 @@
+// Internal declarations shared by the kernels (yk_kernels.cu) and the C-ABI layer (yk_api.cu).
+// Vocabulary follows the reference (KLab/YAIK): planes, tiles, swizzle blocks, passes, streams.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifndef YK_EMULATE
+#include <cuda_runtime.h>
+#define YK_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#define YK_NPASS 7
+#define YK_REGION 64            // one CTA analyses one 64x64 region = the largest swizzle block (YAIK_private.h:212-276)
+#define YK_THREADS 256
+
+// Swizzle geometry of pass id p (HeaderGradientTile::getSwizzleSize, include/YAIK_private.h:212-276),
+// in Convert()'s order (EC.cpp:9057-9093): 16x16 16x8 8x16 8x8 8x4 4x8 4x4.
+struct YkPassGeom { int shx, shy, bw, bh, bits; };
+#define YK_PASS_TABLE { {4,4,64,64,16}, {4,3,64,64,32}, {3,4,64,64,32}, {3,3,64,64,64}, {3,2,64,32,64}, {2,3,32,64,64}, {2,2,32,32,64} }
+
+// per-pass counters written by the analysis kernels (ints)
+enum { YK_ST_TILEDONE = 0, YK_ST_MINX, YK_ST_MINY, YK_ST_MAXX, YK_ST_MAXY, YK_ST_RGBBYTES, YK_ST_PAD0, YK_ST_PAD1, YK_ST_STRIDE };
+// per-slot header ints (device memory, zeroed/initialised before each run)
+enum {
+    YK_HD_ERR = 0,                 // bit0: sample outside 0..255
+    YK_HD_ALPHA_MINX, YK_HD_ALPHA_MINY, YK_HD_ALPHA_MAXX, YK_HD_ALPHA_MAXY, YK_HD_ALPHA_KEPT,
+    YK_HD_R2_CHUNKS, YK_HD_R2_TILES,        // totals from the scan: 16-byte chunks per plane, coded tiles per plane
+    YK_HD_R1_NIB0, YK_HD_R1_NIB1, YK_HD_R1_NIB2, YK_HD_R1_DEF0, YK_HD_R1_DEF1, YK_HD_R1_DEF2,
+    YK_HD_PASS0 = 16,              // YK_NPASS * YK_ST_STRIDE ints
+    YK_HD_INTS = YK_HD_PASS0 + YK_NPASS * YK_ST_STRIDE
+};
+
+// Device-visible description of one slot (one image + all results of its analysis).
+struct YkSlotDev {
+    const int32_t* plane[4];    // int32 row-major planes, pitch == w (Plane::GetPixels(), framework.h:81)
+    const int32_t* rowBelow[3]; // strip mode: the pixel row under the strip (3 x w int32), else NULL
+    int w, h, nPlanes;
+    int nbx, nby;               // 64x64 regions
+    int imgH, y0;               // strip mode: height of the whole image / first row of this strip (else h, 0)
+    int latW, latH;             // lattice of 4-pixel points: w/4+1, h/4+1
+    int cornerWords;            // u32 words per lattice row of the corner masks
+    // ---- compact state (replaces the reference's int32 state planes, EncoderContext.h:300-323)
+    uint16_t* cellMask;         // [h/4][nbx]   bit i = 4x4 cell (16*bx+i) claimed   == smoothMap / mapSmoothTile != 0
+    uint32_t* cornerMask;       // [latH][cornerWords] lattice point claimed          == mappedRGB != 0
+    uint32_t* cornerNew;        // same shape, claims made by the running launch
+    uint8_t*  alphaKept;        // [ceil(h/16)][ceil(w/16)] 1 = tile has a non-zero alpha sample
+    int*      hdr;              // YK_HD_INTS ints
+    // ---- gradient results
+    uint8_t*  bitmap[YK_NPASS];     // pFillBitMap in the reference's swizzled layout
+    uint8_t*  emitMask[YK_NPASS];   // per tile, indexed by stream position: which of TL,TR,BL,BR it emits
+    int*      unitOff[YK_NPASS];    // per swizzle block: rgb byte count, then (after the scan) exclusive offset
+    uint8_t*  rgb[YK_NPASS];        // rgbStream
+    uint8_t*  latRGB;               // [latH][latW][3]  CompressF(Round6(clamped pixel),250) at every lattice point
+    // ---- range stage R2 (DynamicTileCompressor)
+    int*      r2Seg;            // [h/8][nbx] per (tile row, region): chunks | codedTiles<<16, then exclusive offsets
+    int*      r2SegTiles;       // exclusive offsets of coded tiles
+    uint8_t*  r2Idx[3];
+    uint8_t*  r2Type[3];
+    // ---- range stage R1 (DynamicTileEncode)
+    int*      r1Cnt;            // [ (h/8+1) * (w/8) ] valid pixels per block in LeftRightOrder, then exclusive offsets
+    int*      r1Def;            // exclusive offsets of emitted tile defs
+    uint32_t* r1Nib[3];         // nibble stream as zeroed u32 words
+    uint16_t* r1Defs[3];
+    int32_t*  r1Dst;            // optional w*h int32 (one plane at a time)
+    int       alphaReset;       // set by the host after the alpha stage: bbox == full image -> mask all 255 (EC.cpp:1400-1403)
+    int       alphaValid;       // alpha stage has been run for this image
+};
+
+struct YkRun {
+    int nPasses;
+    int passId[YK_NPASS];       // which passes this launch runs, in order
+    int rejectFactor;
+    int doAlpha;
+};
+
+#ifdef __cplusplus
+extern "C++" {
+#endif
+// launch wrappers (yk_kernels.cu); `slots` is a device array, grid.y indexes it from slot0
+void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st);
+void yk_launch_emit_count(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st);
+void yk_launch_scan(const YkSlotDev* slotsDev, int slot0, int nSlots, const YkRun& run, cudaStream_t st);
+void yk_launch_emit_write(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st);
+void yk_launch_range1d(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, cudaStream_t st);
+void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t* smoothMap, int32_t* mipmapMask,
+                     int32_t* mappedRGB, int32_t* recon0, int32_t* recon1, int32_t* recon2, cudaStream_t st);
+void yk_launch_range_dyn_count(const YkSlotDev* slotsDev, int slot, int cx, int cy, int cw, int ch, int nBlocks, cudaStream_t st);
+void yk_launch_range_dyn_scan(const YkSlotDev* slotsDev, int slot, int nBlocks, int plane, cudaStream_t st);
+void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, int plane, int mode3, int cx, int cy, int cw, int ch,
+                                int nBlocks, const int* lutDev, cudaStream_t st);
+#ifdef __cplusplus
+}
+#endif
