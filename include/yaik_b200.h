@@ -144,6 +144,12 @@ int  yk_result_bytes(yk_ctx* ctx, int slot, long long out[6]);
 /* Number of kernel launches enqueued by this context since creation. */
 long long yk_launch_count(yk_ctx* ctx);
 
+/* Per-kernel device time: while enabled, every launch is bracketed by a CUDA event pair on the launching stream;
+ * yk_profile_read synchronises, sums the elapsed milliseconds per kernel (0 analyze, 1 emit_count, 2 scan,
+ * 3 emit_write, 4 range1d) with their launch counts, and clears the record.  Used by bench.py's roofline figure. */
+int  yk_profile(yk_ctx* ctx, int enable);
+int  yk_profile_read(yk_ctx* ctx, double ms[8], long long count[8]);
+
 /* ---- multi-GPU: tile-row strips of one large image ------------------------------------
  * A strip context holds rows [y0, y0+h) of an image of height imgH (h a multiple of 64 except for the last
  * strip).  It needs (i) one pixel row below the strip (the clamped bottom corners of its last tile row) and

@@ -159,6 +159,10 @@ static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new yk_emu_event{0}; return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 #define cudaStreamNonBlocking 1
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 8
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }

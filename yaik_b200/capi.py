@@ -24,6 +24,7 @@ EXPORTS = [
     "yk_set_stream", "yk_sync", "yk_host_alloc", "yk_host_free", "yk_set_image", "yk_set_image_device",
     "yk_device_plane", "yk_reset_state", "yk_analyze", "yk_alpha_reject", "yk_prepare_quad_smooth",
     "yk_gradient_pass", "yk_range1d", "yk_range_dyn", "yk_download_state", "yk_result_bytes", "yk_launch_count",
+    "yk_profile", "yk_profile_read",
     "yk_strip_config", "yk_strip_halo_ptrs", "yk_strip_phase",
 ]
 

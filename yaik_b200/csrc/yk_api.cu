@@ -60,6 +60,21 @@ struct yk_ctx {
     int* lutDev = nullptr;       // R1 tables
     long long launches = 0;
     size_t planeCap = 0;
+    // optional per-kernel timing with CUDA events on the launching stream (yk_profile)
+    bool profile = false;
+    std::vector<cudaEvent_t> evA[5], evB[5];
+};
+
+struct YkTimed {        // records an event pair around one launch when profiling is on
+    yk_ctx* c; int k;
+    YkTimed(yk_ctx* c_, int k_) : c(c_), k(k_) {
+        if (c->profile && c->evA[k].size() < 100000) {
+            cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+            c->evA[k].push_back(a); c->evB[k].push_back(b);
+            cudaEventRecord(a, c->stream);
+        } else k = -1;
+    }
+    ~YkTimed() { if (k >= 0) cudaEventRecord(c->evB[k].back(), c->stream); }
 };
 
 extern "C" int yk_abi_version(void) { return 1; }
@@ -185,6 +200,27 @@ extern "C" int yk_sync(yk_ctx* c) {
 }
 extern "C" long long yk_launch_count(yk_ctx* c) { return c ? c->launches : 0; }
 
+extern "C" int yk_profile(yk_ctx* c, int enable) {
+    if (!c) return YK_ERR_ARG;
+    c->profile = enable != 0;
+    return YK_OK;
+}
+extern "C" int yk_profile_read(yk_ctx* c, double ms[8], long long count[8]) {
+    if (!c || !ms || !count) return YK_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 8; k++) { ms[k] = 0; count[k] = 0; }
+    for (int k = 0; k < 5; k++) {
+        for (size_t i = 0; i < c->evA[k].size(); i++) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, c->evA[k][i], c->evB[k][i]) == cudaSuccess) { ms[k] += t; count[k]++; }
+            cudaEventDestroy(c->evA[k][i]); cudaEventDestroy(c->evB[k][i]);
+        }
+        c->evA[k].clear(); c->evB[k].clear();
+    }
+    return YK_OK;
+}
+
 static int slot_ok(yk_ctx* c, int slot) { return c && slot >= 0 && slot < c->maxSlots; }
 
 static int configure_slot(yk_ctx* c, int slot, int nPlanes, int w, int h) {
@@ -197,7 +233,7 @@ static int configure_slot(yk_ctx* c, int slot, int nPlanes, int w, int h) {
     s.d.latW = w / 4 + 1; s.d.latH = h / 4 + 1;
     s.d.cornerWords = (s.d.latW + 31) / 32 + 1;
     for (int p = 0; p < 3; p++) s.d.rowBelow[p] = nullptr;
-    s.haveImage = true;
+    s.haveImage = true; s.dirty = true;
     return YK_OK;
 }
 
@@ -208,9 +244,10 @@ extern "C" int yk_reset_state(yk_ctx* c, int slot) {
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(s.d.cellMask, 0, (size_t)(s.d.h / 4 + 1) * s.d.nbx * sizeof(uint16_t), c->stream));
     CK(cudaMemsetAsync(s.d.cornerMask, 0, (size_t)s.d.latH * s.d.cornerWords * 4, c->stream));
+    if (s.d.alphaReset || s.d.alphaValid) s.dirty = true;
     s.d.alphaReset = 0; s.d.alphaValid = 0;
     s.k1Ran = s.alphaRan = s.alphaFetched = s.prepared = s.r2Valid = s.pendingHarvest = false;
-    s.nextPass = 0; s.dirty = true; s.rangeErr = 0; s.lastRunPasses = 0;
+    s.nextPass = 0; s.rangeErr = 0; s.lastRunPasses = 0;
     memset(s.hdr, 0, sizeof s.hdr);
     return YK_OK;
 }
@@ -300,11 +337,11 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
         if (c->slots[i].pendingHarvest) { rc = fetch_hdr(c, c->slots[i]); if (rc && rc != YK_ERR_RANGE) return rc; }
     CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * slot0, 0, c->zeroStride * nSlots, c->stream));
     if ((rc = upload_slots(c, slot0, nSlots))) return rc;
-    yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++;
-    if (doEmit && run.nPasses > 0) { yk_launch_emit_count(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
-    yk_launch_scan(c->slotsDev, slot0, nSlots, run, c->stream); c->launches++;
-    if (doEmit && run.nPasses > 0) { yk_launch_emit_write(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
-    if (doR2) { yk_launch_range1d(c->slotsDev, slot0, nSlots, nRegions, c->stream); c->launches++; }
+    { YkTimed t(c, 0); yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
+    if (doEmit && run.nPasses > 0) { YkTimed t(c, 1); yk_launch_emit_count(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
+    { YkTimed t(c, 2); yk_launch_scan(c->slotsDev, slot0, nSlots, run, c->stream); c->launches++; }
+    if (doEmit && run.nPasses > 0) { YkTimed t(c, 3); yk_launch_emit_write(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
+    if (doR2) { YkTimed t(c, 4); yk_launch_range1d(c->slotsDev, slot0, nSlots, nRegions, c->stream); c->launches++; }
     CK(cudaGetLastError());
     for (int i = slot0; i < slot0 + nSlots; i++) {
         YkSlotHost& s = c->slots[i];
