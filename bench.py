@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prewarm", action="store_true", help="skip the clock-settling loop (profiling runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -219,7 +220,7 @@ def main():
         ctx.sync()
         t0 = time.perf_counter()
         i = 0
-        while time.perf_counter() - t0 < 0.3:
+        while not args.no_prewarm and time.perf_counter() - t0 < 0.3:
             for _ in range(50):
                 step(i); i += 1
             ctx.sync()

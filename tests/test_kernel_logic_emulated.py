@@ -21,14 +21,13 @@ def emu_lib():
     return capi.load_library(EMU)
 
 
-EMU_CASES = ["ramp64_a2", "patchy_72x40", "patchy128", "mip32_rgba", "mip16_rgba", "mip8_rgb", "mip4_rgb",
+EMU_CASES = ["synth256_rgb_3bit", "alpha_island256", "ramp64_a2", "patchy_72x40", "patchy128", "mip32_rgba", "mip16_rgba", "mip8_rgb", "mip4_rgb",
              "alpha_island128", "alpha_corner_only", "noise_delta1", "noise_hi", "flat64"]
 
 
 @pytest.mark.parametrize("name", EMU_CASES)
 def test_emulated_kernels_match_oracle(emu_lib, name):
     planes, stages = cases.SMALL_CASES[name]()
-    stages = tuple(s for s in stages if not s.startswith("r1"))
     ctx = capi.Context(256, 256, planes=4, slots=1, lib=emu_lib)
     try:
         check_image(ctx, planes, stages, fused=True)

@@ -499,6 +499,95 @@ extern "C" int yk_range1d(yk_ctx* c, int slot, int plane, uint8_t* idx, int idxC
     return YK_OK;
 }
 
+
+// ---- range R1 ---------------------------------------------------------------------------------------------
+// Six LUTs per (base6, range7) pair, built on the host with the reference's own float expression and glibc powf
+// (DynamicTile::buildTable, EC.cpp:625-699; SURVEY.md hazard 12).  range7 can exceed 7 bits for bases close to 224
+// (a reference quirk: EncodeTileType then spills into the type bits) — the table simply covers it.
+#define YK_R1_R7MAX 176
+static int ensure_r1_lut(yk_ctx* c) {
+    if (c->lutDev) return YK_OK;
+    std::vector<int> lut((size_t)64 * YK_R1_R7MAX * 72, 0);
+    for (int b6 = 0; b6 < 64; b6++) {
+        const int BN = (b6 * 224) / 63, scale = 223 - BN;
+        for (int r7 = 0; r7 < YK_R1_R7MAX; r7++) {
+            const int D = (r7 * scale) / 127 + 32;                 // DiffRangeDecode, EC.cpp:620-623
+            const float DistNormF = (float)D;
+            int* T = &lut[((size_t)b6 * YK_R1_R7MAX + r7) * 72];
+            for (int input = 0; input < 16; input++) {              // EC.cpp:662-677
+                float pos = input / 15.0f;
+                float ExpNormV = powf(pos, 1.4f), LogNormV = 1.0f - powf((1.0f - pos), 1.4f);
+                float outLinear = pos * DistNormF, outExp = ExpNormV * DistNormF, outLog = LogNormV * DistNormF;
+                T[input] = (int)(BN + outLinear); T[16 + input] = (int)(BN + outExp); T[32 + input] = (int)(BN + outLog);
+            }
+            for (int input = 0; input < 8; input++) {               // EC.cpp:680-696
+                float pos = input / 7.0f;
+                float ExpNormV = powf(pos, 1.4f), LogNormV = 1.0f - powf((1.0f - pos), 1.4f);
+                float outLinear = pos * DistNormF, outExp = ExpNormV * DistNormF, outLog = LogNormV * DistNormF;
+                T[48 + input] = (int)(BN + outLinear); T[56 + input] = (int)(BN + outExp); T[64 + input] = (int)(BN + outLog);
+            }
+        }
+    }
+    CK(cudaMalloc((void**)&c->lutDev, lut.size() * sizeof(int)));
+    CK(cudaMemcpy(c->lutDev, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return YK_OK;
+}
+
+extern "C" int yk_range_dyn(yk_ctx* c, int slot, int plane, int mode3BitOnly, uint8_t* nibbles, int nibCap, int* nNibbles,
+                            uint16_t* defs, int defsCap, int* nDefs, int constraint[4], int32_t* dst) {
+    if (!slot_ok(c, slot) || plane < 0 || plane > 2) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    const int w = s.d.w, h = s.d.h;
+    if ((w & 7) || (h & 7)) return YK_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_r1_lut(c))) return rc;
+    int bound[4] = { 0, 0, w, h };                               // CheckMipmapMask: full image (EC.cpp:2784-2794)
+    if (s.alphaRan) { if ((rc = alpha_finish(c, s))) return rc; memcpy(bound, s.bound, sizeof bound); }
+    const int cx = (bound[0] >> 3) << 3, cy = (bound[1] >> 3) << 3;              // EC.cpp:4386-4391
+    const int cw = (((bound[2] + 7) >> 3) << 3) - cx, ch = (((bound[3] + 7) >> 3) << 3) - cy;
+    if (constraint) { constraint[0] = cx; constraint[1] = cy; constraint[2] = cw; constraint[3] = ch; }
+    const int nBlocks = (cw >> 3) * (ch >> 3);
+    if (s.pendingHarvest) { rc = fetch_hdr(c, s); if (rc && rc != YK_ERR_RANGE) return rc; }
+    int32_t* dDst = nullptr;
+    if (dst) {
+        CK(cudaMalloc((void**)&dDst, (size_t)w * h * 4));
+        CK(cudaMemcpyAsync(dDst, dst, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    s.d.r1Dst = dDst; s.dirty = true;
+    if ((rc = upload_slots(c, slot, 1))) return rc;
+    const size_t nibWords = (size_t)(w / 8) * (h / 8) * 8 + 4;
+    CK(cudaMemsetAsync(s.d.r1Nib[plane], 0, nibWords * 4, c->stream));
+    if (nBlocks > 0) {
+        yk_launch_range_dyn_count(c->slotsDev, slot, cx, cy, cw, ch, nBlocks, c->stream);
+        yk_launch_range_dyn_scan(c->slotsDev, slot, nBlocks, plane, c->stream);
+        yk_launch_range_dyn_encode(c->slotsDev, slot, plane, mode3BitOnly ? 1 : 0, cx, cy, cw, ch, nBlocks, c->lutDev, c->stream);
+        c->launches += 3;
+    }
+    CK(cudaGetLastError());
+    int tot[2] = { 0, 0 };
+    if (nBlocks > 0) {
+        CK(cudaMemcpyAsync(&tot[0], s.d.hdr + YK_HD_R1_NIB0 + plane, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&tot[1], s.d.hdr + YK_HD_R1_DEF0 + plane, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    const int nb = (tot[0] + 1) / 2;
+    rc = YK_OK;
+    if (nb > nibCap || tot[1] > defsCap) rc = YK_ERR_CAPACITY;
+    if (!rc) {
+        if (nibbles && nb) CK(cudaMemcpyAsync(nibbles, s.d.r1Nib[plane], nb, cudaMemcpyDeviceToHost, c->stream));
+        if (defs && tot[1]) CK(cudaMemcpyAsync(defs, s.d.r1Defs[plane], (size_t)tot[1] * 2, cudaMemcpyDeviceToHost, c->stream));
+        if (dst) CK(cudaMemcpyAsync(dst, dDst, (size_t)w * h * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    if (dDst) cudaFree(dDst);
+    s.d.r1Dst = nullptr; s.dirty = true;
+    if (nNibbles) *nNibbles = tot[0];
+    if (nDefs) *nDefs = tot[1];
+    return rc;
+}
+
 // ---- compat state download --------------------------------------------------------------------------------
 extern "C" int yk_download_state(yk_ctx* c, int slot, int32_t* smoothMap, int32_t* const* mapSmoothTile,
                                  int32_t* const* mappedRGB, int32_t* mipmapMask, int32_t* const* recon) {
@@ -550,7 +639,6 @@ extern "C" int yk_result_bytes(yk_ctx* c, int slot, long long out[6]) {
 }
 
 // ---- not built yet (declared so the boundary is complete; see DESIGN.md "status") --------------------------
-extern "C" int yk_range_dyn(yk_ctx*, int, int, int, uint8_t*, int, int*, uint16_t*, int, int*, int*, int32_t*) { return YK_ERR_UNSUPPORTED; }
 extern "C" int yk_strip_config(yk_ctx*, int, int, int) { return YK_ERR_UNSUPPORTED; }
 extern "C" int yk_strip_halo_ptrs(yk_ctx*, int, void**, size_t*, void**, void**, void**, size_t*) { return YK_ERR_UNSUPPORTED; }
 extern "C" int yk_strip_phase(yk_ctx*, int, int, int) { return YK_ERR_UNSUPPORTED; }
