@@ -107,6 +107,11 @@ static inline int __reduce_add_sync(unsigned m, int v) { yk_emu_fullmask(m); ret
 static inline unsigned __reduce_add_sync(unsigned m, unsigned v) { yk_emu_fullmask(m); return (unsigned)yk_emu::collect(v, [](unsigned long long* s) { unsigned long long r = 0; for (int i = 0; i < 32; i++) r += s[i]; return r; }); }
 static inline unsigned __reduce_or_sync(unsigned m, unsigned v) { yk_emu_fullmask(m); return (unsigned)yk_emu::collect(v, [](unsigned long long* s) { unsigned long long r = 0; for (int i = 0; i < 32; i++) r |= s[i]; return r; }); }
 
+static inline unsigned __match_any_sync(unsigned m, int v) {
+    yk_emu_fullmask(m);
+    return (unsigned)yk_emu::collect((unsigned long long)(unsigned)v, [v](unsigned long long* s) { unsigned r = 0; for (int i = 0; i < 32; i++) if ((unsigned)s[i] == (unsigned)v) r |= 1u << i; return (unsigned long long)r; });
+}
+static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }

@@ -40,6 +40,8 @@ struct YkSlotHost {
     bool prepared = false;       // fused 7-pass cascade results present
     int  preparedReject = 0, nextPass = 0;
     bool r2Valid = false;
+    bool zeroAClean = false;     // part A of the zero area is still all zero (nothing launched since the reset)
+    bool touchDirty = false;     // the touch map holds claims of an earlier launch (needs folding before the next one)
     bool pendingHarvest = false; // a run's header has not been copied back yet
     int  lastRunPasses = 0;      // bit p: pass p was in the last run; bit 8: alpha
     int  rangeErr = 0;
@@ -56,7 +58,9 @@ struct yk_ctx {
     cudaStream_t stream = 0; bool ownStream = false;
     YkSlotDev* slotsDev = nullptr;
     std::vector<YkSlotHost> slots;
-    uint8_t* zeroArea = nullptr; size_t zeroStride = 0;
+    // per slot one contiguous zeroable area: part A (header, look-back status words) is cleared before every launch,
+    // part B (claimed cells, touch map = the persistent analysis state) only by yk_reset_state
+    uint8_t* zeroArea = nullptr; size_t zeroStride = 0, zeroABytes = 0;
     int* lutDev = nullptr;       // R1 tables
     long long launches = 0;
     size_t planeCap = 0;
@@ -130,33 +134,41 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
     c->ownStream = true;
     CK(cudaMalloc((void**)&c->slotsDev, sizeof(YkSlotDev) * maxSlots));
     const size_t W = maxW, H = maxH;
-    const size_t nbx = (W + 63) / 64, latW = W / 4 + 1, latH = H / 4 + 1, cw = (latW + 31) / 32 + 1;
+    const size_t nbx = (W + 63) / 64, latW = W / 4 + 1, latH = H / 4 + 1;
     c->planeCap = W * H;
-    // zero area per slot: header ints + cornerNew
-    c->zeroStride = ((YK_HD_INTS * sizeof(int) + latH * cw * 4 + 255) / 256) * 256;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    size_t offStatus[YK_NPASS], off = up(YK_HD_INTS * sizeof(int));
+    for (int p = 0; p < YK_NPASS; p++) {
+        const YkPassGeom& g = kGeom[p];
+        offStatus[p] = off;
+        off += up(((W + g.bw - 1) / g.bw) * ((H + g.bh - 1) / g.bh) * sizeof(uint32_t));
+    }
+    const size_t offR2 = off; off += up((H / 8 + 1) * nbx * sizeof(unsigned long long));
+    c->zeroABytes = off;
+    const size_t offCell = off; off += up((H / 4 + 1) * nbx * sizeof(uint16_t));
+    const size_t offTouch = off; off += up(latW * latH * sizeof(uint32_t));
+    c->zeroStride = off;
     CK(cudaMalloc((void**)&c->zeroArea, c->zeroStride * maxSlots));
     CK(cudaMemset(c->zeroArea, 0, c->zeroStride * maxSlots));
     for (int i = 0; i < maxSlots; i++) {
         YkSlotHost& s = c->slots[i];
         memset(&s.d, 0, sizeof s.d);
         int rc;
+        uint8_t* za = c->zeroArea + c->zeroStride * i;
         for (int p = 0; p < maxPlanes; p++) if ((rc = dev_alloc(s, &s.owned[p], W * H))) return rc;
-        if ((rc = dev_alloc(s, &s.d.cellMask, (H / 4 + 1) * nbx))) return rc;
-        if ((rc = dev_alloc(s, &s.d.cornerMask, latH * cw))) return rc;
-        s.d.hdr = (int*)(c->zeroArea + c->zeroStride * i);
-        s.d.cornerNew = (uint32_t*)(c->zeroArea + c->zeroStride * i + YK_HD_INTS * sizeof(int));
+        s.d.hdr = (int*)za;
+        for (int p = 0; p < YK_NPASS; p++) s.d.emitStatus[p] = (uint32_t*)(za + offStatus[p]);
+        s.d.r2Status = (unsigned long long*)(za + offR2);
+        s.d.cellMask = (uint16_t*)(za + offCell);
+        s.d.touchMap = (uint32_t*)(za + offTouch);
         if ((rc = dev_alloc(s, &s.d.alphaKept, ((H + 15) / 16) * ((W + 15) / 16)))) return rc;
         for (int p = 0; p < YK_NPASS; p++) {
             const YkPassGeom& g = kGeom[p];
             size_t nu = ((W + g.bw - 1) / g.bw) * ((H + g.bh - 1) / g.bh);
             if ((rc = dev_alloc(s, &s.d.bitmap[p], nu * g.bits / 8))) return rc;
-            if ((rc = dev_alloc(s, &s.d.emitMask[p], nu * g.bits))) return rc;
-            if ((rc = dev_alloc(s, &s.d.unitOff[p], nu))) return rc;
             if ((rc = dev_alloc(s, &s.d.rgb[p], 3 * ((W >> g.shx) + 1) * ((H >> g.shy) + 1)))) return rc;
         }
         if ((rc = dev_alloc(s, &s.d.latRGB, latW * latH * 3))) return rc;
-        if ((rc = dev_alloc(s, &s.d.r2Seg, (H / 8 + 1) * nbx))) return rc;
-        if ((rc = dev_alloc(s, &s.d.r2SegTiles, (H / 8 + 1) * nbx))) return rc;
         for (int p = 0; p < 3; p++) {
             if ((rc = dev_alloc(s, &s.d.r2Idx[p], W * H))) return rc;
             if ((rc = dev_alloc(s, &s.d.r2Type[p], 3 * (W / 8 + 1) * (H / 8 + 1)))) return rc;
@@ -231,7 +243,6 @@ static int configure_slot(yk_ctx* c, int slot, int nPlanes, int w, int h) {
     s.d.nbx = (w + 63) / 64; s.d.nby = (h + 63) / 64;
     s.d.imgH = h; s.d.y0 = 0;
     s.d.latW = w / 4 + 1; s.d.latH = h / 4 + 1;
-    s.d.cornerWords = (s.d.latW + 31) / 32 + 1;
     for (int p = 0; p < 3; p++) s.d.rowBelow[p] = nullptr;
     s.haveImage = true; s.dirty = true;
     return YK_OK;
@@ -242,8 +253,8 @@ extern "C" int yk_reset_state(yk_ctx* c, int slot) {
     YkSlotHost& s = c->slots[slot];
     if (!s.haveImage) return YK_ERR_STATE;
     CK(cudaSetDevice(c->device));
-    CK(cudaMemsetAsync(s.d.cellMask, 0, (size_t)(s.d.h / 4 + 1) * s.d.nbx * sizeof(uint16_t), c->stream));
-    CK(cudaMemsetAsync(s.d.cornerMask, 0, (size_t)s.d.latH * s.d.cornerWords * 4, c->stream));
+    CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * slot, 0, c->zeroStride, c->stream));
+    s.zeroAClean = true; s.touchDirty = false;
     if (s.d.alphaReset || s.d.alphaValid) s.dirty = true;
     s.d.alphaReset = 0; s.d.alphaValid = 0;
     s.k1Ran = s.alphaRan = s.alphaFetched = s.prepared = s.r2Valid = s.pendingHarvest = false;
@@ -335,20 +346,32 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     const int nRegions = a.d.nbx * a.d.nby;
     for (int i = slot0; i < slot0 + nSlots; i++)            // the header is about to be cleared: keep the previous run's numbers
         if (c->slots[i].pendingHarvest) { rc = fetch_hdr(c, c->slots[i]); if (rc && rc != YK_ERR_RANGE) return rc; }
-    CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * slot0, 0, c->zeroStride * nSlots, c->stream));
+    bool needFold = false;
+    for (int i = slot0; i < slot0 + nSlots; i++) {
+        YkSlotHost& s = c->slots[i];
+        if (!s.zeroAClean) CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * i, 0, c->zeroABytes, c->stream));
+        s.zeroAClean = false;
+        if (s.touchDirty && run.nPasses > 0) needFold = true;
+    }
     if ((rc = upload_slots(c, slot0, nSlots))) return rc;
-    { YkTimed t(c, 0); yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
-    if (doEmit && run.nPasses > 0) { YkTimed t(c, 1); yk_launch_emit_count(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
-    { YkTimed t(c, 2); yk_launch_scan(c->slotsDev, slot0, nSlots, run, c->stream); c->launches++; }
-    if (doEmit && run.nPasses > 0) { YkTimed t(c, 3); yk_launch_emit_write(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
-    if (doR2) { YkTimed t(c, 4); yk_launch_range1d(c->slotsDev, slot0, nSlots, nRegions, c->stream); c->launches++; }
+    if (needFold) { yk_launch_fold_touch(c->slotsDev, slot0, nSlots, a.d.latW * a.d.latH, c->stream); c->launches++; }
+    if (run.nPasses > 0 || run.doAlpha) { YkTimed t(c, 0); yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
+    if (doEmit && run.nPasses > 0) {
+        int totalUnits = 0;
+        for (int p = 0; p < run.nPasses; p++) {
+            const YkPassGeom& g = kGeom[run.passId[p]];
+            totalUnits += ((a.d.w + g.bw - 1) / g.bw) * ((a.d.h + g.bh - 1) / g.bh);
+        }
+        YkTimed t(c, 1); yk_launch_emit(c->slotsDev, slot0, nSlots, totalUnits, run, c->stream); c->launches++;
+    }
+    if (doR2) { YkTimed t(c, 4); yk_launch_range1d(c->slotsDev, slot0, nSlots, (a.d.h / 8) * a.d.nbx, c->stream); c->launches++; }
     CK(cudaGetLastError());
     for (int i = slot0; i < slot0 + nSlots; i++) {
         YkSlotHost& s = c->slots[i];
         s.k1Ran = true; s.pendingHarvest = true; s.lastRunPasses = (run.doAlpha ? 256 : 0);
         for (int p = 0; p < run.nPasses; p++) s.lastRunPasses |= 1 << run.passId[p];
         if (run.doAlpha && s.d.nPlanes == 4) { s.alphaRan = true; s.alphaFetched = false; }
-        if (run.nPasses > 0) s.r2Valid = false;
+        if (run.nPasses > 0) { s.r2Valid = false; s.touchDirty = true; }
         if (doR2) s.r2Valid = true;
     }
     return YK_OK;

@@ -26,6 +26,7 @@ enum {
     YK_HD_ALPHA_MINX, YK_HD_ALPHA_MINY, YK_HD_ALPHA_MAXX, YK_HD_ALPHA_MAXY, YK_HD_ALPHA_KEPT,
     YK_HD_R2_CHUNKS, YK_HD_R2_TILES,        // totals from the scan: 16-byte chunks per plane, coded tiles per plane
     YK_HD_R1_NIB0, YK_HD_R1_NIB1, YK_HD_R1_NIB2, YK_HD_R1_DEF0, YK_HD_R1_DEF1, YK_HD_R1_DEF2,
+    YK_HD_TICKET_EMIT, YK_HD_TICKET_R2,     // work tickets of the look-back kernels (stream order = ticket order)
     YK_HD_PASS0 = 16,              // YK_NPASS * YK_ST_STRIDE ints
     YK_HD_INTS = YK_HD_PASS0 + YK_NPASS * YK_ST_STRIDE
 };
@@ -38,22 +39,20 @@ struct YkSlotDev {
     int nbx, nby;               // 64x64 regions
     int imgH, y0;               // strip mode: height of the whole image / first row of this strip (else h, 0)
     int latW, latH;             // lattice of 4-pixel points: w/4+1, h/4+1
-    int cornerWords;            // u32 words per lattice row of the corner masks
     // ---- compact state (replaces the reference's int32 state planes, EncoderContext.h:300-323)
     uint16_t* cellMask;         // [h/4][nbx]   bit i = 4x4 cell (16*bx+i) claimed   == smoothMap / mapSmoothTile != 0
-    uint32_t* cornerMask;       // [latH][cornerWords] lattice point claimed          == mappedRGB != 0
-    uint32_t* cornerNew;        // same shape, claims made by the running launch
+    uint32_t* touchMap;         // [latH][latW] per lattice point: bit 4*rp+k = in pass position rp of the running launch an
+                                //   accepted tile has this point as corner k (0 TL,1 TR,2 BL,3 BR); bit 31 = claimed by an
+                                //   earlier launch.  != 0  ==  mappedRGB != 0
     uint8_t*  alphaKept;        // [ceil(h/16)][ceil(w/16)] 1 = tile has a non-zero alpha sample
     int*      hdr;              // YK_HD_INTS ints
     // ---- gradient results
     uint8_t*  bitmap[YK_NPASS];     // pFillBitMap in the reference's swizzled layout
-    uint8_t*  emitMask[YK_NPASS];   // per tile, indexed by stream position: which of TL,TR,BL,BR it emits
-    int*      unitOff[YK_NPASS];    // per swizzle block: rgb byte count, then (after the scan) exclusive offset
+    uint32_t* emitStatus[YK_NPASS]; // per swizzle block: decoupled look-back word (rgb bytes << 2 | flag)
     uint8_t*  rgb[YK_NPASS];        // rgbStream
     uint8_t*  latRGB;               // [latH][latW][3]  CompressF(Round6(clamped pixel),250) at every lattice point
     // ---- range stage R2 (DynamicTileCompressor)
-    int*      r2Seg;            // [h/8][nbx] per (tile row, region): chunks | codedTiles<<16, then exclusive offsets
-    int*      r2SegTiles;       // exclusive offsets of coded tiles
+    unsigned long long* r2Status;   // [h/8][nbx] per 8-tile segment: look-back word (chunks << 32 | codedTiles << 2 | flag)
     uint8_t*  r2Idx[3];
     uint8_t*  r2Type[3];
     // ---- range stage R1 (DynamicTileEncode)
@@ -78,10 +77,9 @@ extern "C++" {
 #endif
 // launch wrappers (yk_kernels.cu); `slots` is a device array, grid.y indexes it from slot0
 void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st);
-void yk_launch_emit_count(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st);
-void yk_launch_scan(const YkSlotDev* slotsDev, int slot0, int nSlots, const YkRun& run, cudaStream_t st);
-void yk_launch_emit_write(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st);
-void yk_launch_range1d(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, cudaStream_t st);
+void yk_launch_fold_touch(const YkSlotDev* slotsDev, int slot0, int nSlots, int nWords, cudaStream_t st);
+void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int totalUnits, const YkRun& run, cudaStream_t st);
+void yk_launch_range1d(const YkSlotDev* slotsDev, int slot0, int nSlots, int nSegs, cudaStream_t st);
 void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t* smoothMap, int32_t* mipmapMask,
                      int32_t* mappedRGB, int32_t* recon0, int32_t* recon1, int32_t* recon2, cudaStream_t st);
 void yk_launch_range_dyn_count(const YkSlotDev* slotsDev, int slot, int cx, int cy, int cw, int ch, int nBlocks, cudaStream_t st);

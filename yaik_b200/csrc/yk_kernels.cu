@@ -8,11 +8,11 @@
 //                     by ballot; then the accept decision of all FittingQuadSmooth passes (EC.cpp:3810-3998)
 //                     of the region, pixels staged once in shared memory as packed bytes.  Accept decisions of
 //                     pass k depend only on earlier passes of the same region (tiles nest in 64x64).
-//   yk_k_emit_count   corner ownership (EC.cpp:4001-4021, 4115-4132): a lattice point is emitted by the
-//                     first pass that touches it, by the accepted tile with the smallest stream position.
-//   yk_k_scan         exclusive scans that turn per-swizzle-block byte counts into stream offsets.
-//   yk_k_emit_write   writes rgbStream in stream order.
-//   yk_k_range1d      DynamicTileCompressor (EC.cpp:8398-8522), one warp per 8x8 tile and plane.
+//                     One warp runs the whole 7-pass cascade of a 16x16 macro tile without block barriers.
+//   yk_k_emit         corner ownership + rgbStream (EC.cpp:4001-4021, 4115-4132): a lattice point is emitted by the
+//                     first pass that touches it, by the accepted tile with the smallest stream position; stream
+//                     offsets by decoupled look-back over swizzle blocks taken in stream order.
+//   yk_k_range1d      DynamicTileCompressor (EC.cpp:8398-8522), one warp per 8-tile segment, offsets by look-back.
 //   yk_k_state        expands the compact masks into the reference's int32 state planes (compat download).
 //   yk_k_r1_*         DynamicTileEncode (EC.cpp:4365-4503, 747-1212), LUT search at 3/4 bits per pixel.
 //
@@ -114,114 +114,102 @@ template <int FAM> static __device__ __forceinline__ int yk_family(int v) {
     return FAM == 0 ? v : (FAM == 1 ? yk_round6(v) : yk_round6p(v));
 }
 
-// One FittingQuadSmooth pass (tile 1<<SHX by 1<<SHY, swizzle block BW x BH) over the staged region.
-// Step 1: one thread per tile — eligibility (top-left cell unclaimed, EC.cpp:3871-3875; tile fully inside,
-//         EC.cpp:3818/3826) and a one-quad pre-test that can only prove rejection; survivors are compacted into sList.
-// Step 2: G = N/16 lanes per surviving tile evaluate 16 pixels each, family by family, voting after every quad.
+// One FittingQuadSmooth pass over one 16x16 macro tile, by one warp.  Every tile shape of the cascade nests inside an
+// aligned 16x16 macro tile, and eligibility (EC.cpp:3871-3875) only looks at cells of the same macro tile, so the whole
+// 7-pass cascade of a macro tile is independent of every other macro tile: no block barrier between passes.
+// The 32 lanes split into 32/NTM groups of G lanes, one group per tile of this shape; a lane evaluates 8 pixels
+// (two 4-pixel quads) per family and the group votes after every quad.  `claimed` (16 bits, bit = 4*cellY + cellX) is
+// warp-uniform and returned updated.
 template <int SHX, int SHY, int BW, int BH>
-static __device__ void yk_pass(const uint8_t (*pix)[65 * YK_RS], uint32_t* sCell, uint32_t* sBits, int* sStat,
-                               uint16_t* sList, int* sCount, int X0, int Y0, int w, int h, int yOrg, int R) {
-    constexpr int TW = 1 << SHX, TH = 1 << SHY, N = TW * TH, NX = 64 / TW, NY = 64 / TH, NT = NX * NY;
-    constexpr int G = N / 16, QR = TW / 4, BITS = (BW / TW) * (BH / TH);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int hiT = (2 * R + 1) * N;                    // exclusive upper bound of U for the truncated variant
-    const int loR = -(N / 2 - 1);                       // inclusive lower bound of U for the rounded variant
-    // a family's corners differ from the raw ones by -3..+4 (Round6: -3..+3, Round6P: -2..+4), so no variant can
-    // accept a pixel whose raw-family U is outside [loWide, hiWide)
+static __device__ __forceinline__ unsigned yk_macro_pass(const uint8_t (*pix)[65 * YK_RS], uint32_t* sBits, int* sStat, uint32_t* sTouch,
+                                                         int rp, int mlx, int mly, int X0, int Y0, int w, int h, int yOrg, int R, unsigned claimed) {
+    constexpr int TW = 1 << SHX, TH = 1 << SHY, N = TW * TH;
+    constexpr int NXM = 16 / TW, NTM = NXM * (16 / TH), G = 32 / NTM, QR = TW / 4, BITS = (BW / TW) * (BH / TH);
+    const int lane = threadIdx.x & 31;
+    const int t = lane / G, j = lane % G;
+    const int tx = t % NXM, ty = t / NXM;
+    const int lx0 = mlx + tx * TW, ly0 = mly + ty * TH;
+    const int cell = (ty * (TH / 4)) * 4 + tx * (TW / 4);
+    const bool active = !((claimed >> cell) & 1u) && (X0 + lx0 + TW <= w) && (Y0 + ly0 + TH <= h);   // EC.cpp:3818, 3826, 3871-3875
+    if (!__any_sync(YK_FULL, active)) return claimed;
+
+    const int hiT = (2 * R + 1) * N;                    // |cur - S/N| <= R            <=>  0 <= U < hiT
+    const int loR = -(N / 2 - 1);                       // |cur - (S+N/2-1)/N| <= R    <=>  loR <= U < hiT + loR
+    // a family's corners differ from the raw ones by -3..+4 (Round6: -3..+3, Round6P: -2..+4), so no variant can accept a
+    // pixel whose raw-family U is outside [loWide, hiWide): one failed quad of family 0 can reject the tile for good
     const int loWide = -(4 * N + N / 2 - 1), hiWide = hiT + 3 * N;
+    const unsigned gmask = (G == 32) ? YK_FULL : (((1u << (G & 31)) - 1u) << (t * G));
 
-    bool cand = false;
-    if (tid < NT) {
-        int lx0 = (tid % NX) * TW, ly0 = (tid / NX) * TH;
-        bool inside = (X0 + lx0 + TW <= w) && (Y0 + ly0 + TH <= h);
-        bool claimed = (sCell[ly0 >> 2] >> (lx0 >> 2)) & 1u;
-        if (inside && !claimed) {
-            int umin = INT_MAX, umax = INT_MIN;
-            constexpr int dx0 = 4 * (QR / 2), dy = TH / 2;
+    int cr[3][4];
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const uint8_t* p = pix[c];
-                int tl = p[ly0 * YK_RS + lx0], tr = p[ly0 * YK_RS + lx0 + TW];
-                int bl = p[(ly0 + TH) * YK_RS + lx0], br = p[(ly0 + TH) * YK_RS + lx0 + TW];
-                yk_quad<N>(p, (ly0 + dy) * YK_RS + lx0 + dx0, dx0, dy, tl * N + R * N, TH * (tr - tl), TW * (bl - tl), tl - tr - bl + br, umin, umax);
-            }
-            cand = !(umin < loWide || umax >= hiWide);
-        }
+    for (int c = 0; c < 3; c++) {                       // TL TR BL BR, clamped at the image edge by the staging (EC.cpp:3845-3868)
+        const uint8_t* p = pix[c];
+        cr[c][0] = p[ly0 * YK_RS + lx0]; cr[c][1] = p[ly0 * YK_RS + lx0 + TW];
+        cr[c][2] = p[(ly0 + TH) * YK_RS + lx0]; cr[c][3] = p[(ly0 + TH) * YK_RS + lx0 + TW];
     }
-    {
-        unsigned b = __ballot_sync(YK_FULL, cand);
-        int base = 0;
-        if (lane == 0 && b) base = atomicAdd(sCount, __popc(b));
-        base = __shfl_sync(YK_FULL, base, 0);
-        if (cand) sList[base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)tid;
-    }
-    __syncthreads();
-
-    const int nCand = *sCount;
-    constexpr int TPW = 32 / G;
-    const int j = lane % G, slot = lane / G;
-    const unsigned gmask = (G == 32) ? YK_FULL : (((1u << (G & 31)) - 1u) << (slot * G));
-    for (int base = warp * TPW; base < nCand; base += (YK_THREADS / 32) * TPW) {
-        const int ci = base + slot;
-        const bool active = ci < nCand;
-        const int t = active ? sList[ci] : 0;
-        const int lx0 = (t % NX) * TW, ly0 = (t / NX) * TH;
-        int cr[3][4];
+    bool accepted = false, resolved = !active;
+#pragma unroll
+    for (int fam = 0; fam < 3; fam++) {
+        int A3[3], B[3], C[3], D[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const uint8_t* p = pix[c];
-            cr[c][0] = p[ly0 * YK_RS + lx0]; cr[c][1] = p[ly0 * YK_RS + lx0 + TW];
-            cr[c][2] = p[(ly0 + TH) * YK_RS + lx0]; cr[c][3] = p[(ly0 + TH) * YK_RS + lx0 + TW];
+            int tl, tr, bl, br;
+            if (fam == 0) { tl = cr[c][0]; tr = cr[c][1]; bl = cr[c][2]; br = cr[c][3]; }
+            else if (fam == 1) { tl = yk_round6(cr[c][0]); tr = yk_round6(cr[c][1]); bl = yk_round6(cr[c][2]); br = yk_round6(cr[c][3]); }
+            else { tl = yk_round6p(cr[c][0]); tr = yk_round6p(cr[c][1]); bl = yk_round6p(cr[c][2]); br = yk_round6p(cr[c][3]); }
+            A3[c] = tl * N + R * N; B[c] = TH * (tr - tl); C[c] = TW * (bl - tl); D[c] = tl - tr - bl + br;
         }
-        bool accepted = false, resolved = !active;
+        int umin = INT_MAX, umax = INT_MIN;
+        bool famDead = false;
 #pragma unroll
-        for (int fam = 0; fam < 3; fam++) {
-            int A3[3], B[3], C[3], D[3];
+        for (int k = 0; k < 2; k++) {
+            const int q = j + G * k, dx0 = 4 * (q % QR), dy = q / QR;
+            if (!resolved && !famDead) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                int tl, tr, bl, br;
-                if (fam == 0) { tl = cr[c][0]; tr = cr[c][1]; bl = cr[c][2]; br = cr[c][3]; }
-                else if (fam == 1) { tl = yk_round6(cr[c][0]); tr = yk_round6(cr[c][1]); bl = yk_round6(cr[c][2]); br = yk_round6(cr[c][3]); }
-                else { tl = yk_round6p(cr[c][0]); tr = yk_round6p(cr[c][1]); bl = yk_round6p(cr[c][2]); br = yk_round6p(cr[c][3]); }
-                A3[c] = tl * N + R * N; B[c] = TH * (tr - tl); C[c] = TW * (bl - tl); D[c] = tl - tr - bl + br;
+                for (int c = 0; c < 3; c++)
+                    yk_quad<N>(pix[c], (ly0 + dy) * YK_RS + lx0 + dx0, dx0, dy, A3[c], B[c], C[c], D[c], umin, umax);
             }
-            int umin = INT_MAX, umax = INT_MIN;
-            bool famDead = false;
-            for (int k = 0; k < 4; k++) {
-                const int q = j + G * k, dx0 = 4 * (q % QR), dy = q / QR;
-                if (!resolved && !famDead) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++)
-                        yk_quad<N>(pix[c], (ly0 + dy) * YK_RS + lx0 + dx0, dx0, dy, A3[c], B[c], C[c], D[c], umin, umax);
-                }
-                const bool dT = (umin < 0) || (umax >= hiT);
-                const bool dR = (umin < loR) || (umax >= hiT + loR);
-                const unsigned bT = __ballot_sync(YK_FULL, dT), bR = __ballot_sync(YK_FULL, dR);
-                famDead = ((bT & gmask) != 0u) && ((bR & gmask) != 0u);
-                if (fam == 0) {
-                    const unsigned bH = __ballot_sync(YK_FULL, (umin < loWide) || (umax >= hiWide));
-                    if (bH & gmask) resolved = true;        // no family can accept this tile
-                }
-                if (!__any_sync(YK_FULL, !resolved && !famDead)) break;
+            const bool dT = (umin < 0) || (umax >= hiT);
+            const bool dR = (umin < loR) || (umax >= hiT + loR);
+            const unsigned bT = __ballot_sync(YK_FULL, dT), bR = __ballot_sync(YK_FULL, dR);
+            famDead = ((bT & gmask) != 0u) && ((bR & gmask) != 0u);
+            if (fam == 0) {
+                const unsigned bH = __ballot_sync(YK_FULL, (umin < loWide) || (umax >= hiWide));
+                if (bH & gmask) resolved = true;
             }
-            if (!resolved && !famDead) { accepted = true; resolved = true; }     // EC.cpp:3998: any surviving variant accepts
-            if (!__any_sync(YK_FULL, !resolved)) break;
+            if (k == 0 && !__any_sync(YK_FULL, !resolved && !famDead)) break;
         }
-        if (accepted && j == 0) {
-            const int sub = (ly0 / BH) * (64 / BW) + (lx0 / BW);
-            const int li = sub * BITS + ((ly0 % BH) / TH) * (BW / TW) + (lx0 % BW) / TW;
-            atomicOr(&sBits[li >> 5], 1u << (li & 31));                          // EC.cpp:4026
-#pragma unroll
-            for (int r = 0; r < TH / 4; r++)                                     // EC.cpp:4029-4037
-                atomicOr(&sCell[(ly0 >> 2) + r], ((1u << (TW / 4)) - 1u) << (lx0 >> 2));
-            atomicAdd(&sStat[YK_ST_TILEDONE], 1);                                // EC.cpp:4039-4044 (mins stored as extent - value)
-            atomicMax(&sStat[YK_ST_MINX], w - (X0 + lx0));
-            atomicMax(&sStat[YK_ST_MINY], INT_MAX / 2 - (yOrg + Y0 + ly0));
-            atomicMax(&sStat[YK_ST_MAXX], X0 + lx0 + TW);
-            atomicMax(&sStat[YK_ST_MAXY], yOrg + Y0 + ly0 + TH);
-        }
+        if (!resolved && !famDead) { accepted = true; resolved = true; }         // EC.cpp:3998: any surviving variant accepts
+        if (fam < 2 && !__any_sync(YK_FULL, !resolved)) break;
     }
-    __syncthreads();
+    const unsigned accB = __ballot_sync(YK_FULL, accepted && j == 0);
+    if (accB == 0u) return claimed;
+    if (accepted && j == 0) {
+        const int sub = (ly0 / BH) * (64 / BW) + (lx0 / BW);
+        const int li = sub * BITS + ((ly0 % BH) / TH) * (BW / TW) + (lx0 % BW) / TW;
+        atomicOr(&sBits[li >> 5], 1u << (li & 31));                              // EC.cpp:4026
+        atomicAdd(&sStat[YK_ST_TILEDONE], 1);                                    // EC.cpp:4039-4044 (mins stored as extent - value)
+        atomicMax(&sStat[YK_ST_MINX], w - (X0 + lx0));
+        atomicMax(&sStat[YK_ST_MINY], INT_MAX / 2 - (yOrg + Y0 + ly0));
+        atomicMax(&sStat[YK_ST_MAXX], X0 + lx0 + TW);
+        atomicMax(&sStat[YK_ST_MAXY], yOrg + Y0 + ly0 + TH);
+        // the four lattice points this tile touches, with its role at each (mappedRGB claim, EC.cpp:4001-4021)
+        const int i0 = lx0 >> 2, j0 = ly0 >> 2;
+        atomicOr(&sTouch[j0 * 17 + i0], 1u << (4 * rp + 0));
+        atomicOr(&sTouch[j0 * 17 + i0 + TW / 4], 1u << (4 * rp + 1));
+        atomicOr(&sTouch[(j0 + TH / 4) * 17 + i0], 1u << (4 * rp + 2));
+        atomicOr(&sTouch[(j0 + TH / 4) * 17 + i0 + TW / 4], 1u << (4 * rp + 3));
+    }
+    // EC.cpp:4029-4037: mark the accepted tiles' cells (uniformly, from the ballot)
+    unsigned b = accB;
+    while (b) {
+        const int l = __ffs((int)b) - 1; b &= b - 1u;
+        const int t2 = l / G, tx2 = t2 % NXM, ty2 = t2 / NXM;
+        const unsigned cols = ((1u << (TW / 4)) - 1u) << (tx2 * (TW / 4));
+#pragma unroll
+        for (int r = 0; r < TH / 4; r++) claimed |= cols << (4 * (ty2 * (TH / 4) + r));
+    }
+    return claimed;
 }
 
 __global__ void __launch_bounds__(YK_THREADS, 3)
@@ -230,12 +218,11 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
     __shared__ uint32_t sCell[16];
     __shared__ uint32_t sBits[YK_NPASS][8];
     __shared__ int sStat[YK_NPASS][YK_ST_STRIDE];
-    __shared__ uint16_t sList[256];
-    __shared__ int sCount[YK_NPASS];
+    __shared__ uint32_t sTouch[17 * 17];
     __shared__ uint32_t sAlpha;
 
     const YkSlotDev& S = slots[slot0 + blockIdx.y];
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int w = S.w, h = S.h, nbx = S.nbx;
     const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
     const int X0 = bx * YK_REGION, Y0 = by * YK_REGION;
@@ -253,28 +240,35 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
     }
     for (int i = tid; i < YK_NPASS * 8; i += YK_THREADS) (&sBits[0][0])[i] = 0;
     for (int i = tid; i < YK_NPASS * YK_ST_STRIDE; i += YK_THREADS) (&sStat[0][0])[i] = 0;
-    if (tid < YK_NPASS) sCount[tid] = 0;
+    for (int i = tid; i < 17 * 17; i += YK_THREADS) sTouch[i] = 0;
     if (tid == 0) sAlpha = 0;
-    __syncthreads();
 
-    unsigned bad = 0;
-    yk_stage_pixels(S, X0, Y0, pix, bad);
-
-    // ---- alpha-zero tile rejection: all(alpha == 0) per 16x16 tile (EC.cpp:357-430 restated per tile) by ballot
-    if (run.doAlpha && S.nPlanes == 4) {
+    // ---- alpha plane first (its loads stay in flight while the colour planes are staged)
+    const bool doAlpha = run.doAlpha && S.nPlanes == 4;
+    int anz[4] = { 0, 0, 0, 0 };
+    if (doAlpha) {
         const int32_t* __restrict__ P = S.plane[3];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             int ly = (tid >> 4) + 16 * k, lx = (tid & 15) * 4;
             int y = Y0 + ly, x = X0 + lx;
-            int nz = 0;
             if (y < h && x + 3 < w) {
                 int4 v = __ldg(reinterpret_cast<const int4*>(P + (size_t)y * w + x));
-                nz = v.x | v.y | v.z | v.w;
+                anz[k] = v.x | v.y | v.z | v.w;
             } else if (y < h) {
-                for (int i = 0; i < 4; i++) if (x + i < w) nz |= __ldg(P + (size_t)y * w + x + i);
+                for (int i = 0; i < 4; i++) if (x + i < w) anz[k] |= __ldg(P + (size_t)y * w + x + i);
             }
-            unsigned b = __ballot_sync(YK_FULL, nz != 0);
+        }
+    }
+    unsigned bad = 0;
+    yk_stage_pixels(S, X0, Y0, pix, bad);
+    __syncthreads();        // also orders the sAlpha/sBits/... initialisation
+
+    // ---- alpha-zero tile rejection: all(alpha == 0) per 16x16 tile (EC.cpp:357-430 restated per tile) by ballot
+    if (doAlpha) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned b = __ballot_sync(YK_FULL, anz[k] != 0);
             if (lane == 0 && b) {
                 unsigned m = 0;
 #pragma unroll
@@ -284,21 +278,30 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
         }
     }
     if (bad & ~255u) atomicOr(&S.hdr[YK_HD_ERR], 1);
-    __syncthreads();
 
+    // ---- the cascade: each warp owns two 16x16 macro tiles and runs all passes on them without block barriers
     const int R = run.rejectFactor;
-    for (int rp = 0; rp < run.nPasses; rp++) {
-        const int pid = run.passId[rp];
-        switch (pid) {      // Convert()'s order, EC.cpp:9057-9093
-        case 0: yk_pass<4, 4, 64, 64>(pix, sCell, sBits[0], sStat[0], sList, &sCount[rp], X0, Y0, w, h, S.y0, R); break;
-        case 1: yk_pass<4, 3, 64, 64>(pix, sCell, sBits[1], sStat[1], sList, &sCount[rp], X0, Y0, w, h, S.y0, R); break;
-        case 2: yk_pass<3, 4, 64, 64>(pix, sCell, sBits[2], sStat[2], sList, &sCount[rp], X0, Y0, w, h, S.y0, R); break;
-        case 3: yk_pass<3, 3, 64, 64>(pix, sCell, sBits[3], sStat[3], sList, &sCount[rp], X0, Y0, w, h, S.y0, R); break;
-        case 4: yk_pass<3, 2, 64, 32>(pix, sCell, sBits[4], sStat[4], sList, &sCount[rp], X0, Y0, w, h, S.y0, R); break;
-        case 5: yk_pass<2, 3, 32, 64>(pix, sCell, sBits[5], sStat[5], sList, &sCount[rp], X0, Y0, w, h, S.y0, R); break;
-        default: yk_pass<2, 2, 32, 32>(pix, sCell, sBits[6], sStat[6], sList, &sCount[rp], X0, Y0, w, h, S.y0, R); break;
+    for (int m = warp; m < 16; m += YK_THREADS / 32) {
+        const int mx = m & 3, my = m >> 2;
+        unsigned claimed = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) claimed |= ((sCell[my * 4 + r] >> (4 * mx)) & 15u) << (4 * r);
+        const unsigned claimed0 = claimed;
+        for (int rp = 0; rp < run.nPasses && claimed != 0xFFFFu; rp++) {
+            const int pid = run.passId[rp];
+            switch (pid) {      // Convert()'s order, EC.cpp:9057-9093
+            case 0: claimed = yk_macro_pass<4, 4, 64, 64>(pix, sBits[0], sStat[0], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
+            case 1: claimed = yk_macro_pass<4, 3, 64, 64>(pix, sBits[1], sStat[1], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
+            case 2: claimed = yk_macro_pass<3, 4, 64, 64>(pix, sBits[2], sStat[2], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
+            case 3: claimed = yk_macro_pass<3, 3, 64, 64>(pix, sBits[3], sStat[3], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
+            case 4: claimed = yk_macro_pass<3, 2, 64, 32>(pix, sBits[4], sStat[4], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
+            case 5: claimed = yk_macro_pass<2, 3, 32, 64>(pix, sBits[5], sStat[5], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
+            default: claimed = yk_macro_pass<2, 2, 32, 32>(pix, sBits[6], sStat[6], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
+            }
         }
+        if (lane < 4 && claimed != claimed0) atomicOr(&sCell[my * 4 + lane], ((claimed >> (4 * lane)) & 15u) << (4 * mx));
     }
+    __syncthreads();
 
     // ---- results of the region
     // accept bitmaps in the reference's swizzled layout: 16-bit units of each sub-block
@@ -321,34 +324,25 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
         int cy = (Y0 >> 2) + tid;
         if (cy * 4 < h) S.cellMask[(size_t)cy * nbx + bx] = (uint16_t)sCell[tid];
     }
-    // per 8-tile segment of DynamicTileCompressor's row-major tile order: 16-byte chunks to code and coded tiles
-    if (tid >= 32 && tid < 40) {
-        const int t = tid - 32, ty = (Y0 >> 3) + t;
-        if (ty * 8 < h) {
-            const uint32_t c0 = sCell[2 * t], c1 = sCell[2 * t + 1];
-            int chunks = 0, tiles = 0;
-#pragma unroll
-            for (int x = 0; x < 8; x++) {
-                int n = 4 - __popc(((c0 >> (2 * x)) & 3u) | (((c1 >> (2 * x)) & 3u) << 2));
-                chunks += n; tiles += (n > 0);
-            }
-            S.r2Seg[(size_t)ty * nbx + bx] = chunks | (tiles << 16);
-        }
-    }
-    // corner colours at every 4-pixel lattice point of the region (what an accepted tile would emit, EC.cpp:4115-4132)
+    // corner colours at every 4-pixel lattice point of the region (what an accepted tile would emit, EC.cpp:4115-4132),
+    // and the touch words of the lattice points (interior points are exclusive to the region, border points are shared)
     {
         const int iMax = (bx == nbx - 1) ? 17 : 16, jMax = (by == S.nby - 1) ? 17 : 16;
         for (int idx = tid; idx < 17 * 17; idx += YK_THREADS) {
             const int i = idx % 17, jj = idx / 17;
             const int gx = (X0 >> 2) + i, gy = (Y0 >> 2) + jj;
-            if (i < iMax && jj < jMax && gx < S.latW && gy < S.latH) {
-                uint8_t* d = S.latRGB + ((size_t)gy * S.latW + gx) * 3;
+            if (gx < S.latW && gy < S.latH) {
+                if (i < iMax && jj < jMax) {
+                    uint8_t* d = S.latRGB + ((size_t)gy * S.latW + gx) * 3;
 #pragma unroll
-                for (int c = 0; c < 3; c++) d[c] = (uint8_t)yk_compress250(yk_round6(pix[c][(4 * jj) * YK_RS + 4 * i]));
+                    for (int c = 0; c < 3; c++) d[c] = (uint8_t)yk_compress250(yk_round6(pix[c][(4 * jj) * YK_RS + 4 * i]));
+                }
+                const uint32_t tv = sTouch[idx];
+                if (tv) atomicOr(&S.touchMap[(size_t)gy * S.latW + gx], tv);
             }
         }
     }
-    if (run.doAlpha && S.nPlanes == 4 && tid < 32) {
+    if (doAlpha && tid < 32) {
         const int tx = tid & 3, ty = (tid >> 2) & 3;
         const int px = X0 + 16 * tx, py = Y0 + 16 * ty;
         const bool in = tid < 16 && px < w && py < h;
@@ -378,320 +372,276 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
     }
 }
 
+// A new launch on a state that already holds claims: every touched lattice point becomes "claimed before" (bit 31).
+__global__ void __launch_bounds__(256)
+yk_k_fold_touch(const YkSlotDev* __restrict__ slots, int slot0, int nWords) {
+    const YkSlotDev& S = slots[slot0 + blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nWords) { uint32_t v = S.touchMap[i]; if (v && v != 0x80000000u) S.touchMap[i] = 0x80000000u; }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-// Corner ownership.  The reference walks tiles in stream order and lets a tile emit a corner colour only if no
-// earlier tile (of this or an earlier pass) touched that lattice point (mappedRGB, EC.cpp:4001-4021, 4115-4132).
-// Order-free: firstClaim[L] = first pass of this launch with an accepted tile touching L (0 = claimed before the
-// launch); in that pass the accepted toucher with the smallest stream position emits L.
-static __device__ __forceinline__ int yk_accept_bit(const YkSlotDev& S, int pid, const YkGeomC& g, int gtx, int gty) {
-    if (gtx < 0 || gty < 0 || ((gtx + 1) << g.shx) > S.w || ((gty + 1) << g.shy) > S.h) return 0;
-    int pos = yk_tile_pos(g, S.w, gtx, gty);
-    return (S.bitmap[pid][pos >> 3] >> (pos & 7)) & 1;
+// volatile access + decoupled look-back.  Work units are handed out by an atomic ticket in stream order, so a unit only
+// ever waits for units with smaller tickets, which are already running or finished.
+#ifdef YK_EMULATE
+static inline unsigned yk_ldv(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline void yk_stv(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long yk_ldv64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline void yk_stv64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
+static inline void yk_spin() { std::this_thread::yield(); }
+#else
+static __device__ __forceinline__ unsigned yk_ldv(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+static __device__ __forceinline__ void yk_stv(unsigned* p, unsigned v) { *reinterpret_cast<volatile unsigned*>(p) = v; }
+static __device__ __forceinline__ unsigned long long yk_ldv64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+static __device__ __forceinline__ void yk_stv64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+static __device__ __forceinline__ void yk_spin() { __nanosleep(20); }
+#endif
+
+// status word: value << 2 | flag (1 = this unit's own total, 2 = inclusive prefix).  Returns the exclusive prefix of unit u
+// and publishes its inclusive prefix.  All 32 lanes call it with the same arguments.
+static __device__ unsigned yk_lookback32(uint32_t* status, int u, unsigned total) {
+    const int lane = threadIdx.x & 31;
+    if (u == 0) { if (lane == 0) yk_stv(&status[0], (total << 2) | 2u); return 0u; }
+    if (lane == 0) yk_stv(&status[u], (total << 2) | 1u);
+    unsigned base = 0;
+    int look = u - 1;
+    while (look >= 0) {
+        const int idx = look - lane;
+        const unsigned st = idx >= 0 ? yk_ldv(&status[idx]) : 2u;       // before the first unit: inclusive prefix 0
+        const unsigned ready = __ballot_sync(YK_FULL, (st & 3u) != 0u);
+        const unsigned incl = __ballot_sync(YK_FULL, (st & 3u) == 2u);
+        const unsigned need = incl ? ((2u << (__ffs((int)incl) - 1)) - 1u) : YK_FULL;     // lanes up to the nearest inclusive prefix
+        if ((ready & need) != need) { yk_spin(); continue; }
+        base += __reduce_add_sync(YK_FULL, ((need >> lane) & 1u) ? (st >> 2) : 0u);
+        if (incl) break;
+        look -= 32;
+    }
+    if (lane == 0) yk_stv(&status[u], ((base + total) << 2) | 2u);
+    return base;
+}
+
+// same with two counters packed in 64 bits: hi << 32 | lo << 2 | flag
+static __device__ unsigned long long yk_lookback64(unsigned long long* status, int u, unsigned hi, unsigned lo) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long mine = ((unsigned long long)hi << 32) | ((unsigned long long)lo << 2);
+    if (u == 0) { if (lane == 0) yk_stv64(&status[0], mine | 2ull); return 0ull; }
+    if (lane == 0) yk_stv64(&status[u], mine | 1ull);
+    unsigned bhi = 0, blo = 0;
+    int look = u - 1;
+    while (look >= 0) {
+        const int idx = look - lane;
+        const unsigned long long st = idx >= 0 ? yk_ldv64(&status[idx]) : 2ull;
+        const unsigned fl = (unsigned)(st & 3ull);
+        const unsigned ready = __ballot_sync(YK_FULL, fl != 0u);
+        const unsigned incl = __ballot_sync(YK_FULL, fl == 2u);
+        const unsigned need = incl ? ((2u << (__ffs((int)incl) - 1)) - 1u) : YK_FULL;
+        if ((ready & need) != need) { yk_spin(); continue; }
+        const bool use = (need >> lane) & 1u;
+        bhi += __reduce_add_sync(YK_FULL, use ? (unsigned)(st >> 32) : 0u);
+        blo += __reduce_add_sync(YK_FULL, use ? (unsigned)((st & 0xFFFFFFFFull) >> 2) : 0u);
+        if (incl) break;
+        look -= 32;
+    }
+    if (lane == 0) yk_stv64(&status[u], (((unsigned long long)(bhi + hi)) << 32) | ((unsigned long long)(blo + lo) << 2) | 2ull);
+    return ((unsigned long long)bhi << 32) | blo;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Corner ownership and emission in one kernel.  The reference walks tiles in stream order and lets a tile emit a corner
+// colour only if no earlier tile (of this or an earlier pass) touched that lattice point (mappedRGB, EC.cpp:4001-4021,
+// 4115-4132).  Order-free: a lattice point is emitted in the first pass that touches it, by the accepted toucher with the
+// smallest stream position — all of which the point's touch word says.  One warp per (pass, swizzle block); swizzle
+// blocks are taken in stream order, the running rgb byte offset comes from a decoupled look-back.
+struct YkGeomS { int shx, shy, lbw, lbh, bits; };
+static __device__ __forceinline__ YkGeomS yk_geom_s(int pid) {
+    const YkGeomS t[YK_NPASS] = { {4,4,6,6,16}, {4,3,6,6,32}, {3,4,6,6,32}, {3,3,6,6,64}, {3,2,6,5,64}, {2,3,5,6,64}, {2,2,5,5,64} };
+    return t[pid];
+}
+static __device__ __forceinline__ int yk_pos_s(const YkGeomS& g, int nSwzX, int gtx, int gty) {
+    const int x = gtx << g.shx, y = gty << g.shy;
+    return (((y >> g.lbh) * nSwzX + (x >> g.lbw)) * g.bits) + (((y & ((1 << g.lbh) - 1)) >> g.shy) << (g.lbw - g.shx)) + ((x & ((1 << g.lbw) - 1)) >> g.shx);
 }
 
 __global__ void __launch_bounds__(YK_THREADS)
-yk_k_emit_count(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
-    __shared__ int fc[17 * 17];
-    __shared__ uint8_t acc[YK_NPASS][18 * 18];
-    __shared__ int unitCnt[YK_NPASS][4];
+yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int totalUnits) {
     const YkSlotDev& S = slots[slot0 + blockIdx.y];
-    const int tid = threadIdx.x;
-    const int w = S.w, h = S.h, nbx = S.nbx;
-    const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
-    const int X0 = bx * YK_REGION, Y0 = by * YK_REGION;
-
-    for (int idx = tid; idx < 17 * 17; idx += YK_THREADS) {
-        const int gx = (X0 >> 2) + idx % 17, gy = (Y0 >> 2) + idx / 17;
-        int claimed = 1;
-        if (gx < S.latW && gy < S.latH) claimed = (S.cornerMask[(size_t)gy * S.cornerWords + (gx >> 5)] >> (gx & 31)) & 1u;
-        fc[idx] = claimed ? 0 : 127;
+    const int lane = threadIdx.x & 31;
+    const int w = S.w, h = S.h;
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&S.hdr[YK_HD_TICKET_EMIT], 1);
+    ticket = __shfl_sync(YK_FULL, ticket, 0);
+    if (ticket >= totalUnits) return;
+    // ticket -> (pass position, swizzle block)
+    int rp = 0, u = ticket, nUnits = 0, nSwzX = 0;
+    YkGeomS g = yk_geom_s(run.passId[0]);
+    for (;;) {
+        g = yk_geom_s(run.passId[rp]);
+        nSwzX = (w + (1 << g.lbw) - 1) >> g.lbw;
+        nUnits = nSwzX * ((h + (1 << g.lbh) - 1) >> g.lbh);
+        if (u < nUnits) break;
+        u -= nUnits; rp++;
     }
-    if (tid < YK_NPASS * 4) (&unitCnt[0][0])[tid] = 0;
-    __syncthreads();
-
-    for (int rp = 0; rp < run.nPasses; rp++) {
-        const int pid = run.passId[rp];
-        const YkGeomC g = yk_geom(pid);
-        const int NX = 64 >> g.shx, NY = 64 >> g.shy, EW = NX + 2;
-        const int cw4 = (1 << g.shx) >> 2, ch4 = (1 << g.shy) >> 2;
-        for (int idx = tid; idx < EW * (NY + 2); idx += YK_THREADS) {
-            const int ex = idx % EW - 1, ey = idx / EW - 1;
-            const int a = yk_accept_bit(S, pid, g, bx * NX + ex, by * NY + ey);
-            acc[rp][idx] = (uint8_t)a;
-            if (a) {
-                const int cx0 = ex * cw4, cy0 = ey * ch4;
+    const int pid = run.passId[rp];
+    const int sbx = u % nSwzX, sby = u / nSwzX;
+    const int tprShift = g.lbw - g.shx;                                     // log2(tiles per row of the swizzle block)
+    // accept bits of the block
+    unsigned long long acc;
+    if (g.bits == 16) acc = reinterpret_cast<const uint16_t*>(S.bitmap[pid])[u];
+    else if (g.bits == 32) acc = reinterpret_cast<const uint32_t*>(S.bitmap[pid])[u];
+    else acc = reinterpret_cast<const uint32_t*>(S.bitmap[pid])[2 * u] | ((unsigned long long)reinterpret_cast<const uint32_t*>(S.bitmap[pid])[2 * u + 1] << 32);
+    int mask[2] = { 0, 0 }, gtxv[2] = { 0, 0 }, gtyv[2] = { 0, 0 };
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int cx = cx0 + (k & 1) * cw4, cy = cy0 + (k >> 1) * ch4;
-                    if (cx >= 0 && cx <= 16 && cy >= 0 && cy <= 16) atomicMin(&fc[cy * 17 + cx], rp + 1);
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    for (int rp = 0; rp < run.nPasses; rp++) {
-        const int pid = run.passId[rp];
-        const YkGeomC g = yk_geom(pid);
-        const int NX = 64 >> g.shx, NY = 64 >> g.shy, EW = NX + 2;
-        const int cw4 = (1 << g.shx) >> 2, ch4 = (1 << g.shy) >> 2;
-        const int tw = 1 << g.shx, th = 1 << g.shy;
-        for (int idx = tid; idx < NX * NY; idx += YK_THREADS) {
-            const int tx = idx % NX, ty = idx / NX;
-            const int gtx = bx * NX + tx, gty = by * NY + ty;
-            if (((gtx + 1) << g.shx) > w || ((gty + 1) << g.shy) > h) continue;
-            const int myPos = yk_tile_pos(g, w, gtx, gty);
-            int mask = 0;
-            if (acc[rp][(ty + 1) * EW + tx + 1]) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int tX = tx + (k & 1), tY = ty + (k >> 1);           // lattice point in tile units
-                    if (fc[(tY * ch4) * 17 + tX * cw4] != rp + 1) continue;
-                    bool owner = true;
-#pragma unroll
-                    for (int o = 0; o < 4; o++) {
-                        const int ox = tX - 1 + (o & 1), oy = tY - 1 + (o >> 1);
-                        if (ox == tx && oy == ty) continue;
-                        if (acc[rp][(oy + 1) * EW + ox + 1] && yk_tile_pos(g, w, bx * NX + ox, by * NY + oy) < myPos) owner = false;
-                    }
-                    if (owner) mask |= 1 << k;
-                }
-            }
-            S.emitMask[pid][myPos] = (uint8_t)mask;
-            if (mask) {
-                const int lx0 = tx * tw, ly0 = ty * th;
-                atomicAdd(&unitCnt[rp][(ly0 / g.bh) * (64 / g.bw) + lx0 / g.bw], 3 * __popc(mask));
-            }
-        }
-    }
-    __syncthreads();
-
-    if (tid < run.nPasses * 4) {
-        const int rp = tid >> 2, sub = tid & 3, pid = run.passId[rp];
-        const YkGeomC g = yk_geom(pid);
-        if (sub < (64 / g.bw) * (64 / g.bh)) {
-            const int sx = X0 + (sub % (64 / g.bw)) * g.bw, sy = Y0 + (sub / (64 / g.bw)) * g.bh;
-            if (sx < w && sy < h) S.unitOff[pid][(sy / g.bh) * ((w + g.bw - 1) / g.bw) + sx / g.bw] = unitCnt[rp][sub];
-        }
-    }
-    // lattice points claimed by this launch
-    if (tid >= 64 && tid < 64 + 17) {
-        const int jj = tid - 64, gy = (Y0 >> 2) + jj;
-        if (gy < S.latH) {
-            unsigned long long bits = 0;
-            for (int i = 0; i < 17; i++) {
-                const int v = fc[jj * 17 + i];
-                if (v > 0 && v < 127 && (X0 >> 2) + i < S.latW) bits |= 1ull << i;
-            }
-            if (bits) {
-                const int gx0 = X0 >> 2;                 // multiple of 16
-                bits <<= (gx0 & 31);
-                uint32_t* row = S.cornerNew + (size_t)gy * S.cornerWords + (gx0 >> 5);
-                if ((uint32_t)bits) atomicOr(row, (uint32_t)bits);
-                if ((uint32_t)(bits >> 32)) atomicOr(row + 1, (uint32_t)(bits >> 32));
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Exclusive scans: blockIdx.x < YK_NPASS -> rgb byte counts of that pass per swizzle block (stream order);
-// blockIdx.x == YK_NPASS -> DynamicTileCompressor segments (chunks and coded tiles).
-static __device__ int yk_block_exclusive(int v, int* sWarp, int& total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(YK_FULL, inc, d); if (lane >= d) inc += t; }
-    if (lane == 31) sWarp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        int x = lane < nw ? sWarp[lane] : 0, xi = x;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(YK_FULL, xi, d); if (lane >= d) xi += t; }
-        sWarp[lane] = xi - x;
-        if (lane == 31) sWarp[32] = xi;
-    }
-    __syncthreads();
-    total = sWarp[32];
-    const int r = sWarp[warp] + inc - v;
-    __syncthreads();
-    return r;
-}
-
-__global__ void __launch_bounds__(1024)
-yk_k_scan(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
-    __shared__ int sWarp[33];
-    const YkSlotDev& S = slots[slot0 + blockIdx.y];
-    const int tid = threadIdx.x;
-    if (blockIdx.x < YK_NPASS) {
-        if ((int)blockIdx.x >= run.nPasses) return;
-        const int pid = run.passId[blockIdx.x];
-        const YkGeomC g = yk_geom(pid);
-        const int n = ((S.w + g.bw - 1) / g.bw) * ((S.h + g.bh - 1) / g.bh);
-        int* a = S.unitOff[pid];
-        const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
-        const int b = min(n, tid * per), e = min(n, b + per);
-        int sum = 0;
-        for (int i = b; i < e; i++) sum += a[i];
-        int total;
-        int runv = yk_block_exclusive(sum, sWarp, total);
-        for (int i = b; i < e; i++) { int v = a[i]; a[i] = runv; runv += v; }
-        if (tid == 0) S.hdr[YK_HD_PASS0 + pid * YK_ST_STRIDE + YK_ST_RGBBYTES] = total;
-    } else {
-        const int n = (S.h >> 3) * S.nbx;
-        int* a = S.r2Seg; int* t2 = S.r2SegTiles;
-        const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
-        const int b = min(n, tid * per), e = min(n, b + per);
-        int sc = 0, stl = 0;
-        for (int i = b; i < e; i++) { int v = a[i]; sc += v & 0xFFFF; stl += v >> 16; }
-        int totC, totT;
-        int rc = yk_block_exclusive(sc, sWarp, totC);
-        int rt = yk_block_exclusive(stl, sWarp, totT);
-        for (int i = b; i < e; i++) { int v = a[i]; a[i] = rc; t2[i] = rt; rc += v & 0xFFFF; rt += v >> 16; }
-        if (tid == 0) { S.hdr[YK_HD_R2_CHUNKS] = totC; S.hdr[YK_HD_R2_TILES] = totT; }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(YK_THREADS)
-yk_k_emit_write(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
-    __shared__ int sWarp[33];
-    __shared__ int sP[256];
-    const YkSlotDev& S = slots[slot0 + blockIdx.y];
-    const int tid = threadIdx.x;
-    const int w = S.w, h = S.h, nbx = S.nbx;
-    const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
-    const int X0 = bx * YK_REGION, Y0 = by * YK_REGION;
-
-    for (int rp = 0; rp < run.nPasses; rp++) {
-        const int pid = run.passId[rp];
-        const YkGeomC g = yk_geom(pid);
-        const int tw = 1 << g.shx, th = 1 << g.shy;
-        const int nsub = (64 / g.bw) * (64 / g.bh), NT = nsub * g.bits;
-        // thread = tile in stream order inside the region: li = sub * bits + row * (bw/tw) + col
-        int m = 0, lx0 = 0, ly0 = 0, sub = 0;
-        if (tid < NT) {
-            sub = tid / g.bits;
-            const int within = tid % g.bits, tpr = g.bw / tw;
-            lx0 = (sub % (64 / g.bw)) * g.bw + (within % tpr) * tw;
-            ly0 = (sub / (64 / g.bw)) * g.bh + (within / tpr) * th;
-            if (X0 + lx0 + tw <= w && Y0 + ly0 + th <= h)
-                m = S.emitMask[pid][yk_tile_pos(g, w, (X0 + lx0) >> g.shx, (Y0 + ly0) >> g.shy)];
-        }
-        int total;
-        const int ex = yk_block_exclusive(3 * __popc(m), sWarp, total);
-        sP[tid] = ex;
-        __syncthreads();
-        if (m) {
-            const int sx = X0 + (sub % (64 / g.bw)) * g.bw, sy = Y0 + (sub / (64 / g.bw)) * g.bh;
-            const int gb = (sy / g.bh) * ((w + g.bw - 1) / g.bw) + sx / g.bw;
-            int off = S.unitOff[pid][gb] + ex - sP[sub * g.bits];
-            uint8_t* out = S.rgb[pid];
+    for (int s2 = 0; s2 < 2; s2++) {
+        const int li = lane + 32 * s2;
+        if (li < g.bits && ((acc >> li) & 1ull)) {
+            const int gtx = ((sbx << g.lbw) >> g.shx) + (li & ((1 << tprShift) - 1)), gty = ((sby << g.lbh) >> g.shy) + (li >> tprShift);
+            gtxv[s2] = gtx; gtyv[s2] = gty;
+            const int myPos = u * g.bits + li;
+            int m = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if ((m >> k) & 1) {
-                    const int gx = ((X0 + lx0) >> 2) + (k & 1) * (tw >> 2), gy = ((Y0 + ly0) >> 2) + (k >> 1) * (th >> 2);
+                const int LX = gtx + (k & 1), LY = gty + (k >> 1);                       // lattice point in tile units
+                const uint32_t word = S.touchMap[(size_t)((LY << g.shy) >> 2) * S.latW + ((LX << g.shx) >> 2)];
+                if (word & 0x80000000u) continue;                                        // claimed by an earlier launch
+                if (((__ffs((int)(word & 0x0FFFFFFFu)) - 1) >> 2) != rp) continue;       // an earlier pass of this launch got it
+                const unsigned nib = (word >> (4 * rp)) & 15u;                           // roles present in this pass
+                bool owner = true;
+#pragma unroll
+                for (int k2 = 0; k2 < 4; k2++)
+                    if (k2 != k && ((nib >> k2) & 1u) && yk_pos_s(g, nSwzX, LX - (k2 & 1), LY - (k2 >> 1)) < myPos) owner = false;
+                if (owner) m |= 1 << k;
+            }
+            mask[s2] = m;
+        }
+    }
+    // exclusive prefix of the emitted bytes inside the block (tile order = lane order, second half after the first)
+    const unsigned c0 = 3u * __popc(mask[0]), c1 = 3u * __popc(mask[1]);
+    unsigned i0 = c0, i1 = c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned t0 = __shfl_up_sync(YK_FULL, i0, d), t1 = __shfl_up_sync(YK_FULL, i1, d);
+        if (lane >= d) { i0 += t0; i1 += t1; }
+    }
+    const unsigned tot0 = __shfl_sync(YK_FULL, i0, 31), tot1 = __shfl_sync(YK_FULL, i1, 31);
+    const unsigned base = yk_lookback32(S.emitStatus[pid], u, tot0 + tot1);
+    if (u == nUnits - 1 && lane == 0) S.hdr[YK_HD_PASS0 + pid * YK_ST_STRIDE + YK_ST_RGBBYTES] = (int)(base + tot0 + tot1);
+    uint8_t* out = S.rgb[pid];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; s2++) {
+        if (mask[s2]) {
+            unsigned off = base + (s2 ? tot0 + i1 - c1 : i0 - c0);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if ((mask[s2] >> k) & 1) {                                             // TL, TR, BL, BR (EC.cpp:4115-4132)
+                    const int gx = ((gtxv[s2] + (k & 1)) << g.shx) >> 2, gy = ((gtyv[s2] + (k >> 1)) << g.shy) >> 2;
                     const uint8_t* s = S.latRGB + ((size_t)gy * S.latW + gx) * 3;
                     out[off] = s[0]; out[off + 1] = s[1]; out[off + 2] = s[2];
                     off += 3;
                 }
             }
         }
-        __syncthreads();
-    }
-    // fold this launch's claims into the persistent corner mask (mappedRGB, EC.cpp:4005-4019)
-    if (tid < 17 * 2) {
-        const int jj = tid >> 1, gy = (Y0 >> 2) + jj, wi = ((X0 >> 2) >> 5) + (tid & 1);
-        if (gy < S.latH && wi < S.cornerWords) {
-            const uint32_t v = S.cornerNew[(size_t)gy * S.cornerWords + wi];
-            if (v) atomicOr(&S.cornerMask[(size_t)gy * S.cornerWords + wi], v);
-        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// DynamicTileCompressor (EC.cpp:8398-8522): one warp per (8x8 tile, plane); lane = 2 pixels.
+// DynamicTileCompressor (EC.cpp:8398-8522).  One warp per 8-tile segment (one tile row of one 64-pixel column) in the
+// reference's row-major tile order; stream offsets by decoupled look-back; per tile and plane one pass with lane = 2 pixels.
 __global__ void __launch_bounds__(YK_THREADS)
-yk_k_range1d(const YkSlotDev* __restrict__ slots, int slot0) {
+yk_k_range1d(const YkSlotDev* __restrict__ slots, int slot0, int nSegs) {
     __shared__ uint32_t hist[YK_THREADS / 32][256];
-    __shared__ uint32_t sCell[16];
     const YkSlotDev& S = slots[slot0 + blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int w = S.w, h = S.h, nbx = S.nbx;
-    const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
-    const int X0 = bx * YK_REGION, Y0 = by * YK_REGION;
-    if (tid < 16) {
-        int cy = (Y0 >> 2) + tid;
-        uint32_t v = 0xFFFFu;
-        if (cy * 4 < h) {
-            v = S.cellMask[(size_t)cy * nbx + bx];
-            int cellsIn = (w - X0) >> 2;
-            if (cellsIn < 16) v |= (0xFFFFu << cellsIn) & 0xFFFFu;
-        }
-        sCell[tid] = v;
+    for (int i = lane; i < 256; i += 32) hist[warp][i] = 0;
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&S.hdr[YK_HD_TICKET_R2], 1);
+    ticket = __shfl_sync(YK_FULL, ticket, 0);
+    if (ticket >= nSegs) return;
+    const int bx = ticket % nbx, ty = ticket / nbx;                 // tile row ty, 64-pixel column bx
+    const int X0 = bx * 64, Y0 = ty * 8;
+    uint32_t r0 = S.cellMask[(size_t)(2 * ty) * nbx + bx], r1 = S.cellMask[(size_t)(2 * ty + 1) * nbx + bx];
+    {
+        const int cellsIn = (w - X0) >> 2;
+        if (cellsIn < 16) { r0 |= (0xFFFFu << cellsIn) & 0xFFFFu; r1 |= (0xFFFFu << cellsIn) & 0xFFFFu; }
     }
-    for (int i = tid; i < (YK_THREADS / 32) * 256; i += YK_THREADS) (&hist[0][0])[i] = 0;
-    __syncthreads();
+    // quadrant needs coding iff its top-left map pixel is 0 (EC.cpp:8420-8430) == its 4x4 cell is unclaimed
+    int chunks = 0, tiles = 0;
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+        const int n = 4 - __popc(((r0 >> (2 * x)) & 3u) | (((r1 >> (2 * x)) & 3u) << 2));
+        chunks += n; tiles += (n > 0);
+    }
+    const unsigned long long basePacked = yk_lookback64(S.r2Status, ticket, (unsigned)chunks, (unsigned)tiles);
+    int chunkOff = (int)(basePacked >> 32), tileOff = (int)(basePacked & 0xFFFFFFFFull);
+    if (ticket == nSegs - 1 && lane == 0) { S.hdr[YK_HD_R2_CHUNKS] = chunkOff + chunks; S.hdr[YK_HD_R2_TILES] = tileOff + tiles; }
+    if (chunks == 0) return;
+    __syncwarp();
 
     const int r = lane >> 2, c0 = (lane & 3) * 2;           // pixel row / first column of this lane inside the tile
     const int band = r >> 2, right = c0 >> 2;
-    for (int item = warp; item < 64 * 3; item += YK_THREADS / 32) {
-        const int tile = item % 64, plane = item / 64;
-        const int tx = tile & 7, ty = tile >> 3;
-        if (X0 + 8 * tx + 8 > w || Y0 + 8 * ty + 8 > h) continue;
-        const uint32_t r0 = sCell[2 * ty], r1 = sCell[2 * ty + 1];
-        // quadrant needs coding iff its top-left map pixel is 0 (EC.cpp:8420-8430) == its 4x4 cell is unclaimed
+    for (int tx = 0; tx < 8; tx++) {
         const unsigned q = (~(((r0 >> (2 * tx)) & 3u) | (((r1 >> (2 * tx)) & 3u) << 2))) & 15u;   // bit0 TL, 1 TR, 2 BL, 3 BR
         if (q == 0) continue;
-        // offsets: scanned segment base + tiles to the left inside the segment
-        int chunkOff, tileOff;
-        {
-            const size_t seg = (size_t)((Y0 >> 3) + ty) * nbx + bx;
-            chunkOff = S.r2Seg[seg]; tileOff = S.r2SegTiles[seg];
-            for (int x = 0; x < tx; x++) {
-                int n = 4 - __popc(((r0 >> (2 * x)) & 3u) | (((r1 >> (2 * x)) & 3u) << 2));
-                chunkOff += n; tileOff += (n > 0);
-            }
-        }
         const bool valid = (q >> (band * 2 + right)) & 1u;
-        int vx = 0, vy = 0;
-        if (valid) {
-            int2 p = __ldg(reinterpret_cast<const int2*>(S.plane[plane] + (size_t)(Y0 + 8 * ty + r) * w + X0 + 8 * tx + c0));
-            vx = p.x & 255; vy = p.y & 255;             // CompressF(v, 255) == v (EC.cpp:8442)
-            atomicAdd(&hist[warp][vx], 1u); atomicAdd(&hist[warp][vy], 1u);
+        const unsigned qb = (q >> (band * 2)) & 3u;                     // coded quadrants of this band: bit0 left, bit1 right
+        const int lengthX = (qb == 3u) ? 8 : 4, x2 = (qb == 2u) ? 4 : 0;
+        const int pos = (band ? 16 * __popc(q & 3u) : 0) + (r & 3) * lengthX + (c0 - x2);
+        for (int plane = 0; plane < 3; plane++) {
+            int vx = 0, vy = 0;
+            if (valid) {
+                int2 p = __ldg(reinterpret_cast<const int2*>(S.plane[plane] + (size_t)(Y0 + r) * w + X0 + 8 * tx + c0));
+                vx = p.x & 255; vy = p.y & 255;             // CompressF(v, 255) == v (EC.cpp:8442)
+            }
+            // histogram of the coded pixels; equal values are pre-aggregated with match.any so a flat tile costs one atomic
+            {
+                const unsigned mxm = __match_any_sync(YK_FULL, valid ? vx : -1 - lane);
+                const unsigned mym = __match_any_sync(YK_FULL, valid ? vy : -1 - lane);
+                if (valid) {
+                    if ((__ffs((int)mxm) - 1) == lane) atomicAdd(&hist[warp][vx], (unsigned)__popc(mxm));
+                    if ((__ffs((int)mym) - 1) == lane) atomicAdd(&hist[warp][vy], (unsigned)__popc(mym));
+                }
+            }
+            __syncwarp();
+            // FindAndRemoveMostUsedColor (EC.cpp:8335-8356): highest index among the maximal counts; only present values can win
+            unsigned key = 0;
+            if (valid) key = max((hist[warp][vx] << 8) | (unsigned)vx, (hist[warp][vy] << 8) | (unsigned)vy);
+            key = __reduce_max_sync(YK_FULL, key);
+            __syncwarp();
+            if (valid) { hist[warp][vx] = 0; hist[warp][vy] = 0; }
+            int color0 = min(max((int)(key & 255u), 1), 254);
+            // Model1 (EC.cpp:8358-8381) over what is left of the histogram
+            const bool remx = valid && (vx < color0 - 1 || vx > color0 + 1), remy = valid && (vy < color0 - 1 || vy > color0 + 1);
+            int mn = min(remx ? vx : 999, remy ? vy : 999), mx = max(remx ? vx : -1, remy ? vy : -1);
+            mn = __reduce_min_sync(YK_FULL, mn); mx = __reduce_max_sync(YK_FULL, mx);
+            int minCol = 0, delta = 0;
+            if (mn != 999) { minCol = mn; delta = mx - mn; }
+            if (valid) {
+                // GetValueModel1 (EC.cpp:8383-8391): C division of a numerator in -1..3951 by delta in 1..255.
+                // floor(n/d) == (n * ceil(2^20/d)) >> 20 for 0 <= n < 4112, d <= 255; n == -1 only happens for delta == 1.
+                int bxv = 0, byv = 0;
+                if (delta) {
+                    const unsigned magic = ((1u << 20) + (unsigned)delta - 1u) / (unsigned)delta;
+                    const int rnd = (delta >> 1) - 1;
+                    if (remx) { const int n = (vx - minCol) * 15 + rnd; bxv = 1 + (n < 0 ? n : (int)(((unsigned)n * magic) >> 20)); }
+                    if (remy) { const int n = (vy - minCol) * 15 + rnd; byv = 1 + (n < 0 ? n : (int)(((unsigned)n * magic) >> 20)); }
+                } else { bxv = remx ? 1 : 0; byv = remy ? 1 : 0; }
+                uint8_t* d = S.r2Idx[plane] + (size_t)chunkOff * 16 + pos;
+                *reinterpret_cast<uint16_t*>(d) = (uint16_t)((bxv & 255) | ((byv & 255) << 8));
+            }
+            if (lane == 0) {
+                uint8_t* t = S.r2Type[plane] + (size_t)tileOff * 3;            // EC.cpp:8503-8505
+                t[0] = (uint8_t)color0; t[1] = (uint8_t)minCol; t[2] = (uint8_t)delta;
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        // FindAndRemoveMostUsedColor (EC.cpp:8335-8356): highest index among the maximal counts
-        unsigned key = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { unsigned cnt = hist[warp][lane * 8 + i]; key = max(key, (cnt << 8) | (unsigned)(lane * 8 + i)); hist[warp][lane * 8 + i] = 0; }
-        key = __reduce_max_sync(YK_FULL, key);
-        int color0 = (int)(key & 255u);
-        color0 = min(max(color0, 1), 254);
-        // Model1 (EC.cpp:8358-8381) over what is left of the histogram
-        const bool remx = valid && (vx < color0 - 1 || vx > color0 + 1), remy = valid && (vy < color0 - 1 || vy > color0 + 1);
-        int mn = min(remx ? vx : 999, remy ? vy : 999), mx = max(remx ? vx : -1, remy ? vy : -1);
-        mn = __reduce_min_sync(YK_FULL, mn); mx = __reduce_max_sync(YK_FULL, mx);
-        int minCol = 0, delta = 0;
-        if (mn != 999) { minCol = mn; delta = mx - mn; }
-        if (valid) {
-            // GetValueModel1 (EC.cpp:8383-8391): C division; numerator -1 only when delta == 1
-            int bxv = 0, byv = 0;
-            if (remx) bxv = 1 + (delta ? ((vx - minCol) * 15 + ((delta >> 1) - 1)) / delta : 0);
-            if (remy) byv = 1 + (delta ? ((vy - minCol) * 15 + ((delta >> 1) - 1)) / delta : 0);
-            const unsigned qb = (q >> (band * 2)) & 3u;                     // coded quadrants of this band: bit0 left, bit1 right
-            const int lengthX = (qb == 3u) ? 8 : 4, x2 = (qb == 2u) ? 4 : 0;
-            const int bandBase = band ? 16 * __popc(q & 3u) : 0;
-            const int pos = bandBase + (r & 3) * lengthX + (c0 - x2);
-            uint8_t* d = S.r2Idx[plane] + (size_t)chunkOff * 16 + pos;
-            *reinterpret_cast<uint16_t*>(d) = (uint16_t)((bxv & 255) | ((byv & 255) << 8));
-        }
-        if (lane == 0) {
-            uint8_t* t = S.r2Type[plane] + (size_t)tileOff * 3;            // EC.cpp:8503-8505
-            t[0] = (uint8_t)color0; t[1] = (uint8_t)minCol; t[2] = (uint8_t)delta;
-        }
-        __syncwarp();
+        chunkOff += __popc(q); tileOff += 1;
     }
+}
+
+static __device__ __forceinline__ int yk_accept_bit(const YkSlotDev& S, int pid, const YkGeomC& g, int gtx, int gty) {
+    if (gtx < 0 || gty < 0 || ((gtx + 1) << g.shx) > S.w || ((gty + 1) << g.shy) > S.h) return 0;
+    int pos = yk_tile_pos(g, S.w, gtx, gty);
+    return (S.bitmap[pid][pos >> 3] >> (pos & 7)) & 1;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -734,7 +684,7 @@ yk_k_state(const YkSlotDev* __restrict__ slots, int slot, int32_t* smoothMap, in
             const int lx = i % 65, ly = i / 65, x = X0 + lx, y = Y0 + ly;
             if (lx >= xMax || ly >= yMax || x > w || y > h) continue;
             int v = 0;
-            if (!(x & 3) && !(y & 3)) v = ((S.cornerMask[(size_t)(y >> 2) * S.cornerWords + (x >> 7)] >> ((x >> 2) & 31)) & 1u) ? 255 : 0;
+            if (!(x & 3) && !(y & 3)) v = S.touchMap[(size_t)(y >> 2) * S.latW + (x >> 2)] ? 255 : 0;
             mappedRGB[(size_t)y * (w + 1) + x] = v;
         }
     }
@@ -776,6 +726,28 @@ static __device__ __forceinline__ unsigned yk_r1_cells(const YkSlotDev& S, int x
     const int cx = x >> 2, cy = y >> 2;
     const unsigned r0 = S.cellMask[(size_t)cy * S.nbx + (cx >> 4)], r1 = S.cellMask[(size_t)(cy + 1) * S.nbx + (cx >> 4)];
     return (~(((r0 >> (cx & 15)) & 3u) | (((r1 >> (cx & 15)) & 3u) << 2))) & 15u;
+}
+
+// block-wide exclusive scan of one int per thread (used by the R1 offset scan)
+static __device__ int yk_block_exclusive(int v, int* sWarp, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(YK_FULL, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) sWarp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int x = lane < nw ? sWarp[lane] : 0, xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(YK_FULL, xi, d); if (lane >= d) xi += t; }
+        sWarp[lane] = xi - x;
+        if (lane == 31) sWarp[32] = xi;
+    }
+    __syncthreads();
+    total = sWarp[32];
+    const int r = sWarp[warp] + inc - v;
+    __syncthreads();
+    return r;
 }
 
 __global__ void __launch_bounds__(256)
@@ -893,17 +865,16 @@ yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, int plane, int mod
 void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st) {
     YK_LAUNCH(yk_k_analyze, dim3(nRegions, nSlots), dim3(YK_THREADS), 0, st, slotsDev, slot0, run);
 }
-void yk_launch_emit_count(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st) {
-    YK_LAUNCH(yk_k_emit_count, dim3(nRegions, nSlots), dim3(YK_THREADS), 0, st, slotsDev, slot0, run);
+void yk_launch_fold_touch(const YkSlotDev* slotsDev, int slot0, int nSlots, int nWords, cudaStream_t st) {
+    YK_LAUNCH(yk_k_fold_touch, dim3((nWords + 255) / 256, nSlots), dim3(256), 0, st, slotsDev, slot0, nWords);
 }
-void yk_launch_scan(const YkSlotDev* slotsDev, int slot0, int nSlots, const YkRun& run, cudaStream_t st) {
-    YK_LAUNCH(yk_k_scan, dim3(YK_NPASS + 1, nSlots), dim3(1024), 0, st, slotsDev, slot0, run);
+void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int totalUnits, const YkRun& run, cudaStream_t st) {
+    const int per = YK_THREADS / 32;
+    YK_LAUNCH(yk_k_emit, dim3((totalUnits + per - 1) / per, nSlots), dim3(YK_THREADS), 0, st, slotsDev, slot0, run, totalUnits);
 }
-void yk_launch_emit_write(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st) {
-    YK_LAUNCH(yk_k_emit_write, dim3(nRegions, nSlots), dim3(YK_THREADS), 0, st, slotsDev, slot0, run);
-}
-void yk_launch_range1d(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, cudaStream_t st) {
-    YK_LAUNCH(yk_k_range1d, dim3(nRegions, nSlots), dim3(YK_THREADS), 0, st, slotsDev, slot0);
+void yk_launch_range1d(const YkSlotDev* slotsDev, int slot0, int nSlots, int nSegs, cudaStream_t st) {
+    const int per = YK_THREADS / 32;
+    YK_LAUNCH(yk_k_range1d, dim3((nSegs + per - 1) / per, nSlots), dim3(YK_THREADS), 0, st, slotsDev, slot0, nSegs);
 }
 void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t* smoothMap, int32_t* mipmapMask,
                      int32_t* mappedRGB, int32_t* recon0, int32_t* recon1, int32_t* recon2, cudaStream_t st) {
