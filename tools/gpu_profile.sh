@@ -1,0 +1,10 @@
+#!/bin/bash
+# Usage (on the GPU box, from the repo root): tools/gpu_profile.sh TAG [kernel-regex]
+# Plain bench run first (must exit 0), then the ncu launch list and one full capture, as B200_PROFILING.md asks.
+TAG=${1:-rXX}; KRE=${2:-yk_k_}
+B="python bench.py --steps 6 --warmup 3 --e2e-steps 0 --no-cpu --no-prewarm"
+mkdir -p gpurun_out
+$B > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 40 --csv --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/ncu_list_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:$KRE -s 9 -c 3 -o gpurun_out/prof_$TAG $B > gpurun_out/ncu_full_$TAG.log 2>&1
+tail -2 gpurun_out/ncu_full_$TAG.log

@@ -169,6 +169,7 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
             if ((rc = dev_alloc(s, &s.d.rgb[p], 3 * ((W >> g.shx) + 1) * ((H >> g.shy) + 1)))) return rc;
         }
         if ((rc = dev_alloc(s, &s.d.latRGB, latW * latH * 3))) return rc;
+        if ((rc = dev_alloc(s, &s.d.r2Off, (H / 8 + 1) * nbx))) return rc;
         for (int p = 0; p < 3; p++) {
             if ((rc = dev_alloc(s, &s.d.r2Idx[p], W * H))) return rc;
             if ((rc = dev_alloc(s, &s.d.r2Type[p], 3 * (W / 8 + 1) * (H / 8 + 1)))) return rc;
@@ -356,15 +357,19 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     if ((rc = upload_slots(c, slot0, nSlots))) return rc;
     if (needFold) { yk_launch_fold_touch(c->slotsDev, slot0, nSlots, a.d.latW * a.d.latH, c->stream); c->launches++; }
     if (run.nPasses > 0 || run.doAlpha) { YkTimed t(c, 0); yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
-    if (doEmit && run.nPasses > 0) {
-        int totalUnits = 0;
-        for (int p = 0; p < run.nPasses; p++) {
-            const YkPassGeom& g = kGeom[run.passId[p]];
-            totalUnits += ((a.d.w + g.bw - 1) / g.bw) * ((a.d.h + g.bh - 1) / g.bh);
-        }
-        YkTimed t(c, 1); yk_launch_emit(c->slotsDev, slot0, nSlots, totalUnits, run, c->stream); c->launches++;
+    {
+        // one scan/compaction kernel: rgbStream emission of the run's passes + offsets of the R2 segments
+        int gradGroups = 0;
+        if (doEmit)
+            for (int p = 0; p < run.nPasses; p++) {
+                const YkPassGeom& g = kGeom[run.passId[p]];
+                gradGroups += (((a.d.w + g.bw - 1) / g.bw) * ((a.d.h + g.bh - 1) / g.bh) + 31) / 32;
+            }
+        const int nSegs = (a.d.h / 8) * a.d.nbx;
+        const int r2Groups = doR2 ? (nSegs + 1023) / 1024 : 0;
+        if (gradGroups + r2Groups > 0) { YkTimed t(c, 1); yk_launch_emit(c->slotsDev, slot0, nSlots, gradGroups, r2Groups, run, c->stream); c->launches++; }
+        if (doR2 && nSegs > 0) { YkTimed t(c, 4); yk_launch_range1d(c->slotsDev, slot0, nSlots, nSegs, c->stream); c->launches++; }
     }
-    if (doR2) { YkTimed t(c, 4); yk_launch_range1d(c->slotsDev, slot0, nSlots, (a.d.h / 8) * a.d.nbx, c->stream); c->launches++; }
     CK(cudaGetLastError());
     for (int i = slot0; i < slot0 + nSlots; i++) {
         YkSlotHost& s = c->slots[i];

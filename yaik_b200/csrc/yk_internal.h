@@ -53,6 +53,7 @@ struct YkSlotDev {
     uint8_t*  latRGB;               // [latH][latW][3]  CompressF(Round6(clamped pixel),250) at every lattice point
     // ---- range stage R2 (DynamicTileCompressor)
     unsigned long long* r2Status;   // [h/8][nbx] per 8-tile segment: look-back word (chunks << 32 | codedTiles << 2 | flag)
+    uint2*    r2Off;            // [h/8][nbx] exclusive offsets of each segment: x = 16-byte chunks, y = coded tiles
     uint8_t*  r2Idx[3];
     uint8_t*  r2Type[3];
     // ---- range stage R1 (DynamicTileEncode)
@@ -78,7 +79,7 @@ extern "C++" {
 // launch wrappers (yk_kernels.cu); `slots` is a device array, grid.y indexes it from slot0
 void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st);
 void yk_launch_fold_touch(const YkSlotDev* slotsDev, int slot0, int nSlots, int nWords, cudaStream_t st);
-void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int totalUnits, const YkRun& run, cudaStream_t st);
+void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int gradGroups, int r2Groups, const YkRun& run, cudaStream_t st);
 void yk_launch_range1d(const YkSlotDev* slotsDev, int slot0, int nSlots, int nSegs, cudaStream_t st);
 void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t* smoothMap, int32_t* mipmapMask,
                      int32_t* mappedRGB, int32_t* recon0, int32_t* recon1, int32_t* recon2, cudaStream_t st);

@@ -140,44 +140,55 @@ static __device__ __forceinline__ unsigned yk_macro_pass(const uint8_t (*pix)[65
     const int loWide = -(4 * N + N / 2 - 1), hiWide = hiT + 3 * N;
     const unsigned gmask = (G == 32) ? YK_FULL : (((1u << (G & 31)) - 1u) << (t * G));
 
-    int cr[3][4];
+    // this lane's two quads
+    const int q0 = j, q1 = j + G;
+    const int dxA = 4 * (q0 % QR), dyA = q0 / QR, dxB = 4 * (q1 % QR), dyB = q1 / QR;
+    const int offA = (ly0 + dyA) * YK_RS + lx0 + dxA, offB = (ly0 + dyB) * YK_RS + lx0 + dxB;
+
+    int cr[3][4];                                       // TL TR BL BR, clamped at the image edge by the staging (EC.cpp:3845-3868)
+    bool resolved = !active;
+    int umin = INT_MAX, umax = INT_MIN;
+    {
+        // cheap rejection first: one quad of one channel with the raw corners proves most non-gradient tiles hopeless
+        const uint8_t* p = pix[0];
+        cr[0][0] = p[ly0 * YK_RS + lx0]; cr[0][1] = p[ly0 * YK_RS + lx0 + TW];
+        cr[0][2] = p[(ly0 + TH) * YK_RS + lx0]; cr[0][3] = p[(ly0 + TH) * YK_RS + lx0 + TW];
+        if (active)
+            yk_quad<N>(p, offA, dxA, dyA, cr[0][0] * N + R * N, TH * (cr[0][1] - cr[0][0]), TW * (cr[0][2] - cr[0][0]),
+                       cr[0][0] - cr[0][1] - cr[0][2] + cr[0][3], umin, umax);
+        const unsigned bH = __ballot_sync(YK_FULL, (umin < loWide) || (umax >= hiWide));
+        if (bH & gmask) resolved = true;
+        if (!__any_sync(YK_FULL, !resolved)) return claimed;
+    }
 #pragma unroll
-    for (int c = 0; c < 3; c++) {                       // TL TR BL BR, clamped at the image edge by the staging (EC.cpp:3845-3868)
+    for (int c = 1; c < 3; c++) {
         const uint8_t* p = pix[c];
         cr[c][0] = p[ly0 * YK_RS + lx0]; cr[c][1] = p[ly0 * YK_RS + lx0 + TW];
         cr[c][2] = p[(ly0 + TH) * YK_RS + lx0]; cr[c][3] = p[(ly0 + TH) * YK_RS + lx0 + TW];
     }
-    bool accepted = false, resolved = !active;
+    bool accepted = false;
 #pragma unroll
     for (int fam = 0; fam < 3; fam++) {
-        int A3[3], B[3], C[3], D[3];
+        if (fam > 0) { umin = INT_MAX; umax = INT_MIN; }
+        if (!resolved) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            int tl, tr, bl, br;
-            if (fam == 0) { tl = cr[c][0]; tr = cr[c][1]; bl = cr[c][2]; br = cr[c][3]; }
-            else if (fam == 1) { tl = yk_round6(cr[c][0]); tr = yk_round6(cr[c][1]); bl = yk_round6(cr[c][2]); br = yk_round6(cr[c][3]); }
-            else { tl = yk_round6p(cr[c][0]); tr = yk_round6p(cr[c][1]); bl = yk_round6p(cr[c][2]); br = yk_round6p(cr[c][3]); }
-            A3[c] = tl * N + R * N; B[c] = TH * (tr - tl); C[c] = TW * (bl - tl); D[c] = tl - tr - bl + br;
+            for (int c = 0; c < 3; c++) {
+                int tl, tr, bl, br;
+                if (fam == 0) { tl = cr[c][0]; tr = cr[c][1]; bl = cr[c][2]; br = cr[c][3]; }
+                else if (fam == 1) { tl = yk_round6(cr[c][0]); tr = yk_round6(cr[c][1]); bl = yk_round6(cr[c][2]); br = yk_round6(cr[c][3]); }
+                else { tl = yk_round6p(cr[c][0]); tr = yk_round6p(cr[c][1]); bl = yk_round6p(cr[c][2]); br = yk_round6p(cr[c][3]); }
+                const int A3 = tl * N + R * N, B = TH * (tr - tl), C = TW * (bl - tl), D = tl - tr - bl + br;
+                if (!(fam == 0 && c == 0)) yk_quad<N>(pix[c], offA, dxA, dyA, A3, B, C, D, umin, umax);     // family 0 / channel 0 / quad A is already in
+                yk_quad<N>(pix[c], offB, dxB, dyB, A3, B, C, D, umin, umax);
+            }
         }
-        int umin = INT_MAX, umax = INT_MIN;
-        bool famDead = false;
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int q = j + G * k, dx0 = 4 * (q % QR), dy = q / QR;
-            if (!resolved && !famDead) {
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    yk_quad<N>(pix[c], (ly0 + dy) * YK_RS + lx0 + dx0, dx0, dy, A3[c], B[c], C[c], D[c], umin, umax);
-            }
-            const bool dT = (umin < 0) || (umax >= hiT);
-            const bool dR = (umin < loR) || (umax >= hiT + loR);
-            const unsigned bT = __ballot_sync(YK_FULL, dT), bR = __ballot_sync(YK_FULL, dR);
-            famDead = ((bT & gmask) != 0u) && ((bR & gmask) != 0u);
-            if (fam == 0) {
-                const unsigned bH = __ballot_sync(YK_FULL, (umin < loWide) || (umax >= hiWide));
-                if (bH & gmask) resolved = true;
-            }
-            if (k == 0 && !__any_sync(YK_FULL, !resolved && !famDead)) break;
+        const bool dT = (umin < 0) || (umax >= hiT);
+        const bool dR = (umin < loR) || (umax >= hiT + loR);
+        const unsigned bT = __ballot_sync(YK_FULL, dT), bR = __ballot_sync(YK_FULL, dR);
+        const bool famDead = ((bT & gmask) != 0u) && ((bR & gmask) != 0u);
+        if (fam == 0) {
+            const unsigned bH = __ballot_sync(YK_FULL, (umin < loWide) || (umax >= hiWide));
+            if (bH & gmask) resolved = true;            // no family can accept this tile
         }
         if (!resolved && !famDead) { accepted = true; resolved = true; }         // EC.cpp:3998: any surviving variant accepts
         if (fam < 2 && !__any_sync(YK_FULL, !resolved)) break;
@@ -212,7 +223,7 @@ static __device__ __forceinline__ unsigned yk_macro_pass(const uint8_t (*pix)[65
     return claimed;
 }
 
-__global__ void __launch_bounds__(YK_THREADS, 3)
+__global__ void __launch_bounds__(YK_THREADS, 4)
 yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
     __shared__ __align__(16) uint8_t pix[3][65 * YK_RS];
     __shared__ uint32_t sCell[16];
@@ -220,9 +231,10 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
     __shared__ int sStat[YK_NPASS][YK_ST_STRIDE];
     __shared__ uint32_t sTouch[17 * 17];
     __shared__ uint32_t sAlpha;
+    __shared__ int sNext;
 
     const YkSlotDev& S = slots[slot0 + blockIdx.y];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int w = S.w, h = S.h, nbx = S.nbx;
     const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
     const int X0 = bx * YK_REGION, Y0 = by * YK_REGION;
@@ -241,7 +253,7 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
     for (int i = tid; i < YK_NPASS * 8; i += YK_THREADS) (&sBits[0][0])[i] = 0;
     for (int i = tid; i < YK_NPASS * YK_ST_STRIDE; i += YK_THREADS) (&sStat[0][0])[i] = 0;
     for (int i = tid; i < 17 * 17; i += YK_THREADS) sTouch[i] = 0;
-    if (tid == 0) sAlpha = 0;
+    if (tid == 0) { sAlpha = 0; sNext = 0; }
 
     // ---- alpha plane first (its loads stay in flight while the colour planes are staged)
     const bool doAlpha = run.doAlpha && S.nPlanes == 4;
@@ -281,7 +293,11 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
 
     // ---- the cascade: each warp owns two 16x16 macro tiles and runs all passes on them without block barriers
     const int R = run.rejectFactor;
-    for (int m = warp; m < 16; m += YK_THREADS / 32) {
+    for (;;) {
+        int m = 0;
+        if (lane == 0) m = atomicAdd(&sNext, 1);        // macro tiles are handed out dynamically: their cost varies a lot
+        m = __shfl_sync(YK_FULL, m, 0);
+        if (m >= 16) break;
         const int mx = m & 3, my = m >> 2;
         unsigned claimed = 0;
 #pragma unroll
@@ -462,57 +478,109 @@ static __device__ __forceinline__ int yk_pos_s(const YkGeomS& g, int nSwzX, int 
     return (((y >> g.lbh) * nSwzX + (x >> g.lbw)) * g.bits) + (((y & ((1 << g.lbh) - 1)) >> g.shy) << (g.lbw - g.shx)) + ((x & ((1 << g.lbw) - 1)) >> g.shx);
 }
 
-__global__ void __launch_bounds__(YK_THREADS)
-yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int totalUnits) {
+// emit mask (which of TL,TR,BL,BR the accepted tile at (gtx,gty), stream position myPos, emits) from the touch words
+static __device__ __forceinline__ int yk_emit_mask(const YkSlotDev& S, const YkGeomS& g, int nSwzX, int rp, int gtx, int gty, int myPos) {
+    int m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int LX = gtx + (k & 1), LY = gty + (k >> 1);                       // lattice point in tile units
+        const uint32_t word = __ldg(&S.touchMap[(size_t)((LY << g.shy) >> 2) * S.latW + ((LX << g.shx) >> 2)]);
+        if (word & 0x80000000u) continue;                                        // claimed by an earlier launch
+        if (((__ffs((int)(word & 0x0FFFFFFFu)) - 1) >> 2) != rp) continue;       // an earlier pass of this launch got it
+        const unsigned nib = (word >> (4 * rp)) & 15u;                           // roles present in this pass
+        bool owner = true;
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++)
+            if (k2 != k && ((nib >> k2) & 1u) && yk_pos_s(g, nSwzX, LX - (k2 & 1), LY - (k2 >> 1)) < myPos) owner = false;
+        if (owner) m |= 1 << k;
+    }
+    return m;
+}
+
+// One warp per swizzle block (lane = up to 2 tiles), one 1024-thread CTA per group of 32 consecutive blocks of a pass.
+// Groups are taken in stream order (ticket) and chained by one look-back per CTA, so the chain is nUnits/32 long.
+// Tickets past the gradient groups scan the DynamicTileCompressor segments (r2Off), 1024 segments per CTA.
+#define YK_EMIT_THREADS 1024
+__global__ void __launch_bounds__(YK_EMIT_THREADS)
+yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGroups, int r2Groups) {
+    __shared__ int sTicket;
+    __shared__ unsigned sA[33], sB[33];
     const YkSlotDev& S = slots[slot0 + blockIdx.y];
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int w = S.w, h = S.h;
-    int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(&S.hdr[YK_HD_TICKET_EMIT], 1);
-    ticket = __shfl_sync(YK_FULL, ticket, 0);
-    if (ticket >= totalUnits) return;
-    // ticket -> (pass position, swizzle block)
-    int rp = 0, u = ticket, nUnits = 0, nSwzX = 0;
+    if (tid == 0) sTicket = atomicAdd(&S.hdr[YK_HD_TICKET_EMIT], 1);
+    __syncthreads();
+    const int ticket = sTicket;
+    if (ticket >= gradGroups + r2Groups) return;
+    if (ticket >= gradGroups) {
+        // ---- offsets of DynamicTileCompressor's 8-tile segments in its row-major tile order (EC.cpp:8412-8413)
+        const int grp = ticket - gradGroups, nbx = S.nbx, nSegs = (h >> 3) * nbx;
+        const int seg = grp * YK_EMIT_THREADS + tid;
+        unsigned chunks = 0, tiles = 0;
+        if (seg < nSegs) {
+            const int bx = seg % nbx, ty = seg / nbx;
+            uint32_t r0 = S.cellMask[(size_t)(2 * ty) * nbx + bx], r1 = S.cellMask[(size_t)(2 * ty + 1) * nbx + bx];
+            const int cellsIn = (w - bx * 64) >> 2;
+            if (cellsIn < 16) { r0 |= (0xFFFFu << cellsIn) & 0xFFFFu; r1 |= (0xFFFFu << cellsIn) & 0xFFFFu; }
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                const int n = 4 - __popc(((r0 >> (2 * x)) & 3u) | (((r1 >> (2 * x)) & 3u) << 2));
+                chunks += n; tiles += (n > 0);
+            }
+        }
+        unsigned ic = chunks, it = tiles;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned t0 = __shfl_up_sync(YK_FULL, ic, d), t1 = __shfl_up_sync(YK_FULL, it, d);
+            if (lane >= d) { ic += t0; it += t1; }
+        }
+        if (lane == 31) { sA[warp] = ic; sB[warp] = it; }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned a = sA[lane], b2 = sB[lane], ia = a, ib = b2;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned t0 = __shfl_up_sync(YK_FULL, ia, d), t1 = __shfl_up_sync(YK_FULL, ib, d);
+                if (lane >= d) { ia += t0; ib += t1; }
+            }
+            const unsigned totC = __shfl_sync(YK_FULL, ia, 31), totT = __shfl_sync(YK_FULL, ib, 31);
+            const unsigned long long base = yk_lookback64(S.r2Status, grp, totC, totT);
+            const unsigned bc = (unsigned)(base >> 32), bt = (unsigned)(base & 0xFFFFFFFFull);
+            sA[lane] = bc + ia - a; sB[lane] = bt + ib - b2;
+            if (grp == r2Groups - 1 && lane == 0) { S.hdr[YK_HD_R2_CHUNKS] = (int)(bc + totC); S.hdr[YK_HD_R2_TILES] = (int)(bt + totT); }
+        }
+        __syncthreads();
+        if (seg < nSegs) S.r2Off[seg] = make_uint2(sA[warp] + ic - chunks, sB[warp] + it - tiles);
+        return;
+    }
+    // ticket -> (pass position, group of 32 swizzle blocks)
+    int rp = 0, grp = ticket, nUnits = 0, nSwzX = 0, nGroups = 0;
     YkGeomS g = yk_geom_s(run.passId[0]);
     for (;;) {
         g = yk_geom_s(run.passId[rp]);
         nSwzX = (w + (1 << g.lbw) - 1) >> g.lbw;
         nUnits = nSwzX * ((h + (1 << g.lbh) - 1) >> g.lbh);
-        if (u < nUnits) break;
-        u -= nUnits; rp++;
+        nGroups = (nUnits + 31) >> 5;
+        if (grp < nGroups) break;
+        grp -= nGroups; rp++;
     }
     const int pid = run.passId[rp];
-    const int sbx = u % nSwzX, sby = u / nSwzX;
+    const int u = grp * 32 + warp;
     const int tprShift = g.lbw - g.shx;                                     // log2(tiles per row of the swizzle block)
-    // accept bits of the block
-    unsigned long long acc;
-    if (g.bits == 16) acc = reinterpret_cast<const uint16_t*>(S.bitmap[pid])[u];
-    else if (g.bits == 32) acc = reinterpret_cast<const uint32_t*>(S.bitmap[pid])[u];
-    else acc = reinterpret_cast<const uint32_t*>(S.bitmap[pid])[2 * u] | ((unsigned long long)reinterpret_cast<const uint32_t*>(S.bitmap[pid])[2 * u + 1] << 32);
-    int mask[2] = { 0, 0 }, gtxv[2] = { 0, 0 }, gtyv[2] = { 0, 0 };
+    unsigned long long acc = 0;
+    int tx0 = 0, ty0 = 0;
+    if (u < nUnits) {
+        if (g.bits == 16) acc = __ldg(&reinterpret_cast<const uint16_t*>(S.bitmap[pid])[u]);
+        else if (g.bits == 32) acc = __ldg(&reinterpret_cast<const uint32_t*>(S.bitmap[pid])[u]);
+        else { uint2 v = __ldg(&reinterpret_cast<const uint2*>(S.bitmap[pid])[u]); acc = v.x | ((unsigned long long)v.y << 32); }
+        tx0 = ((u % nSwzX) << g.lbw) >> g.shx; ty0 = ((u / nSwzX) << g.lbh) >> g.shy;
+    }
+    int mask[2] = { 0, 0 };
 #pragma unroll
     for (int s2 = 0; s2 < 2; s2++) {
         const int li = lane + 32 * s2;
-        if (li < g.bits && ((acc >> li) & 1ull)) {
-            const int gtx = ((sbx << g.lbw) >> g.shx) + (li & ((1 << tprShift) - 1)), gty = ((sby << g.lbh) >> g.shy) + (li >> tprShift);
-            gtxv[s2] = gtx; gtyv[s2] = gty;
-            const int myPos = u * g.bits + li;
-            int m = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int LX = gtx + (k & 1), LY = gty + (k >> 1);                       // lattice point in tile units
-                const uint32_t word = S.touchMap[(size_t)((LY << g.shy) >> 2) * S.latW + ((LX << g.shx) >> 2)];
-                if (word & 0x80000000u) continue;                                        // claimed by an earlier launch
-                if (((__ffs((int)(word & 0x0FFFFFFFu)) - 1) >> 2) != rp) continue;       // an earlier pass of this launch got it
-                const unsigned nib = (word >> (4 * rp)) & 15u;                           // roles present in this pass
-                bool owner = true;
-#pragma unroll
-                for (int k2 = 0; k2 < 4; k2++)
-                    if (k2 != k && ((nib >> k2) & 1u) && yk_pos_s(g, nSwzX, LX - (k2 & 1), LY - (k2 >> 1)) < myPos) owner = false;
-                if (owner) m |= 1 << k;
-            }
-            mask[s2] = m;
-        }
+        if (li < g.bits && ((acc >> li) & 1ull))
+            mask[s2] = yk_emit_mask(S, g, nSwzX, rp, tx0 + (li & ((1 << tprShift) - 1)), ty0 + (li >> tprShift), u * g.bits + li);
     }
     // exclusive prefix of the emitted bytes inside the block (tile order = lane order, second half after the first)
     const unsigned c0 = 3u * __popc(mask[0]), c1 = 3u * __popc(mask[1]);
@@ -523,19 +591,32 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int totalUn
         if (lane >= d) { i0 += t0; i1 += t1; }
     }
     const unsigned tot0 = __shfl_sync(YK_FULL, i0, 31), tot1 = __shfl_sync(YK_FULL, i1, 31);
-    const unsigned base = yk_lookback32(S.emitStatus[pid], u, tot0 + tot1);
-    if (u == nUnits - 1 && lane == 0) S.hdr[YK_HD_PASS0 + pid * YK_ST_STRIDE + YK_ST_RGBBYTES] = (int)(base + tot0 + tot1);
+    if (lane == 0) sA[warp] = tot0 + tot1;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned a = sA[lane], ia = a;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned t0 = __shfl_up_sync(YK_FULL, ia, d); if (lane >= d) ia += t0; }
+        const unsigned tot = __shfl_sync(YK_FULL, ia, 31);
+        const unsigned base = yk_lookback32(S.emitStatus[pid], grp, tot);
+        sA[lane] = base + ia - a;
+        if (grp == nGroups - 1 && lane == 0) S.hdr[YK_HD_PASS0 + pid * YK_ST_STRIDE + YK_ST_RGBBYTES] = (int)(base + tot);
+    }
+    __syncthreads();
+    const unsigned base = sA[warp];
     uint8_t* out = S.rgb[pid];
 #pragma unroll
     for (int s2 = 0; s2 < 2; s2++) {
         if (mask[s2]) {
+            const int li = lane + 32 * s2;
+            const int gtx = tx0 + (li & ((1 << tprShift) - 1)), gty = ty0 + (li >> tprShift);
             unsigned off = base + (s2 ? tot0 + i1 - c1 : i0 - c0);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if ((mask[s2] >> k) & 1) {                                             // TL, TR, BL, BR (EC.cpp:4115-4132)
-                    const int gx = ((gtxv[s2] + (k & 1)) << g.shx) >> 2, gy = ((gtyv[s2] + (k >> 1)) << g.shy) >> 2;
-                    const uint8_t* s = S.latRGB + ((size_t)gy * S.latW + gx) * 3;
-                    out[off] = s[0]; out[off + 1] = s[1]; out[off + 2] = s[2];
+                    const int gx = ((gtx + (k & 1)) << g.shx) >> 2, gy = ((gty + (k >> 1)) << g.shy) >> 2;
+                    const uint8_t* sp = S.latRGB + ((size_t)gy * S.latW + gx) * 3;
+                    out[off] = sp[0]; out[off + 1] = sp[1]; out[off + 2] = sp[2];
                     off += 3;
                 }
             }
@@ -545,7 +626,7 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int totalUn
 
 // ------------------------------------------------------------------------------------------------------------------
 // DynamicTileCompressor (EC.cpp:8398-8522).  One warp per 8-tile segment (one tile row of one 64-pixel column) in the
-// reference's row-major tile order; stream offsets by decoupled look-back; per tile and plane one pass with lane = 2 pixels.
+// reference's row-major tile order; stream offsets were scanned by yk_k_emit; per tile and plane one pass with lane = 2 pixels.
 __global__ void __launch_bounds__(YK_THREADS)
 yk_k_range1d(const YkSlotDev* __restrict__ slots, int slot0, int nSegs) {
     __shared__ uint32_t hist[YK_THREADS / 32][256];
@@ -553,9 +634,7 @@ yk_k_range1d(const YkSlotDev* __restrict__ slots, int slot0, int nSegs) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int w = S.w, h = S.h, nbx = S.nbx;
     for (int i = lane; i < 256; i += 32) hist[warp][i] = 0;
-    int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(&S.hdr[YK_HD_TICKET_R2], 1);
-    ticket = __shfl_sync(YK_FULL, ticket, 0);
+    const int ticket = blockIdx.x * (YK_THREADS / 32) + warp;
     if (ticket >= nSegs) return;
     const int bx = ticket % nbx, ty = ticket / nbx;                 // tile row ty, 64-pixel column bx
     const int X0 = bx * 64, Y0 = ty * 8;
@@ -565,15 +644,11 @@ yk_k_range1d(const YkSlotDev* __restrict__ slots, int slot0, int nSegs) {
         if (cellsIn < 16) { r0 |= (0xFFFFu << cellsIn) & 0xFFFFu; r1 |= (0xFFFFu << cellsIn) & 0xFFFFu; }
     }
     // quadrant needs coding iff its top-left map pixel is 0 (EC.cpp:8420-8430) == its 4x4 cell is unclaimed
-    int chunks = 0, tiles = 0;
+    int chunks = 0;
 #pragma unroll
-    for (int x = 0; x < 8; x++) {
-        const int n = 4 - __popc(((r0 >> (2 * x)) & 3u) | (((r1 >> (2 * x)) & 3u) << 2));
-        chunks += n; tiles += (n > 0);
-    }
-    const unsigned long long basePacked = yk_lookback64(S.r2Status, ticket, (unsigned)chunks, (unsigned)tiles);
-    int chunkOff = (int)(basePacked >> 32), tileOff = (int)(basePacked & 0xFFFFFFFFull);
-    if (ticket == nSegs - 1 && lane == 0) { S.hdr[YK_HD_R2_CHUNKS] = chunkOff + chunks; S.hdr[YK_HD_R2_TILES] = tileOff + tiles; }
+    for (int x = 0; x < 8; x++) chunks += 4 - __popc(((r0 >> (2 * x)) & 3u) | (((r1 >> (2 * x)) & 3u) << 2));
+    const uint2 off = __ldg(&S.r2Off[ticket]);              // scanned by yk_k_emit
+    int chunkOff = (int)off.x, tileOff = (int)off.y;
     if (chunks == 0) return;
     __syncwarp();
 
@@ -868,9 +943,8 @@ void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRe
 void yk_launch_fold_touch(const YkSlotDev* slotsDev, int slot0, int nSlots, int nWords, cudaStream_t st) {
     YK_LAUNCH(yk_k_fold_touch, dim3((nWords + 255) / 256, nSlots), dim3(256), 0, st, slotsDev, slot0, nWords);
 }
-void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int totalUnits, const YkRun& run, cudaStream_t st) {
-    const int per = YK_THREADS / 32;
-    YK_LAUNCH(yk_k_emit, dim3((totalUnits + per - 1) / per, nSlots), dim3(YK_THREADS), 0, st, slotsDev, slot0, run, totalUnits);
+void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int gradGroups, int r2Groups, const YkRun& run, cudaStream_t st) {
+    YK_LAUNCH(yk_k_emit, dim3(gradGroups + r2Groups, nSlots), dim3(YK_EMIT_THREADS), 0, st, slotsDev, slot0, run, gradGroups, r2Groups);
 }
 void yk_launch_range1d(const YkSlotDev* slotsDev, int slot0, int nSlots, int nSegs, cudaStream_t st) {
     const int per = YK_THREADS / 32;
