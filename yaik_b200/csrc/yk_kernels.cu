@@ -28,10 +28,8 @@ static __device__ __forceinline__ int yk_round6p(int v) { v = min(v + 1, 255); i
 static __device__ __forceinline__ int yk_compress250(int v) { return (v * 250 + 127) / 255; }                          // CompressF(v, colorCompressionQuad), EC.cpp:3191-3194
 
 struct YkGeomC { int shx, shy, bw, bh, bits; };
-static __device__ __forceinline__ YkGeomC yk_geom(int pid) {
-    const YkGeomC t[YK_NPASS] = YK_PASS_TABLE;
-    return t[pid];
-}
+__constant__ YkGeomC yk_geom_tab[YK_NPASS] = YK_PASS_TABLE;
+static __device__ __forceinline__ YkGeomC yk_geom(int pid) { return yk_geom_tab[pid]; }
 
 // stream position (== bitmap bit index) of the tile at global tile coords (gtx, gty), EC.cpp:3801-3828, 4227-4234
 static __device__ __forceinline__ int yk_tile_pos(const YkGeomC& g, int w, int gtx, int gty) {
@@ -114,6 +112,45 @@ template <int FAM> static __device__ __forceinline__ int yk_family(int v) {
     return FAM == 0 ? v : (FAM == 1 ? yk_round6(v) : yk_round6p(v));
 }
 
+// Cheap rejection of all 41 tiles (1 + 2 + 2 + 4 + 8 + 8 + 16 over the seven shapes) of a 16x16 macro tile before the
+// cascade: lane = tile, one channel, the quad at the tile centre, raw corners.  A pixel whose raw-family U is outside
+// [loWide, hiWide) cannot be accepted by any of the six variants, so a cleared bit is a proven rejection; a set bit only
+// means "run the real test".  Bit (start(pid) + t) of the result belongs to tile t of pass id pid.
+static __device__ __forceinline__ unsigned long long yk_pretest(const uint8_t (*pix)[65 * YK_RS], int mlx, int mly, int X0, int Y0,
+                                                                int w, int h, int R, unsigned claimed) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long P = 0;
+#pragma unroll
+    for (int round = 0; round < 2; round++) {
+        const int ti = lane + 32 * round;
+        bool possible = false;
+        if (ti < 41) {
+            const int pid = (ti >= 1) + (ti >= 3) + (ti >= 5) + (ti >= 9) + (ti >= 17) + (ti >= 25);
+            const int t = ti - (int)((0x19110905030100ull >> (8 * pid)) & 255ull);
+            const int shx = (0x2233344 >> (4 * pid)) & 15, shy = (0x2323434 >> (4 * pid)) & 15, sh = shx + shy;
+            const int tx = t & ((16 >> shx) - 1), ty = t >> (4 - shx);
+            const int lx0 = mlx + (tx << shx), ly0 = mly + (ty << shy), TW = 1 << shx, TH = 1 << shy, N = 1 << sh;
+            const int cell = ((ty << shy) >> 2) * 4 + ((tx << shx) >> 2);
+            if (!((claimed >> cell) & 1u) && X0 + lx0 + TW <= w && Y0 + ly0 + TH <= h) {
+                const uint8_t* p = pix[0];
+                const int tl = p[ly0 * YK_RS + lx0], tr = p[ly0 * YK_RS + lx0 + TW];
+                const int bl = p[(ly0 + TH) * YK_RS + lx0], br = p[(ly0 + TH) * YK_RS + lx0 + TW];
+                const int dx0 = (TW >> 1) & ~3, dy = TH >> 1;
+                const unsigned word = *reinterpret_cast<const unsigned*>(p + (ly0 + dy) * YK_RS + lx0 + dx0);
+                const int B = (tr - tl) << shy, C = (bl - tl) << shx, D = tl - tr - bl + br;
+                const int step = B + D * dy;
+                const int s0 = (tl << sh) + (R << sh) + B * dx0 + dy * (C + D * dx0);
+                const int u0 = s0 - (int)((word & 255u) << sh), u1 = s0 + step - (int)(((word >> 8) & 255u) << sh);
+                const int u2 = s0 + 2 * step - (int)(((word >> 16) & 255u) << sh), u3 = s0 + 3 * step - (int)((word >> 24) << sh);
+                const int umin = min(min(u0, u1), min(u2, u3)), umax = max(max(u0, u1), max(u2, u3));
+                possible = !(umin < -(4 * N + N / 2 - 1) || umax >= (2 * R + 1) * N + 3 * N);
+            }
+        }
+        P |= (unsigned long long)__ballot_sync(YK_FULL, possible) << (32 * round);
+    }
+    return P;
+}
+
 // One FittingQuadSmooth pass over one 16x16 macro tile, by one warp.  Every tile shape of the cascade nests inside an
 // aligned 16x16 macro tile, and eligibility (EC.cpp:3871-3875) only looks at cells of the same macro tile, so the whole
 // 7-pass cascade of a macro tile is independent of every other macro tile: no block barrier between passes.
@@ -122,7 +159,7 @@ template <int FAM> static __device__ __forceinline__ int yk_family(int v) {
 // warp-uniform and returned updated.
 template <int SHX, int SHY, int BW, int BH>
 static __device__ __forceinline__ unsigned yk_macro_pass(const uint8_t (*pix)[65 * YK_RS], uint32_t* sBits, int* sStat, uint32_t* sTouch,
-                                                         int rp, int mlx, int mly, int X0, int Y0, int w, int h, int yOrg, int R, unsigned claimed) {
+                                                         int rp, int mlx, int mly, int X0, int Y0, int w, int h, int yOrg, int R, unsigned claimed, unsigned poss) {
     constexpr int TW = 1 << SHX, TH = 1 << SHY, N = TW * TH;
     constexpr int NXM = 16 / TW, NTM = NXM * (16 / TH), G = 32 / NTM, QR = TW / 4, BITS = (BW / TW) * (BH / TH);
     const int lane = threadIdx.x & 31;
@@ -130,7 +167,8 @@ static __device__ __forceinline__ unsigned yk_macro_pass(const uint8_t (*pix)[65
     const int tx = t % NXM, ty = t / NXM;
     const int lx0 = mlx + tx * TW, ly0 = mly + ty * TH;
     const int cell = (ty * (TH / 4)) * 4 + tx * (TW / 4);
-    const bool active = !((claimed >> cell) & 1u) && (X0 + lx0 + TW <= w) && (Y0 + ly0 + TH <= h);   // EC.cpp:3818, 3826, 3871-3875
+    // eligible (EC.cpp:3818, 3826, 3871-3875; the pre-test already checked the image bounds) and not yet proven hopeless
+    const bool active = ((poss >> t) & 1u) && !((claimed >> cell) & 1u);
     if (!__any_sync(YK_FULL, active)) return claimed;
 
     const int hiT = (2 * R + 1) * N;                    // |cur - S/N| <= R            <=>  0 <= U < hiT
@@ -303,16 +341,18 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
 #pragma unroll
         for (int r = 0; r < 4; r++) claimed |= ((sCell[my * 4 + r] >> (4 * mx)) & 15u) << (4 * r);
         const unsigned claimed0 = claimed;
+        const unsigned long long P = (claimed != 0xFFFFu && run.nPasses > 0) ? yk_pretest(pix, 16 * mx, 16 * my, X0, Y0, w, h, R, claimed) : 0ull;
         for (int rp = 0; rp < run.nPasses && claimed != 0xFFFFu; rp++) {
             const int pid = run.passId[rp];
+            const unsigned poss = (unsigned)(P >> ((0x19110905030100ull >> (8 * pid)) & 255ull)) & 0xFFFFu;     // tiles of this shape
             switch (pid) {      // Convert()'s order, EC.cpp:9057-9093
-            case 0: claimed = yk_macro_pass<4, 4, 64, 64>(pix, sBits[0], sStat[0], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
-            case 1: claimed = yk_macro_pass<4, 3, 64, 64>(pix, sBits[1], sStat[1], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
-            case 2: claimed = yk_macro_pass<3, 4, 64, 64>(pix, sBits[2], sStat[2], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
-            case 3: claimed = yk_macro_pass<3, 3, 64, 64>(pix, sBits[3], sStat[3], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
-            case 4: claimed = yk_macro_pass<3, 2, 64, 32>(pix, sBits[4], sStat[4], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
-            case 5: claimed = yk_macro_pass<2, 3, 32, 64>(pix, sBits[5], sStat[5], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
-            default: claimed = yk_macro_pass<2, 2, 32, 32>(pix, sBits[6], sStat[6], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed); break;
+            case 0: if (poss & 0x1u)    claimed = yk_macro_pass<4, 4, 64, 64>(pix, sBits[0], sStat[0], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed, poss); break;
+            case 1: if (poss & 0x3u)    claimed = yk_macro_pass<4, 3, 64, 64>(pix, sBits[1], sStat[1], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed, poss); break;
+            case 2: if (poss & 0x3u)    claimed = yk_macro_pass<3, 4, 64, 64>(pix, sBits[2], sStat[2], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed, poss); break;
+            case 3: if (poss & 0xFu)    claimed = yk_macro_pass<3, 3, 64, 64>(pix, sBits[3], sStat[3], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed, poss); break;
+            case 4: if (poss & 0xFFu)   claimed = yk_macro_pass<3, 2, 64, 32>(pix, sBits[4], sStat[4], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed, poss); break;
+            case 5: if (poss & 0xFFu)   claimed = yk_macro_pass<2, 3, 32, 64>(pix, sBits[5], sStat[5], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed, poss); break;
+            default: if (poss & 0xFFFFu) claimed = yk_macro_pass<2, 2, 32, 32>(pix, sBits[6], sStat[6], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed, poss); break;
             }
         }
         if (lane < 4 && claimed != claimed0) atomicOr(&sCell[my * 4 + lane], ((claimed >> (4 * lane)) & 15u) << (4 * mx));
@@ -469,10 +509,8 @@ static __device__ unsigned long long yk_lookback64(unsigned long long* status, i
 // smallest stream position — all of which the point's touch word says.  One warp per (pass, swizzle block); swizzle
 // blocks are taken in stream order, the running rgb byte offset comes from a decoupled look-back.
 struct YkGeomS { int shx, shy, lbw, lbh, bits; };
-static __device__ __forceinline__ YkGeomS yk_geom_s(int pid) {
-    const YkGeomS t[YK_NPASS] = { {4,4,6,6,16}, {4,3,6,6,32}, {3,4,6,6,32}, {3,3,6,6,64}, {3,2,6,5,64}, {2,3,5,6,64}, {2,2,5,5,64} };
-    return t[pid];
-}
+__constant__ YkGeomS yk_geom_s_tab[YK_NPASS] = { {4,4,6,6,16}, {4,3,6,6,32}, {3,4,6,6,32}, {3,3,6,6,64}, {3,2,6,5,64}, {2,3,5,6,64}, {2,2,5,5,64} };
+static __device__ __forceinline__ YkGeomS yk_geom_s(int pid) { return yk_geom_s_tab[pid]; }
 static __device__ __forceinline__ int yk_pos_s(const YkGeomS& g, int nSwzX, int gtx, int gty) {
     const int x = gtx << g.shx, y = gty << g.shy;
     return (((y >> g.lbh) * nSwzX + (x >> g.lbw)) * g.bits) + (((y & ((1 << g.lbh) - 1)) >> g.shy) << (g.lbw - g.shx)) + ((x & ((1 << g.lbw) - 1)) >> g.shx);
