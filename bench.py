@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="contexts/streams the steps are pipelined over (1, 2, 4 or 8)")
     ap.add_argument("--no-prewarm", action="store_true", help="skip the clock-settling loop (profiling runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -192,20 +193,30 @@ def main():
     torch.cuda.set_device(local)
 
     lib = capi.load_library()          # fails loudly if the CUDA library is missing: there is no fallback
-    ctx = capi.Context(W, H, planes=CH, slots=NSLOTS, device=local, lib=lib)
-    stream = torch.cuda.Stream(device=local)
-    ctx.set_stream(stream.cuda_stream)
+    # Textures are independent, so consecutive steps are pipelined over NCTX contexts (one CUDA stream each): while
+    # one texture is in its emission / range kernels the next one's analysis kernel already runs.
+    NCTX = max(1, args.streams)
+    ctxs = [capi.Context(W, H, planes=CH, slots=NSLOTS // NCTX, device=local, lib=lib) for _ in range(NCTX)]
+    streams = [torch.cuda.Stream(device=local) for _ in range(NCTX)]
+    for c, st in zip(ctxs, streams):
+        c.set_stream(st.cuda_stream)
+    ctx, stream = ctxs[0], streams[0]
 
     # two distinct textures per rank, uploaded alternately into the 8 slots (distinct HBM addresses are what defeats L2)
     imgs = [make_image(W, H, CH, SEED_BASE + 1 + 16 * rank + i) for i in range(2)]
     for s in range(NSLOTS):
-        ctx.set_image(imgs[s % 2], s)
+        ctxs[s % NCTX].set_image(imgs[(s // NCTX) % 2], s // NCTX)
     STAGES = capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D
 
     def step(i):
-        s = i % NSLOTS
-        ctx.reset_state(s)
-        ctx.analyze(STAGES, slot0=s)
+        c = ctxs[i % NCTX]
+        s = (i // NCTX) % (NSLOTS // NCTX)
+        c.reset_state(s)
+        c.analyze(STAGES, slot0=s)
+
+    def sync_all():
+        for c in ctxs:
+            c.sync()
 
     def barrier():
         torch.cuda.synchronize(local)
@@ -214,40 +225,49 @@ def main():
         torch.cuda.synchronize(local)
 
     # untimed: the W warm-up steps asked for, plus enough work for the clocks to settle
-    with torch.cuda.stream(stream):
-        for i in range(max(args.warmup, 3)):
-            step(i)
-        ctx.sync()
-        t0 = time.perf_counter()
-        i = 0
-        while not args.no_prewarm and time.perf_counter() - t0 < 0.3:
-            for _ in range(50):
-                step(i); i += 1
-            ctx.sync()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sync_all()
+    t0 = time.perf_counter()
+    i = 0
+    while not args.no_prewarm and time.perf_counter() - t0 < 0.3:
+        for _ in range(50):
+            step(i); i += 1
+        sync_all()
 
     lib.yk_profile.argtypes = [C.c_void_p, C.c_int]
     lib.yk_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     sampler = ClockSampler(physical_gpu_index(local))
-    launches0 = ctx.launch_count()
+    launches0 = sum(c.launch_count() for c in ctxs)
     barrier()
-    lib.yk_profile(ctx.ctx, 1)
+    for c in ctxs:
+        lib.yk_profile(c.ctx, 1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    joins = [torch.cuda.Event() for _ in streams]
     sampler.sample()
     sampler.start()
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for i in range(args.steps):
-            step(i)
-        ev1.record(stream)
+    ev0.record(stream)                      # every stream starts after ev0 ...
+    for st in streams[1:]:
+        st.wait_event(ev0)
+    for i in range(args.steps):
+        step(i)
+    for st, j in zip(streams[1:], joins[1:]):
+        j.record(st)
+        stream.wait_event(j)                # ... and ev1 is recorded after all of them have finished
+    ev1.record(stream)
     sampler.sample()
     barrier()
     sampler.stop_flag = True
     sampler.sample()
     ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - launches0
+    launches = sum(c.launch_count() for c in ctxs) - launches0
     kms = (C.c_double * 8)(); kcnt = (C.c_longlong * 8)()
-    lib.yk_profile_read(ctx.ctx, kms, kcnt)
-    lib.yk_profile(ctx.ctx, 0)
+    for c in ctxs:
+        a = (C.c_double * 8)(); b = (C.c_longlong * 8)()
+        lib.yk_profile_read(c.ctx, a, b)
+        lib.yk_profile(c.ctx, 0)
+        for k in range(8):
+            kms[k] += a[k]; kcnt[k] += b[k]
     if dist is not None:
         t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -256,10 +276,10 @@ def main():
     value = world * mp_per_step * args.steps / (ms / 1e3)
 
     # algorithmic bytes per image: every input plane read once + every emitted pre-entropy stream
-    rb = ctx.result_bytes((args.steps - 1) % NSLOTS)
+    rb = ctx.result_bytes(0)
     alg_bytes = 4 * CH * W * H + sum(rb)
     peak, peak_src = peaks()
-    names = ["analyze", "emit_count", "scan", "emit_write", "range1d"]
+    names = ["analyze", "emit", "scan", "emit_write", "range1d"]
     kern_ms = {n: (kms[i] / kcnt[i] if kcnt[i] else None) for i, n in enumerate(names)}
     dom = kern_ms["analyze"]
     roof = None
@@ -328,11 +348,13 @@ def main():
                 "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "images_per_step_per_gpu": 1, "sharding": "by image, no collective",
+                           "pipelining": f"steps are independent textures, issued round-robin on {NCTX} CUDA streams (contexts)",
                            "l2": "inputs rotate over 8 resident 64 MiB images (512 MiB > 126 MB L2), so every step reads cold planes",
                            "stages": "MipPrefilter + 7x FittingQuadSmooth + 3x DynamicTileCompressor, results left in HBM"},
                 "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if dist is not None:
         dist.destroy_process_group()
 

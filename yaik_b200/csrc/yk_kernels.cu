@@ -51,8 +51,8 @@ static __device__ __forceinline__ int yk_src(const YkSlotDev& S, int c, int x, i
     return __ldg(S.plane[c] + (size_t)y * S.w + x);
 }
 
-static __device__ __forceinline__ unsigned yk_pack4(int4 v) {
-    return (unsigned)(v.x & 255) | ((unsigned)(v.y & 255) << 8) | ((unsigned)(v.z & 255) << 16) | ((unsigned)(v.w & 255) << 24);
+static __device__ __forceinline__ unsigned yk_pack4(int4 v) {      // low bytes of four samples -> one word (3 PRMT)
+    return __byte_perm(__byte_perm((unsigned)v.x, (unsigned)v.y, 0x0040), __byte_perm((unsigned)v.z, (unsigned)v.w, 0x0040), 0x5410);
 }
 
 static __device__ void yk_stage_pixels(const YkSlotDev& S, int X0, int Y0, uint8_t (*pix)[65 * YK_RS], unsigned& bad) {
@@ -116,8 +116,18 @@ template <int FAM> static __device__ __forceinline__ int yk_family(int v) {
 // cascade: lane = tile, one channel, the quad at the tile centre, raw corners.  A pixel whose raw-family U is outside
 // [loWide, hiWide) cannot be accepted by any of the six variants, so a cleared bit is a proven rejection; a set bit only
 // means "run the real test".  Bit (start(pid) + t) of the result belongs to tile t of pass id pid.
-static __device__ __forceinline__ unsigned long long yk_pretest(const uint8_t (*pix)[65 * YK_RS], int mlx, int mly, int X0, int Y0,
-                                                                int w, int h, int R, unsigned claimed) {
+// table entry of tile ti (0..40): offX | offY << 4 | shx << 8 | shy << 11 | cell << 14   (offsets in pixels inside the macro tile)
+static __device__ __forceinline__ uint32_t yk_pretest_entry(int ti) {
+    const int pid = (ti >= 1) + (ti >= 3) + (ti >= 5) + (ti >= 9) + (ti >= 17) + (ti >= 25);
+    const int t = ti - (int)((0x19110905030100ull >> (8 * pid)) & 255ull);
+    const int shx = (0x2233344 >> (4 * pid)) & 15, shy = (0x2323434 >> (4 * pid)) & 15;
+    const int tx = t & ((16 >> shx) - 1), ty = t >> (4 - shx);
+    const int offX = tx << shx, offY = ty << shy;
+    return (uint32_t)(offX | (offY << 4) | (shx << 8) | (shy << 11) | (((offY >> 2) * 4 + (offX >> 2)) << 14));
+}
+
+static __device__ __forceinline__ unsigned long long yk_pretest(const uint8_t (*pix)[65 * YK_RS], const uint32_t* sTab, int mlx, int mly,
+                                                                int X0, int Y0, int w, int h, int R, unsigned claimed) {
     const int lane = threadIdx.x & 31;
     unsigned long long P = 0;
 #pragma unroll
@@ -125,25 +135,21 @@ static __device__ __forceinline__ unsigned long long yk_pretest(const uint8_t (*
         const int ti = lane + 32 * round;
         bool possible = false;
         if (ti < 41) {
-            const int pid = (ti >= 1) + (ti >= 3) + (ti >= 5) + (ti >= 9) + (ti >= 17) + (ti >= 25);
-            const int t = ti - (int)((0x19110905030100ull >> (8 * pid)) & 255ull);
-            const int shx = (0x2233344 >> (4 * pid)) & 15, shy = (0x2323434 >> (4 * pid)) & 15, sh = shx + shy;
-            const int tx = t & ((16 >> shx) - 1), ty = t >> (4 - shx);
-            const int lx0 = mlx + (tx << shx), ly0 = mly + (ty << shy), TW = 1 << shx, TH = 1 << shy, N = 1 << sh;
-            const int cell = ((ty << shy) >> 2) * 4 + ((tx << shx) >> 2);
-            if (!((claimed >> cell) & 1u) && X0 + lx0 + TW <= w && Y0 + ly0 + TH <= h) {
-                const uint8_t* p = pix[0];
-                const int tl = p[ly0 * YK_RS + lx0], tr = p[ly0 * YK_RS + lx0 + TW];
-                const int bl = p[(ly0 + TH) * YK_RS + lx0], br = p[(ly0 + TH) * YK_RS + lx0 + TW];
+            const uint32_t e = sTab[ti];
+            const int shx = (e >> 8) & 7, shy = (e >> 11) & 7, sh = shx + shy;
+            const int lx0 = mlx + (e & 15), ly0 = mly + ((e >> 4) & 15), TW = 1 << shx, TH = 1 << shy, N = 1 << sh;
+            if (!((claimed >> (e >> 14)) & 1u) && X0 + lx0 + TW <= w && Y0 + ly0 + TH <= h) {
+                const uint8_t* p = pix[0] + ly0 * YK_RS + lx0;
+                const int tl = p[0], tr = p[TW], bl = p[TH * YK_RS], br = p[TH * YK_RS + TW];
                 const int dx0 = (TW >> 1) & ~3, dy = TH >> 1;
-                const unsigned word = *reinterpret_cast<const unsigned*>(p + (ly0 + dy) * YK_RS + lx0 + dx0);
+                const unsigned word = *reinterpret_cast<const unsigned*>(p + dy * YK_RS + dx0);
                 const int B = (tr - tl) << shy, C = (bl - tl) << shx, D = tl - tr - bl + br;
                 const int step = B + D * dy;
-                const int s0 = (tl << sh) + (R << sh) + B * dx0 + dy * (C + D * dx0);
+                const int s0 = ((tl + R) << sh) + B * dx0 + dy * (C + D * dx0);
                 const int u0 = s0 - (int)((word & 255u) << sh), u1 = s0 + step - (int)(((word >> 8) & 255u) << sh);
                 const int u2 = s0 + 2 * step - (int)(((word >> 16) & 255u) << sh), u3 = s0 + 3 * step - (int)((word >> 24) << sh);
-                const int umin = min(min(u0, u1), min(u2, u3)), umax = max(max(u0, u1), max(u2, u3));
-                possible = !(umin < -(4 * N + N / 2 - 1) || umax >= (2 * R + 1) * N + 3 * N);
+                const int umin = __vimin3_s32(min(u0, u1), u2, u3), umax = __vimax3_s32(max(u0, u1), u2, u3);
+                possible = !(umin < -(4 * N + N / 2 - 1) || umax >= (2 * R + 4) * N);
             }
         }
         P |= (unsigned long long)__ballot_sync(YK_FULL, possible) << (32 * round);
@@ -270,6 +276,7 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
     __shared__ uint32_t sTouch[17 * 17];
     __shared__ uint32_t sAlpha;
     __shared__ int sNext;
+    __shared__ uint32_t sTab[41];
 
     const YkSlotDev& S = slots[slot0 + blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -292,6 +299,7 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
     for (int i = tid; i < YK_NPASS * YK_ST_STRIDE; i += YK_THREADS) (&sStat[0][0])[i] = 0;
     for (int i = tid; i < 17 * 17; i += YK_THREADS) sTouch[i] = 0;
     if (tid == 0) { sAlpha = 0; sNext = 0; }
+    if (tid >= 64 && tid < 64 + 41) sTab[tid - 64] = yk_pretest_entry(tid - 64);
 
     // ---- alpha plane first (its loads stay in flight while the colour planes are staged)
     const bool doAlpha = run.doAlpha && S.nPlanes == 4;
@@ -341,9 +349,14 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, YkRun run) {
 #pragma unroll
         for (int r = 0; r < 4; r++) claimed |= ((sCell[my * 4 + r] >> (4 * mx)) & 15u) << (4 * r);
         const unsigned claimed0 = claimed;
-        const unsigned long long P = (claimed != 0xFFFFu && run.nPasses > 0) ? yk_pretest(pix, 16 * mx, 16 * my, X0, Y0, w, h, R, claimed) : 0ull;
+        // the 16x16 pass runs straight away (most macro tiles of illustration-like content end there); the other
+        // shapes are pre-tested together, once, the first time one of them comes up
+        const bool in16 = (X0 + 16 * mx + 16 <= w) && (Y0 + 16 * my + 16 <= h);
+        unsigned long long P = in16 ? 1ull : 0ull;
+        bool pretested = false;
         for (int rp = 0; rp < run.nPasses && claimed != 0xFFFFu; rp++) {
             const int pid = run.passId[rp];
+            if (pid != 0 && !pretested) { P = yk_pretest(pix, sTab, 16 * mx, 16 * my, X0, Y0, w, h, R, claimed); pretested = true; }
             const unsigned poss = (unsigned)(P >> ((0x19110905030100ull >> (8 * pid)) & 255ull)) & 0xFFFFu;     // tiles of this shape
             switch (pid) {      // Convert()'s order, EC.cpp:9057-9093
             case 0: if (poss & 0x1u)    claimed = yk_macro_pass<4, 4, 64, 64>(pix, sBits[0], sStat[0], sTouch, rp, 16 * mx, 16 * my, X0, Y0, w, h, S.y0, R, claimed, poss); break;
@@ -667,11 +680,13 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGro
 // reference's row-major tile order; stream offsets were scanned by yk_k_emit; per tile and plane one pass with lane = 2 pixels.
 __global__ void __launch_bounds__(YK_THREADS)
 yk_k_range1d(const YkSlotDev* __restrict__ slots, int slot0, int nSegs) {
-    __shared__ uint32_t hist[YK_THREADS / 32][256];
+    __shared__ uint32_t hist[YK_THREADS / 32][3][256];
+    __shared__ uint32_t sMagic[256];                        // ceil(2^20 / d): exact floor(n / d) for n < 4112, d <= 255
     const YkSlotDev& S = slots[slot0 + blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int w = S.w, h = S.h, nbx = S.nbx;
-    for (int i = lane; i < 256; i += 32) hist[warp][i] = 0;
+    const int w = S.w, nbx = S.nbx;
+    sMagic[tid] = tid ? ((1u << 20) + (unsigned)tid - 1u) / (unsigned)tid : 0u;
+    __syncthreads();
     const int ticket = blockIdx.x * (YK_THREADS / 32) + warp;
     if (ticket >= nSegs) return;
     const int bx = ticket % nbx, ty = ticket / nbx;                 // tile row ty, 64-pixel column bx
@@ -681,71 +696,83 @@ yk_k_range1d(const YkSlotDev* __restrict__ slots, int slot0, int nSegs) {
         const int cellsIn = (w - X0) >> 2;
         if (cellsIn < 16) { r0 |= (0xFFFFu << cellsIn) & 0xFFFFu; r1 |= (0xFFFFu << cellsIn) & 0xFFFFu; }
     }
-    // quadrant needs coding iff its top-left map pixel is 0 (EC.cpp:8420-8430) == its 4x4 cell is unclaimed
-    int chunks = 0;
-#pragma unroll
-    for (int x = 0; x < 8; x++) chunks += 4 - __popc(((r0 >> (2 * x)) & 3u) | (((r1 >> (2 * x)) & 3u) << 2));
+    if (((r0 & r1) & 0xFFFFu) == 0xFFFFu) return;           // every cell claimed: nothing to code in this segment
+    for (int i = lane; i < 3 * 256; i += 32) (&hist[warp][0][0])[i] = 0;
     const uint2 off = __ldg(&S.r2Off[ticket]);              // scanned by yk_k_emit
     int chunkOff = (int)off.x, tileOff = (int)off.y;
-    if (chunks == 0) return;
     __syncwarp();
 
     const int r = lane >> 2, c0 = (lane & 3) * 2;           // pixel row / first column of this lane inside the tile
     const int band = r >> 2, right = c0 >> 2;
+    const int32_t* __restrict__ P0 = S.plane[0] + (size_t)(Y0 + r) * w + X0 + c0;
+    const int32_t* __restrict__ P1 = S.plane[1] + (size_t)(Y0 + r) * w + X0 + c0;
+    const int32_t* __restrict__ P2 = S.plane[2] + (size_t)(Y0 + r) * w + X0 + c0;
     for (int tx = 0; tx < 8; tx++) {
+        // quadrant needs coding iff its top-left map pixel is 0 (EC.cpp:8420-8430) == its 4x4 cell is unclaimed
         const unsigned q = (~(((r0 >> (2 * tx)) & 3u) | (((r1 >> (2 * tx)) & 3u) << 2))) & 15u;   // bit0 TL, 1 TR, 2 BL, 3 BR
         if (q == 0) continue;
         const bool valid = (q >> (band * 2 + right)) & 1u;
         const unsigned qb = (q >> (band * 2)) & 3u;                     // coded quadrants of this band: bit0 left, bit1 right
         const int lengthX = (qb == 3u) ? 8 : 4, x2 = (qb == 2u) ? 4 : 0;
         const int pos = (band ? 16 * __popc(q & 3u) : 0) + (r & 3) * lengthX + (c0 - x2);
-        for (int plane = 0; plane < 3; plane++) {
-            int vx = 0, vy = 0;
-            if (valid) {
-                int2 p = __ldg(reinterpret_cast<const int2*>(S.plane[plane] + (size_t)(Y0 + r) * w + X0 + 8 * tx + c0));
-                vx = p.x & 255; vy = p.y & 255;             // CompressF(v, 255) == v (EC.cpp:8442)
-            }
-            // histogram of the coded pixels; equal values are pre-aggregated with match.any so a flat tile costs one atomic
-            {
-                const unsigned mxm = __match_any_sync(YK_FULL, valid ? vx : -1 - lane);
-                const unsigned mym = __match_any_sync(YK_FULL, valid ? vy : -1 - lane);
-                if (valid) {
-                    if ((__ffs((int)mxm) - 1) == lane) atomicAdd(&hist[warp][vx], (unsigned)__popc(mxm));
-                    if ((__ffs((int)mym) - 1) == lane) atomicAdd(&hist[warp][vy], (unsigned)__popc(mym));
-                }
-            }
-            __syncwarp();
-            // FindAndRemoveMostUsedColor (EC.cpp:8335-8356): highest index among the maximal counts; only present values can win
-            unsigned key = 0;
-            if (valid) key = max((hist[warp][vx] << 8) | (unsigned)vx, (hist[warp][vy] << 8) | (unsigned)vy);
-            key = __reduce_max_sync(YK_FULL, key);
-            __syncwarp();
-            if (valid) { hist[warp][vx] = 0; hist[warp][vy] = 0; }
-            int color0 = min(max((int)(key & 255u), 1), 254);
+        // the three planes of the tile are coded side by side so their latencies overlap
+        int vx[3] = { 0, 0, 0 }, vy[3] = { 0, 0, 0 };
+        if (valid) {
+            const int2 a = __ldg(reinterpret_cast<const int2*>(P0 + 8 * tx));
+            const int2 b = __ldg(reinterpret_cast<const int2*>(P1 + 8 * tx));
+            const int2 c = __ldg(reinterpret_cast<const int2*>(P2 + 8 * tx));
+            vx[0] = a.x & 255; vy[0] = a.y & 255; vx[1] = b.x & 255; vy[1] = b.y & 255; vx[2] = c.x & 255; vy[2] = c.y & 255;   // CompressF(v,255) == v (EC.cpp:8442)
+#pragma unroll
+            for (int p = 0; p < 3; p++) { atomicAdd(&hist[warp][p][vx[p]], 1u); atomicAdd(&hist[warp][p][vy[p]], 1u); }
+        }
+        __syncwarp();
+        // FindAndRemoveMostUsedColor (EC.cpp:8335-8356): highest index among the maximal counts; only present values can win
+        unsigned key[3] = { 0, 0, 0 };
+        if (valid) {
+#pragma unroll
+            for (int p = 0; p < 3; p++) key[p] = max((hist[warp][p][vx[p]] << 8) | (unsigned)vx[p], (hist[warp][p][vy[p]] << 8) | (unsigned)vy[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < 3; p++) key[p] = __reduce_max_sync(YK_FULL, key[p]);
+        __syncwarp();
+        if (valid) {
+#pragma unroll
+            for (int p = 0; p < 3; p++) { hist[warp][p][vx[p]] = 0; hist[warp][p][vy[p]] = 0; }
+        }
+        int color0[3], mn[3], mx[3];
+        bool remx[3], remy[3];
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            color0[p] = min(max((int)(key[p] & 255u), 1), 254);
             // Model1 (EC.cpp:8358-8381) over what is left of the histogram
-            const bool remx = valid && (vx < color0 - 1 || vx > color0 + 1), remy = valid && (vy < color0 - 1 || vy > color0 + 1);
-            int mn = min(remx ? vx : 999, remy ? vy : 999), mx = max(remx ? vx : -1, remy ? vy : -1);
-            mn = __reduce_min_sync(YK_FULL, mn); mx = __reduce_max_sync(YK_FULL, mx);
+            remx[p] = valid && (vx[p] < color0[p] - 1 || vx[p] > color0[p] + 1);
+            remy[p] = valid && (vy[p] < color0[p] - 1 || vy[p] > color0[p] + 1);
+            mn[p] = min(remx[p] ? vx[p] : 999, remy[p] ? vy[p] : 999);
+            mx[p] = max(remx[p] ? vx[p] : -1, remy[p] ? vy[p] : -1);
+        }
+#pragma unroll
+        for (int p = 0; p < 3; p++) { mn[p] = __reduce_min_sync(YK_FULL, mn[p]); mx[p] = __reduce_max_sync(YK_FULL, mx[p]); }
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
             int minCol = 0, delta = 0;
-            if (mn != 999) { minCol = mn; delta = mx - mn; }
+            if (mn[p] != 999) { minCol = mn[p]; delta = mx[p] - mn[p]; }
             if (valid) {
                 // GetValueModel1 (EC.cpp:8383-8391): C division of a numerator in -1..3951 by delta in 1..255.
                 // floor(n/d) == (n * ceil(2^20/d)) >> 20 for 0 <= n < 4112, d <= 255; n == -1 only happens for delta == 1.
                 int bxv = 0, byv = 0;
                 if (delta) {
-                    const unsigned magic = ((1u << 20) + (unsigned)delta - 1u) / (unsigned)delta;
+                    const unsigned magic = sMagic[delta];
                     const int rnd = (delta >> 1) - 1;
-                    if (remx) { const int n = (vx - minCol) * 15 + rnd; bxv = 1 + (n < 0 ? n : (int)(((unsigned)n * magic) >> 20)); }
-                    if (remy) { const int n = (vy - minCol) * 15 + rnd; byv = 1 + (n < 0 ? n : (int)(((unsigned)n * magic) >> 20)); }
-                } else { bxv = remx ? 1 : 0; byv = remy ? 1 : 0; }
-                uint8_t* d = S.r2Idx[plane] + (size_t)chunkOff * 16 + pos;
+                    if (remx[p]) { const int n = (vx[p] - minCol) * 15 + rnd; bxv = 1 + (n < 0 ? n : (int)(((unsigned)n * magic) >> 20)); }
+                    if (remy[p]) { const int n = (vy[p] - minCol) * 15 + rnd; byv = 1 + (n < 0 ? n : (int)(((unsigned)n * magic) >> 20)); }
+                } else { bxv = remx[p] ? 1 : 0; byv = remy[p] ? 1 : 0; }
+                uint8_t* d = S.r2Idx[p] + (size_t)chunkOff * 16 + pos;
                 *reinterpret_cast<uint16_t*>(d) = (uint16_t)((bxv & 255) | ((byv & 255) << 8));
             }
-            if (lane == 0) {
-                uint8_t* t = S.r2Type[plane] + (size_t)tileOff * 3;            // EC.cpp:8503-8505
-                t[0] = (uint8_t)color0; t[1] = (uint8_t)minCol; t[2] = (uint8_t)delta;
+            if (lane == p) {
+                uint8_t* t = S.r2Type[p] + (size_t)tileOff * 3;            // EC.cpp:8503-8505
+                t[0] = (uint8_t)color0[p]; t[1] = (uint8_t)minCol; t[2] = (uint8_t)delta;
             }
-            __syncwarp();
         }
         chunkOff += __popc(q); tileOff += 1;
     }
