@@ -1,0 +1,110 @@
+// TEST DRIVER for the host-side C++ mirror (yaik_b200/host/EncoderContext.h): calls the stage members exactly the way
+// the reference's Convert() does (EC.cpp:9027-9093, 9451-9460, 9542-9544) and dumps the results in the same record
+// format as oracle/ref_harness.cpp, so tests/test_host_mirror.py can compare them with the golden vectors / the oracle.
+// usage: host_mirror_test <in.ykin> <out.ykout> [alpha] [grad] [r2] [r1] [r1_3bit] [noprepare]
+#include "EncoderContext.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+static FILE* g_out = NULL;
+static void rec(const char* name, char dtype, const void* data, uint64_t count) {
+    char nm[32]; memset(nm, 0, sizeof nm); strncpy(nm, name, 31);
+    size_t esz = dtype == 'i' ? 4 : dtype == 'H' ? 2 : dtype == 'd' ? 8 : 1;
+    fwrite(nm, 1, 32, g_out); fwrite(&dtype, 1, 1, g_out); fwrite(&count, 8, 1, g_out);
+    if (count) fwrite(data, esz, count, g_out);
+}
+static void recPlane(const char* name, Plane* p) { rec(name, 'i', p->GetPixels(), (uint64_t)p->GetWidth() * p->GetHeight()); }
+static void recInts(const char* name, std::vector<int> v) { rec(name, 'i', v.data(), v.size()); }
+
+int main(int argc, char** argv) {
+    if (argc < 3) return 2;
+    bool doAlpha = false, doGrad = false, doR2 = false, doR1 = false, r1_3bit = false, prepare = true;
+    for (int i = 3; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "alpha") doAlpha = true; else if (a == "grad") doGrad = true; else if (a == "r2") doR2 = true;
+        else if (a == "r1") doR1 = true; else if (a == "r1_3bit") { doR1 = true; r1_3bit = true; }
+        else if (a == "noprepare") prepare = false;
+    }
+    FILE* fi = fopen(argv[1], "rb");
+    char magic[4]; int hdr[3];
+    if (!fi || fread(magic, 1, 4, fi) != 4 || memcmp(magic, "YKIN", 4) || fread(hdr, 4, 3, fi) != 3) { fprintf(stderr, "bad input\n"); return 1; }
+    const int W = hdr[0], H = hdr[1], NP = hdr[2];
+    std::vector<u8> px((size_t)W * H * NP);
+    if (fread(px.data(), 1, px.size(), fi) != px.size()) return 1;
+    fclose(fi);
+    g_out = fopen(argv[2], "wb");
+
+    EncoderContext ctx(0);
+    Image* img = Image::CreateImage(W, H, NP, false);
+    for (int c = 0; c < NP; c++) {
+        int* d = img->GetPlane(c)->GetPixels(); const u8* s = px.data() + (size_t)c * W * H;
+        for (size_t i = 0; i < (size_t)W * H; i++) d[i] = s[i];
+    }
+    ctx.SetImageToEncode(img);
+    Image* output = Image::CreateImage(W, H, 3, true);
+
+    if (doAlpha && NP == 4) {
+        ctx.MipPrefilter(true);                                                     // EC.cpp:9027
+        recInts("alpha.bound", { ctx.boundX0, ctx.boundY0, ctx.boundX1, ctx.boundY1 });
+        recInts("alpha.remaining", { ctx.remainingPixels, ctx.mipMapTileSize });
+        if (ctx.lastAlpha.wroteChunk) recInts("alpha.chunk_bbox", { ctx.lastAlpha.chunkBBoxTiles[0], ctx.lastAlpha.chunkBBoxTiles[1], ctx.lastAlpha.chunkBBoxTiles[2], ctx.lastAlpha.chunkBBoxTiles[3], 1, 4 });
+        else recInts("alpha.chunk_bbox", {});
+        rec("alpha.bitmap", 'B', ctx.lastAlpha.bitmap.data(), ctx.lastAlpha.bitmap.size());
+    }
+    if (doGrad) {
+        if (prepare) ctx.PrepareQuadSmooth();                                       // EC.cpp:9045
+        static const int order[7][2] = { {4,4},{4,3},{3,4},{3,3},{3,2},{2,3},{2,2} };   // EC.cpp:9057-9093
+        for (int k = 0; k < 7; k++) {
+            int done = ctx.FittingQuadSmooth(3, img->GetPlane(0), img->GetPlane(1), img->GetPlane(2), output, false, order[k][0], order[k][1]);
+            auto& g = ctx.lastGradient;
+            const int wrote = (g.maxX > g.minX && g.maxY > g.minY && !g.rgbStream.empty()) ? 1 : 0;      // EC.cpp:4239
+            char nm[32];
+            snprintf(nm, sizeof nm, "grad%d.tiledone", k); recInts(nm, { done, wrote });
+            snprintf(nm, sizeof nm, "grad%d.bbox", k);     recInts(nm, { g.minX, g.minY, g.maxX - g.minX, g.maxY - g.minX });   // EC.cpp:4255-4258
+            snprintf(nm, sizeof nm, "grad%d.bitmap", k);   rec(nm, 'B', g.bitmap.data(), g.bitmap.size());
+            snprintf(nm, sizeof nm, "grad%d.rgb", k);      rec(nm, 'B', g.rgbStream.data(), g.rgbStream.size());
+        }
+        ctx.SyncStatePlanes();
+        recPlane("state.smoothMap", ctx.smoothMap);
+        recPlane("state.mipmapMask", ctx.mipmapMask);
+        for (int c = 0; c < 3; c++) {
+            char nm[32];
+            snprintf(nm, sizeof nm, "state.mapSmoothTile%d", c); recPlane(nm, ctx.mapSmoothTile->GetPlane(c));
+            snprintf(nm, sizeof nm, "state.mappedRGB%d", c);     recPlane(nm, ctx.mappedRGB->GetPlane(c));
+            snprintf(nm, sizeof nm, "state.recon%d", c);         recPlane(nm, output->GetPlane(c));
+        }
+    }
+    if (doR2) {
+        if (!ctx.mapSmoothTile) ctx.SyncStatePlanes();
+        std::vector<u8> stream((size_t)W * H * 3 + 64);
+        streamType = new u8[(size_t)(W / 8 + 1) * (H / 8 + 1) * 9 + 64]; pType = streamType;
+        u8* p = stream.data();
+        for (int c = 0; c < 3; c++) {
+            u8* p0 = p; u8* t0 = pType;
+            p = ctx.DynamicTileCompressor(p, img->GetPlane(c), ctx.mapSmoothTile->GetPlane(c), output->GetPlane(c));       // EC.cpp:9451-9460
+            char nm[32];
+            snprintf(nm, sizeof nm, "r2.idx%d", c);  rec(nm, 'B', p0, p - p0);
+            snprintf(nm, sizeof nm, "r2.type%d", c); rec(nm, 'B', t0, pType - t0);
+        }
+    }
+    if (doR1) {
+        for (int c = 0; c < 3; c++) {
+            Plane* dst = new Plane(W, H);
+            BoundingBox all = dst->GetRect(); dst->Fill(all, -1);
+            int ret = ctx.DynamicTileEncode(r1_3bit, img->GetPlane(c), dst, false, false, false, false);                    // EC.cpp:9542-9544
+            auto& d = ctx.lastDynamic;
+            char nm[32];
+            snprintf(nm, sizeof nm, "r1.defs%d", c);    rec(nm, 'H', d.tileDefs.data(), d.tileDefs.size());
+            snprintf(nm, sizeof nm, "r1.nibbles%d", c); rec(nm, 'B', d.nibbles.data(), d.nibbles.size());
+            snprintf(nm, sizeof nm, "r1.hdr%d", c);     recInts(nm, { d.constraint.x, d.constraint.y, d.constraint.w, d.constraint.h, (int)d.nibbles.size(), 1, 0, ret });
+            snprintf(nm, sizeof nm, "r1.dst%d", c);     recPlane(nm, dst);
+            delete dst;
+        }
+    }
+    recInts("meta", { W, H, NP, ctx.lastError });
+    fclose(g_out);
+    return ctx.lastError ? 3 : 0;
+}

@@ -1,0 +1,75 @@
+"""The host-side C++ mirror of the reference's EncoderContext (yaik_b200/host) driven the way Convert() drives the
+reference, compared with the golden vectors of the reference.  CPU: the mirror linked against the emulated library
+(logic of the mirror itself); -m gpu: the real binary on the CUDA library."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import golden_check
+from refrun import parse_records
+from yaik_b200.synth import to_ykin
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_BIN = os.path.join(ROOT, "tests", "emu", "_build", "host_mirror_test_emu")
+GPU_BIN = os.path.join(ROOT, "yaik_b200", "host", "_build", "host_mirror_test")
+
+
+def run_mirror(binary, planes, stages, extra=()):
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.ykin"), os.path.join(td, "out.ykout")
+        open(fin, "wb").write(to_ykin(planes))
+        subprocess.run([binary, fin, fout, *stages, *extra], check=True, timeout=600)
+        return parse_records(open(fout, "rb").read())
+
+
+def compare(name, binary, extra=()):
+    g, planes, stages = golden_check.load(name)
+    r = run_mirror(binary, planes, stages, extra)
+    h, w = planes.shape[1:]
+
+    def grad(sx, sy):
+        k = golden_check.PASS_ORDER.index((sx, sy))
+        bb = list(r[f"grad{k}.bbox"])
+        return dict(tiledone=int(r[f"grad{k}.tiledone"][0]), rgb=r[f"grad{k}.rgb"], bitmap=r[f"grad{k}.bitmap"],
+                    bbox=[bb[0], bb[1], bb[0] + bb[2], bb[0] + bb[3]])         # undo the header form (maxY - minX, EC.cpp:4258)
+    golden_check.check(
+        g, stages,
+        alpha=lambda: dict(bound=list(r["alpha.bound"]), remaining=int(r["alpha.remaining"][0]), bitmap=r["alpha.bitmap"],
+                           chunk_bbox=list(r["alpha.chunk_bbox"][:4])),
+        gradient_pass=grad,
+        range1d=lambda n: dict(idx=r[f"r2.idx{n}"], type=r[f"r2.type{n}"]),
+        range_dyn=lambda n, m3: dict(defs=r[f"r1.defs{n}"], nibbles=r[f"r1.nibbles{n}"], constraint=list(r[f"r1.hdr{n}"][:4]), dst=r[f"r1.dst{n}"]),
+        state=lambda: dict(smoothMap=r["state.smoothMap"], mipmapMask=r["state.mipmapMask"],
+                           mapSmoothTile=[r[f"state.mapSmoothTile{i}"] for i in range(3)],
+                           mappedRGB=[r[f"state.mappedRGB{i}"] for i in range(3)], recon=[r[f"state.recon{i}"] for i in range(3)]))
+    assert int(r["meta"][3]) == 0
+
+
+@pytest.fixture(scope="module")
+def emu_bin():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu"), "mirror"], check=True)
+    return EMU_BIN
+
+
+@pytest.mark.parametrize("name", ["patchy_72x40", "mip32_rgba", "alpha_island128"])
+def test_mirror_logic_on_emulated_library(emu_bin, name):
+    compare(name, emu_bin)
+
+
+def test_mirror_without_prepare_runs_pass_by_pass(emu_bin):
+    compare("patchy_72x40", emu_bin, extra=("noprepare",))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_check.fixtures())
+def test_mirror_on_gpu_matches_reference_vectors(name):
+    assert os.path.exists(GPU_BIN), "build it: make -C yaik_b200/host"
+    compare(name, GPU_BIN)
+
+
+@pytest.mark.gpu
+def test_mirror_on_gpu_pass_by_pass():
+    compare("patchy128", GPU_BIN, extra=("noprepare",))

@@ -1,0 +1,158 @@
+// See EncoderContext.h.  Every stage member is a thin call into the C ABI (include/yaik_b200.h).
+#include "EncoderContext.h"
+#include <stdio.h>
+
+u8* streamType = new u8[1];     // re-pointed by the caller exactly as with the reference (its 100000-byte buffer overflows
+u8* pType = streamType;         // beyond 33 333 tile records); DynamicTileCompressor appends at pType
+
+EncoderContext::EncoderContext(int cudaDevice)
+    : original(NULL), mipmapMask(NULL), smoothMap(NULL), mapSmoothTile(NULL), mappedRGB(NULL),
+      boundX0(0), boundY0(0), boundX1(0), boundY1(0), remainingPixels(0), mipMapTileSize(16),
+      colorCompressionQuad(250), colorCompression1D(255), rangeCompression1D(15), lastError(YK_OK),
+      ctx(NULL), device(cudaDevice), capW(0), capH(0), lastTestOutput(NULL), prepared(false) {}
+
+EncoderContext::~EncoderContext() {
+    if (ctx) yk_destroy(ctx);
+    delete mipmapMask; delete smoothMap; delete mapSmoothTile; delete mappedRGB;
+}
+
+void EncoderContext::ensureContext(int w, int h, int planes) {
+    if (ctx && w <= capW && h <= capH) return;
+    if (ctx) yk_destroy(ctx);
+    ctx = NULL;
+    lastError = yk_create(&ctx, device, w, h, 4, 1);
+    if (lastError) { fprintf(stderr, "yaik_b200: yk_create failed: %s %s\n", yk_error_string(lastError), yk_last_cuda_error()); return; }
+    capW = w; capH = h; (void)planes;
+}
+
+void EncoderContext::SetImageToEncode(Image* img) {
+    original = img;
+    const int w = img->GetWidth(), h = img->GetHeight(), n = img->HasAlpha() ? 4 : 3;
+    ensureContext(w, h, n);
+    if (!ctx) return;
+    const int32_t* planes[4] = { 0, 0, 0, 0 };
+    for (int i = 0; i < n; i++) planes[i] = img->GetPlane(i)->GetPixels();
+    lastError = yk_set_image(ctx, 0, planes, n, w, h);
+    delete mipmapMask; delete smoothMap; delete mapSmoothTile; delete mappedRGB;
+    mipmapMask = NULL; smoothMap = NULL; mapSmoothTile = NULL; mappedRGB = NULL;
+    boundX0 = 0; boundY0 = 0; boundX1 = w; boundY1 = h; remainingPixels = w * h; mipMapTileSize = 16;
+    prepared = false; lastTestOutput = NULL;
+}
+
+void EncoderContext::CheckMipmapMask() {            // EC.cpp:2784-2794: all-255 mask, bound = full image
+    if (!mipmapMask && original) {
+        mipmapMask = new Plane(original->GetWidth(), original->GetHeight(), false);
+        BoundingBox bb = mipmapMask->GetRect();
+        mipmapMask->Fill(bb, 255);
+    }
+}
+
+void EncoderContext::MipPrefilter(bool active) {
+    (void)active;                                   // the reference ignores it as well (EC.cpp:1257)
+    if (!ctx || !original) { lastError = YK_ERR_STATE; return; }
+    const int w = original->GetWidth(), h = original->GetHeight();
+    if (!mipmapMask) mipmapMask = new Plane(w, h, false);
+    if (!original->HasAlpha()) {                    // EC.cpp:1419-1426
+        boundX0 = 0; boundY0 = 0; boundX1 = w; boundY1 = h; remainingPixels = w * h;
+        BoundingBox bb = mipmapMask->GetRect(); mipmapMask->Fill(bb, 255);
+        return;
+    }
+    lastAlpha.bitmap.assign((size_t)((w + 15) / 16) * ((h + 15) / 16) / 8 + 8, 0);
+    int nb = 0, wrote = 0;
+    lastError = yk_alpha_reject(ctx, 0, lastAlpha.bitmap.data(), (int)lastAlpha.bitmap.size(), &nb, lastAlpha.bbox,
+                                &lastAlpha.remainingPixels, &wrote, lastAlpha.chunkBBoxTiles);
+    if (lastError) return;
+    lastAlpha.bitmap.resize(nb); lastAlpha.wroteChunk = wrote != 0;
+    boundX0 = lastAlpha.bbox[0]; boundY0 = lastAlpha.bbox[1]; boundX1 = lastAlpha.bbox[2]; boundY1 = lastAlpha.bbox[3];
+    remainingPixels = lastAlpha.remainingPixels; mipMapTileSize = 16;       // EC.cpp:1287-1291
+    // host tail of the reference from here: fwrite 'MIPM' HeaderBase + MipmapHeader + lastAlpha.bitmap (EC.cpp:1367-1396)
+}
+
+void EncoderContext::PrepareQuadSmooth() {
+    if (!ctx || !original) { lastError = YK_ERR_STATE; return; }
+    lastError = yk_prepare_quad_smooth(ctx, 0, 3);  // rejectFactor of Convert(), EC.cpp:9042
+    prepared = lastError == YK_OK;
+}
+
+int EncoderContext::FittingQuadSmooth(int rejectFactor, Plane* a, Plane* b, Plane* c, Image* testOutput, bool useYCoCg,
+                                      int tileBitSizeX, int tileBitSizeY) {
+    CheckMipmapMask();
+    if (!ctx || !original) { lastError = YK_ERR_STATE; return 0; }
+    if (useYCoCg || a != original->GetPlane(0) || b != original->GetPlane(1) || c != original->GetPlane(2)) {
+        lastError = YK_ERR_UNSUPPORTED;             // only the RGB form Convert() uses (PlaneBit 7, EC.cpp:9043)
+        fprintf(stderr, "yaik_b200: FittingQuadSmooth is provided for the three RGB planes of the image only\n");
+        return 0;
+    }
+    const int w = original->GetWidth(), h = original->GetHeight();
+    const int tsx = 1 << tileBitSizeX, tsy = 1 << tileBitSizeY;
+    if (!smoothMap) {                               // EC.cpp:3739-3749: state planes appear on the first call (filled by SyncStatePlanes)
+        smoothMap = new Plane(w, h, false); smoothMap->Clear();
+        mapSmoothTile = Image::CreateImage(w, h, 3, true, false);
+        mappedRGB = Image::CreateImage(w + 1, h + 1, 3, true, false);
+    }
+    lastGradient.bitmap.assign((size_t)((w + 63) / 32) * ((h + 63) / 32) * 64 / 8 + 16, 0);
+    lastGradient.rgbStream.assign((size_t)3 * (w / tsx + 1) * (h / tsy + 1) + 16, 0);   // EC.cpp:3780-3785
+    int nb = 0, nr = 0, bbox[4] = { 0, 0, 0, 0 }, done = 0;
+    lastError = yk_gradient_pass(ctx, 0, rejectFactor, tileBitSizeX, tileBitSizeY, lastGradient.bitmap.data(), (int)lastGradient.bitmap.size(), &nb,
+                                 lastGradient.rgbStream.data(), (int)lastGradient.rgbStream.size(), &nr, bbox, &done);
+    if (lastError) { fprintf(stderr, "yaik_b200: FittingQuadSmooth: %s %s\n", yk_error_string(lastError), yk_last_cuda_error()); return 0; }
+    lastGradient.bitmap.resize(nb); lastGradient.rgbStream.resize(nr);
+    lastGradient.minX = bbox[0]; lastGradient.minY = bbox[1]; lastGradient.maxX = bbox[2]; lastGradient.maxY = bbox[3];
+    lastGradient.tileDone = done; lastGradient.shX = tileBitSizeX; lastGradient.shY = tileBitSizeY;
+    lastTestOutput = testOutput;
+    // host tail of the reference from here (EC.cpp:4239-4350): if (maxX > minX && maxY > minY && rgbStream.size() > 0)
+    //   CompressStream(bitmap), PaletteCompressor(rgbStream) -> CompressStream, fwrite 'GTIL' + HeaderGradientTile + streams
+    return done;
+}
+
+int EncoderContext::planeIndexOf(Plane* p, Image* img) {
+    if (!img) return -1;
+    for (int n = 0; n < 3; n++) if (img->GetPlane(n) == p) return n;
+    return -1;
+}
+
+u8* EncoderContext::DynamicTileCompressor(u8* stream, Plane* src, Plane* map, Plane* debug) {
+    (void)debug; (void)map;                         // map is mapSmoothTile[plane]: the device holds it in compact form
+    if (!ctx || !original) { lastError = YK_ERR_STATE; return stream; }
+    const int n = planeIndexOf(src, original);
+    if (n < 0) { lastError = YK_ERR_UNSUPPORTED; return stream; }
+    const int w = original->GetWidth(), h = original->GetHeight();
+    int ni = 0, nt = 0;
+    lastError = yk_range1d(ctx, 0, n, stream, w * h, &ni, pType, 3 * (w / 8 + 1) * (h / 8 + 1), &nt);
+    if (lastError) { fprintf(stderr, "yaik_b200: DynamicTileCompressor: %s\n", yk_error_string(lastError)); return stream; }
+    pType += nt;                                    // EC.cpp:8503-8505
+    return stream + ni;
+}
+
+int EncoderContext::DynamicTileEncode(bool mode3BitOnly, Plane* plane, Plane* dst, bool isCo, bool isCg, bool isHalfX, bool isHalfY) {
+    CheckMipmapMask();
+    if (!ctx || !original) { lastError = YK_ERR_STATE; return 0; }
+    const int n = planeIndexOf(plane, original);
+    if (n < 0 || isCo || isCg || isHalfX || isHalfY) { lastError = YK_ERR_UNSUPPORTED; return 0; }   // full-resolution planes of the image
+    const int w = original->GetWidth(), h = original->GetHeight(), nt = (w / 8) * (h / 8);
+    lastDynamic.nibbles.assign((size_t)nt * 32 + 8, 0);
+    lastDynamic.tileDefs.assign((size_t)nt + 8, 0);
+    int nn = 0, nd = 0, cons[4] = { 0, 0, 0, 0 };
+    lastError = yk_range_dyn(ctx, 0, n, mode3BitOnly ? 1 : 0, lastDynamic.nibbles.data(), (int)lastDynamic.nibbles.size(), &nn,
+                             lastDynamic.tileDefs.data(), (int)lastDynamic.tileDefs.size(), &nd, cons, dst ? dst->GetPixels() : NULL);
+    if (lastError) { fprintf(stderr, "yaik_b200: DynamicTileEncode: %s\n", yk_error_string(lastError)); return 0; }
+    lastDynamic.nibbles.resize((nn + 1) / 2); lastDynamic.tileDefs.resize(nd); lastDynamic.nNibbles = nn;
+    lastDynamic.constraint.x = (s16)cons[0]; lastDynamic.constraint.y = (s16)cons[1];
+    lastDynamic.constraint.w = (s16)cons[2]; lastDynamic.constraint.h = (s16)cons[3];
+    // host tail of the reference from here (EC.cpp:4515-4589): ZSTD-21 of tileDefs and nibbles, fwrite 'PLNT' + PlaneTile
+    return 0;                                       // the reference returns layerSize, which it never updates (EC.cpp:4407, 4601)
+}
+
+void EncoderContext::SyncStatePlanes() {
+    if (!ctx || !original) { lastError = YK_ERR_STATE; return; }
+    const int w = original->GetWidth(), h = original->GetHeight();
+    if (!smoothMap) smoothMap = new Plane(w, h, false);
+    if (!mipmapMask) mipmapMask = new Plane(w, h, false);
+    if (!mapSmoothTile) mapSmoothTile = Image::CreateImage(w, h, 3, true, false);
+    if (!mappedRGB) mappedRGB = Image::CreateImage(w + 1, h + 1, 3, true, false);
+    int32_t* mst[3] = { mapSmoothTile->GetPlane(0)->GetPixels(), mapSmoothTile->GetPlane(1)->GetPixels(), mapSmoothTile->GetPlane(2)->GetPixels() };
+    int32_t* mrgb[3] = { mappedRGB->GetPlane(0)->GetPixels(), mappedRGB->GetPlane(1)->GetPixels(), mappedRGB->GetPlane(2)->GetPixels() };
+    int32_t* rec[3] = { 0, 0, 0 };
+    if (lastTestOutput) for (int n = 0; n < 3; n++) rec[n] = lastTestOutput->GetPlane(n)->GetPixels();
+    lastError = yk_download_state(ctx, 0, smoothMap->GetPixels(), mst, mrgb, mipmapMask->GetPixels(), lastTestOutput ? rec : NULL);
+}
