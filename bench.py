@@ -117,11 +117,18 @@ def cpu_reference_run(planes, stages, reps):
     return (time.perf_counter() - t0) / reps, "port"
 
 
+_REF_IMG = {}
+
+
 def _ref_worker(args):
+    """One encoder process: returns the seconds the reference spent in MipPrefilter + 7x FittingQuadSmooth (with its host
+    tail) + 3x DynamicTileCompressor, measured inside the process around the member calls (no image generation, no I/O)."""
     side, seed = args
-    from yaik_b200.synth import make_image
-    planes = make_image(side, side, CH, seed)
-    t, kind = cpu_reference_run(planes, ("alpha", "grad", "r2"), 1)
+    if (side, seed) not in _REF_IMG:
+        from yaik_b200.synth import make_image
+        _REF_IMG.clear()
+        _REF_IMG[(side, seed)] = make_image(side, side, CH, seed)
+    t, kind = cpu_reference_run(_REF_IMG[(side, seed)], ("alpha", "grad", "r2"), 1)
     return t, kind
 
 
@@ -141,18 +148,18 @@ def run_reference_arm(args):
         side //= 2
     with mp.get_context("spawn").Pool(cores) as pool:
         work = [(side, SEED_BASE + 1 + i) for i in range(cores)]
-        for _ in range(args.warmup):
-            pool.map(_ref_worker, work)
-        t0 = time.perf_counter()
+        for _ in range(max(1, args.warmup)):
+            pool.map(_ref_worker, work, chunksize=1)
+        dt = 0.0
         kind = "port"
         for _ in range(args.steps):
-            res = pool.map(_ref_worker, work)
+            res = pool.map(_ref_worker, work, chunksize=1)      # all cores busy at once; a step lasts as long as its slowest encoder
             kind = res[0][1]
-        dt = time.perf_counter() - t0
+            dt += max(r[0] for r in res)
     mp_per_step = cores * side * side / 1e6
     value = mp_per_step * args.steps / dt
     sample = (f"{cores} independent encoder processes per step, each one {side}x{side} RGBA synthetic texture "
-              f"({'full configs[1] size' if side == 2048 else 'crop-sized sample of configs[1]'}); wall clock over all processes")
+              f"({'full configs[1] size' if side == 2048 else 'crop-sized sample of configs[1]'}); step time = slowest encoder's in-process stage time")
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
