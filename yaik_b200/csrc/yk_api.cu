@@ -11,6 +11,9 @@
 #include <math.h>
 #include <string>
 #include <vector>
+#ifndef YK_EMULATE
+#include <cuda.h>               // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
+#endif
 
 static thread_local std::string g_lastCuda;
 
@@ -62,11 +65,12 @@ struct yk_ctx {
     // part B (claimed cells, touch map = the persistent analysis state) only by yk_reset_state
     uint8_t* zeroArea = nullptr; size_t zeroStride = 0, zeroABytes = 0;
     int* lutDev = nullptr;       // R1 tables
+    int numSMs = 1;              // grid of the persistent analysis kernel
     long long launches = 0;
     size_t planeCap = 0;
     // optional per-kernel timing with CUDA events on the launching stream (yk_profile)
     bool profile = false;
-    std::vector<cudaEvent_t> evA[5], evB[5];
+    std::vector<cudaEvent_t> evA[5], evB[5];      // 0 analyze, 1 emit, 2 owner
 };
 
 struct YkTimed {        // records an event pair around one launch when profiling is on
@@ -120,6 +124,44 @@ template <class T> static int dev_alloc(YkSlotHost& s, T** out, size_t count) {
     return YK_OK;
 }
 
+// TMA descriptor of one int32 plane [h][w] with a boxW x boxH box (yk_k_analyze stages regions with it).
+static int encode_plane_tmap(YkTmap* tm, const int32_t* plane, int w, int h, int boxW, int boxH) {
+#ifdef YK_EMULATE
+    memset(tm, 0, sizeof *tm);
+    tm->opaque[0] = (unsigned long long)(uintptr_t)plane; tm->opaque[1] = (unsigned long long)w; tm->opaque[2] = (unsigned long long)h;
+    (void)boxW; (void)boxH;
+    return YK_OK;
+#else
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { g_lastCuda = "cuTensorMapEncodeTiled not available in this driver"; return YK_ERR_CUDA; }
+        encode = (EncodeFn)fn;
+    }
+    static_assert(sizeof(YkTmap) == sizeof(CUtensorMap), "YkTmap must be a CUtensorMap");
+    const cuuint64_t dims[2] = { (cuuint64_t)w, (cuuint64_t)h };
+    const cuuint64_t strides[1] = { (cuuint64_t)w * sizeof(int32_t) };
+    const cuuint32_t box[2] = { (cuuint32_t)boxW, (cuuint32_t)boxH };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult r = encode(reinterpret_cast<CUtensorMap*>(tm), CU_TENSOR_MAP_DATA_TYPE_INT32, 2, (void*)plane, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_lastCuda = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r); return YK_ERR_CUDA; }
+    return YK_OK;
+#endif
+}
+
+static int encode_slot_tmaps(YkSlotHost& s) {
+    for (int p = 0; p < s.d.nPlanes; p++) {
+        const int rc = encode_plane_tmap(&s.d.tmap[p], s.d.plane[p], s.d.w, s.d.h, p < 3 ? YK_RAW_PITCH : 64, p < 3 ? YK_RAW_ROWS : 64);
+        if (rc) return rc;
+    }
+    return YK_OK;
+}
+
 extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPlanes, int maxSlots) {
     if (!out || maxW < 4 || maxH < 4 || (maxW & 3) || (maxH & 3) || maxPlanes < 3 || maxPlanes > 4 || maxSlots < 1) return YK_ERR_ARG;
     if (maxW > 32764 || maxH > 32764) return YK_ERR_ARG;      // BoundingBox is s16 in the stream headers (YAIK_private.h:15-20)
@@ -132,6 +174,7 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
     c->slots.resize(maxSlots);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->ownStream = true;
+    { const int e = yk_analyze_setup(&c->numSMs); if (e) { g_lastCuda = std::string("yk_analyze_setup: ") + cudaGetErrorString((cudaError_t)e); return YK_ERR_CUDA; } }
     CK(cudaMalloc((void**)&c->slotsDev, sizeof(YkSlotDev) * maxSlots));
     const size_t W = maxW, H = maxH;
     const size_t nbx = (W + 63) / 64, latW = W / 4 + 1, latH = H / 4 + 1;
@@ -143,7 +186,13 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
         offStatus[p] = off;
         off += up(((W + g.bw - 1) / g.bw) * ((H + g.bh - 1) / g.bh) * sizeof(uint32_t));
     }
-    const size_t offR2 = off; off += up((H / 8 + 1) * nbx * sizeof(unsigned long long));
+    size_t offNib[YK_NPASS];
+    for (int p = 0; p < YK_NPASS; p++) {
+        const YkPassGeom& g = kGeom[p];
+        offNib[p] = off;
+        off += up(((W + g.bw - 1) / g.bw) * ((H + g.bh - 1) / g.bh) * (size_t)g.bits / 2 + 16);
+    }
+    const size_t offR2 = off; off += up(((W / 8) * (H / 8) / 1024 + 2) * sizeof(unsigned long long));
     c->zeroABytes = off;
     const size_t offCell = off; off += up((H / 4 + 1) * nbx * sizeof(uint16_t));
     const size_t offTouch = off; off += up(latW * latH * sizeof(uint32_t));
@@ -158,6 +207,7 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
         for (int p = 0; p < maxPlanes; p++) if ((rc = dev_alloc(s, &s.owned[p], W * H))) return rc;
         s.d.hdr = (int*)za;
         for (int p = 0; p < YK_NPASS; p++) s.d.emitStatus[p] = (uint32_t*)(za + offStatus[p]);
+        for (int p = 0; p < YK_NPASS; p++) s.d.emitNib[p] = (uint32_t*)(za + offNib[p]);
         s.d.r2Status = (unsigned long long*)(za + offR2);
         s.d.cellMask = (uint16_t*)(za + offCell);
         s.d.touchMap = (uint32_t*)(za + offTouch);
@@ -169,8 +219,9 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
             if ((rc = dev_alloc(s, &s.d.rgb[p], 3 * ((W >> g.shx) + 1) * ((H >> g.shy) + 1)))) return rc;
         }
         if ((rc = dev_alloc(s, &s.d.latRGB, latW * latH * 3))) return rc;
-        if ((rc = dev_alloc(s, &s.d.r2Off, (H / 8 + 1) * nbx))) return rc;
         for (int p = 0; p < 3; p++) {
+            if ((rc = dev_alloc(s, &s.d.r2Raw[p], W * H + 64))) return rc;
+            if ((rc = dev_alloc(s, &s.d.r2RawType[p], (W / 8 + 1) * (H / 8 + 1)))) return rc;
             if ((rc = dev_alloc(s, &s.d.r2Idx[p], W * H))) return rc;
             if ((rc = dev_alloc(s, &s.d.r2Type[p], 3 * (W / 8 + 1) * (H / 8 + 1)))) return rc;
         }
@@ -277,6 +328,7 @@ extern "C" int yk_set_image(yk_ctx* c, int slot, const int32_t* const* planes, i
     }
     for (int p = nPlanes; p < 4; p++) s.d.plane[p] = nullptr;
     s.borrowed = false;
+    if ((rc = encode_slot_tmaps(s))) return rc;
     return yk_reset_state(c, slot);
 }
 
@@ -291,6 +343,7 @@ extern "C" int yk_set_image_device(yk_ctx* c, int slot, const int32_t* const* de
     }
     for (int p = nPlanes; p < 4; p++) s.d.plane[p] = nullptr;
     s.borrowed = true;
+    if ((rc = encode_slot_tmaps(s))) return rc;
     return yk_reset_state(c, slot);
 }
 
@@ -356,19 +409,27 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     }
     if ((rc = upload_slots(c, slot0, nSlots))) return rc;
     if (needFold) { yk_launch_fold_touch(c->slotsDev, slot0, nSlots, a.d.latW * a.d.latH, c->stream); c->launches++; }
-    if (run.nPasses > 0 || run.doAlpha) { YkTimed t(c, 0); yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, run, c->stream); c->launches++; }
+    const bool r2Domain = doR2 && !(a.d.w & 7) && !(a.d.h & 7);
+    YkRun krun = run;
+    krun.doR2 = r2Domain ? 1 : 0;
+    if (krun.nPasses > 0 || krun.doAlpha || krun.doR2) {
+        YkTimed t(c, 0);
+        yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, c->numSMs, krun, c->stream); c->launches++;
+    }
     {
-        // one scan/compaction kernel: rgbStream emission of the run's passes + offsets of the R2 segments
+        // ownership of the touched lattice points, then one scan/compaction kernel: rgbStream emission of the run's
+        // passes + gather of the range stage's per-tile output into stream order
         int gradGroups = 0;
         if (doEmit)
-            for (int p = 0; p < run.nPasses; p++) {
-                const YkPassGeom& g = kGeom[run.passId[p]];
-                gradGroups += (((a.d.w + g.bw - 1) / g.bw) * ((a.d.h + g.bh - 1) / g.bh) + 31) / 32;
+            for (int p = 0; p < krun.nPasses; p++) {
+                const YkPassGeom& g = kGeom[krun.passId[p]];
+                const int nWords = ((a.d.w + g.bw - 1) / g.bw) * ((a.d.h + g.bh - 1) / g.bh) * g.bits / 8;
+                gradGroups += (nWords + 255) / 256;
             }
-        const int nSegs = (a.d.h / 8) * a.d.nbx;
-        const int r2Groups = doR2 ? (nSegs + 1023) / 1024 : 0;
-        if (gradGroups + r2Groups > 0) { YkTimed t(c, 1); yk_launch_emit(c->slotsDev, slot0, nSlots, gradGroups, r2Groups, run, c->stream); c->launches++; }
-        if (doR2 && nSegs > 0) { YkTimed t(c, 4); yk_launch_range1d(c->slotsDev, slot0, nSlots, nSegs, c->stream); c->launches++; }
+        const int nTiles = (a.d.w / 8) * (a.d.h / 8);
+        const int r2Groups = (r2Domain && nTiles > 0) ? (nTiles + 1023) / 1024 : 0;
+        if (gradGroups > 0) { YkTimed t(c, 2); yk_launch_owner(c->slotsDev, slot0, nSlots, a.d.latW * a.d.latH, krun, c->stream); c->launches++; }
+        if (gradGroups + r2Groups > 0) { YkTimed t(c, 1); yk_launch_emit(c->slotsDev, slot0, nSlots, gradGroups, r2Groups, krun, c->stream); c->launches++; }
     }
     CK(cudaGetLastError());
     for (int i = slot0; i < slot0 + nSlots; i++) {

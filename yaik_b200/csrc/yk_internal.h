@@ -26,13 +26,21 @@ enum {
     YK_HD_ALPHA_MINX, YK_HD_ALPHA_MINY, YK_HD_ALPHA_MAXX, YK_HD_ALPHA_MAXY, YK_HD_ALPHA_KEPT,
     YK_HD_R2_CHUNKS, YK_HD_R2_TILES,        // totals from the scan: 16-byte chunks per plane, coded tiles per plane
     YK_HD_R1_NIB0, YK_HD_R1_NIB1, YK_HD_R1_NIB2, YK_HD_R1_DEF0, YK_HD_R1_DEF1, YK_HD_R1_DEF2,
-    YK_HD_TICKET_EMIT, YK_HD_TICKET_R2,     // work tickets of the look-back kernels (stream order = ticket order)
+    YK_HD_TICKET_EMIT, YK_HD_TICKET_ANALYZE, // work tickets: emission groups in stream order / regions of the persistent analysis kernel
     YK_HD_PASS0 = 16,              // YK_NPASS * YK_ST_STRIDE ints
     YK_HD_INTS = YK_HD_PASS0 + YK_NPASS * YK_ST_STRIDE
 };
 
+// TMA descriptor of one int32 plane as a 2-D tensor [h][w] (a CUtensorMap: 128 bytes, 64-byte aligned), encoded on
+// the host by cuTensorMapEncodeTiled.  Box = 68 x 65 samples for the colour planes (a 64x64 region plus its right /
+// bottom corner row), 64 x 64 for alpha; out-of-image samples arrive as zeros and are never used unclamped.
+struct alignas(64) YkTmap { unsigned long long opaque[16]; };
+#define YK_RAW_PITCH 68         // ints per row of a staged colour box
+#define YK_RAW_ROWS 65
+
 // Device-visible description of one slot (one image + all results of its analysis).
-struct YkSlotDev {
+struct alignas(128) YkSlotDev {
+    YkTmap tmap[4];             // per plane (R, G, B, alpha)
     const int32_t* plane[4];    // int32 row-major planes, pitch == w (Plane::GetPixels(), framework.h:81)
     const int32_t* rowBelow[3]; // strip mode: the pixel row under the strip (3 x w int32), else NULL
     int w, h, nPlanes;
@@ -51,10 +59,12 @@ struct YkSlotDev {
     uint32_t* emitStatus[YK_NPASS]; // per swizzle block: decoupled look-back word (rgb bytes << 2 | flag)
     uint8_t*  rgb[YK_NPASS];        // rgbStream
     uint8_t*  latRGB;               // [latH][latW][3]  CompressF(Round6(clamped pixel),250) at every lattice point
+    uint32_t* emitNib[YK_NPASS];    // per tile in stream order 4 bits: which of TL,TR,BL,BR the tile emits (8 tiles per word)
     // ---- range stage R2 (DynamicTileCompressor)
-    unsigned long long* r2Status;   // [h/8][nbx] per 8-tile segment: look-back word (chunks << 32 | codedTiles << 2 | flag)
-    uint2*    r2Off;            // [h/8][nbx] exclusive offsets of each segment: x = 16-byte chunks, y = coded tiles
-    uint8_t*  r2Idx[3];
+    unsigned long long* r2Status;   // per group of 1024 tiles (row-major tile order): look-back word (chunks << 32 | codedTiles << 2 | flag)
+    uint8_t*  r2Raw[3];         // [h/8][w/8][64] index bytes of every coded tile at a fixed place (written by the analysis kernel)
+    uint32_t* r2RawType[3];     // [h/8][w/8] color0 | minCol << 8 | delta << 16
+    uint8_t*  r2Idx[3];         // the streams in the reference's order (gathered by yk_k_emit)
     uint8_t*  r2Type[3];
     // ---- range stage R1 (DynamicTileEncode)
     int*      r1Cnt;            // [ (h/8+1) * (w/8) ] valid pixels per block in LeftRightOrder, then exclusive offsets
@@ -71,16 +81,18 @@ struct YkRun {
     int passId[YK_NPASS];       // which passes this launch runs, in order
     int rejectFactor;
     int doAlpha;
+    int doR2;                   // code the DynamicTileCompressor tiles of every region after its cascade
 };
 
 #ifdef __cplusplus
 extern "C++" {
 #endif
 // launch wrappers (yk_kernels.cu); `slots` is a device array, grid.y indexes it from slot0
-void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, const YkRun& run, cudaStream_t st);
+int  yk_analyze_setup(int* numSMs);      // opt-in shared memory of the persistent kernel; returns a cudaError_t
+void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, int gridCtas, const YkRun& run, cudaStream_t st);
 void yk_launch_fold_touch(const YkSlotDev* slotsDev, int slot0, int nSlots, int nWords, cudaStream_t st);
+void yk_launch_owner(const YkSlotDev* slotsDev, int slot0, int nSlots, int nPoints, const YkRun& run, cudaStream_t st);
 void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int gradGroups, int r2Groups, const YkRun& run, cudaStream_t st);
-void yk_launch_range1d(const YkSlotDev* slotsDev, int slot0, int nSlots, int nSegs, cudaStream_t st);
 void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t* smoothMap, int32_t* mipmapMask,
                      int32_t* mappedRGB, int32_t* recon0, int32_t* recon1, int32_t* recon2, cudaStream_t st);
 void yk_launch_range_dyn_count(const YkSlotDev* slotsDev, int slot, int cx, int cy, int cw, int ch, int nBlocks, cudaStream_t st);
