@@ -1,0 +1,24 @@
+"""Developer tool: run the bench texture through the -DYK_TIMING build and print where producer / consumer cycles go."""
+import sys, os, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from yaik_b200 import capi
+from yaik_b200.synth import make_image, SEED_BASE
+lib = capi.load_library(os.path.join(ROOT, 'yaik_b200', 'csrc', 'libyaik_b200_timing.so'))
+ctx = capi.Context(2048, 2048, planes=4, slots=1, lib=lib)
+img = make_image(2048, 2048, 4, SEED_BASE + 1)
+ctx.set_image(img, 0)
+st = capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D
+for _ in range(3):
+    ctx.reset_state(0); ctx.analyze(st); ctx.sync()
+out = (C.c_ulonglong * 16)()
+lib.yk_debug_timing(out, 1)
+N = 5
+for _ in range(N):
+    ctx.reset_state(0); ctx.analyze(st); ctx.sync()
+lib.yk_debug_timing(out, 0)
+names = {0: "prod: region init", 1: "prod: wait raw free", 2: "prod: issue TMA",
+         8: "cons(w0): queue+wait raw", 9: "cons(w0): pack", 10: "cons(w0): cascade+range", 11: "cons(w0): finalize"}
+for i, n in names.items():
+    print(f"{n:34s} {out[i] / N / 148:12.0f} cycles per CTA per launch")

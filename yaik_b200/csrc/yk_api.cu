@@ -156,7 +156,7 @@ static int encode_plane_tmap(YkTmap* tm, const int32_t* plane, int w, int h, int
 
 static int encode_slot_tmaps(YkSlotHost& s) {
     for (int p = 0; p < s.d.nPlanes; p++) {
-        const int rc = encode_plane_tmap(&s.d.tmap[p], s.d.plane[p], s.d.w, s.d.h, p < 3 ? YK_RAW_PITCH : 64, p < 3 ? YK_RAW_ROWS : 64);
+        const int rc = encode_plane_tmap(&s.d.tmap[p], s.d.plane[p], s.d.w, s.d.h, p < 3 ? YK_RAW_PITCH : 64, p < 3 ? YK_RAW_ROWS : 16);
         if (rc) return rc;
     }
     return YK_OK;
@@ -192,7 +192,7 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
         offNib[p] = off;
         off += up(((W + g.bw - 1) / g.bw) * ((H + g.bh - 1) / g.bh) * (size_t)g.bits / 2 + 16);
     }
-    const size_t offR2 = off; off += up(((W / 8) * (H / 8) / 1024 + 2) * sizeof(unsigned long long));
+    const size_t offR2 = off; off += up(((W / 8) * (H / 8) / 256 + 2) * sizeof(unsigned long long));
     c->zeroABytes = off;
     const size_t offCell = off; off += up((H / 4 + 1) * nbx * sizeof(uint16_t));
     const size_t offTouch = off; off += up(latW * latH * sizeof(uint32_t));
@@ -427,7 +427,7 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
                 gradGroups += (nWords + 255) / 256;
             }
         const int nTiles = (a.d.w / 8) * (a.d.h / 8);
-        const int r2Groups = (r2Domain && nTiles > 0) ? (nTiles + 1023) / 1024 : 0;
+        const int r2Groups = (r2Domain && nTiles > 0) ? (nTiles + 255) / 256 : 0;
         if (gradGroups > 0) { YkTimed t(c, 2); yk_launch_owner(c->slotsDev, slot0, nSlots, a.d.latW * a.d.latH, krun, c->stream); c->launches++; }
         if (gradGroups + r2Groups > 0) { YkTimed t(c, 1); yk_launch_emit(c->slotsDev, slot0, nSlots, gradGroups, r2Groups, krun, c->stream); c->launches++; }
     }

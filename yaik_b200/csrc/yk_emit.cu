@@ -40,7 +40,6 @@ yk_k_owner(const YkSlotDev* __restrict__ slots, int slot0, int nPoints, YkRun ru
 }
 
 #define YK_EMIT_THREADS 256
-#define YK_R2_PER_THREAD 4
 
 __global__ void __launch_bounds__(YK_EMIT_THREADS)
 yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGroups, int r2Groups) {
@@ -58,20 +57,26 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGro
     if (ticket >= gradGroups) {
         // ---- DynamicTileCompressor streams: tiles in row-major order, 16 bytes per coded quadrant, 3 type bytes per coded tile
         const int grp = ticket - gradGroups, nbx = S.nbx, tilesW = w >> 3, nTiles = tilesW * (h >> 3);
-        const int t0 = (grp * YK_EMIT_THREADS + tid) * YK_R2_PER_THREAD;
-        unsigned n[YK_R2_PER_THREAD];
-        unsigned chunks = 0, tiles = 0;
+        const int t = grp * YK_EMIT_THREADS + tid;
+        unsigned chunks = 0;
+        if (t < nTiles) {
+            const int ty = t / tilesW, tx = t - ty * tilesW;
+            const uint32_t r0 = S.cellMask[(size_t)(2 * ty) * nbx + (tx >> 3)], r1 = S.cellMask[(size_t)(2 * ty + 1) * nbx + (tx >> 3)];
+            const int s2 = 2 * (tx & 7);
+            chunks = 4u - (unsigned)__popc(((r0 >> s2) & 3u) | (((r1 >> s2) & 3u) << 2));       // quadrants whose top-left map pixel is 0 (EC.cpp:8420-8430)
+        }
+        const unsigned tiles = chunks > 0;
+        // the tile's output is fetched while the offsets are being scanned
+        uint4 v[3][4];
+        uint32_t ty3[3] = { 0, 0, 0 };
+        if (chunks) {
 #pragma unroll
-        for (int e = 0; e < YK_R2_PER_THREAD; e++) {
-            const int t = t0 + e;
-            n[e] = 0;
-            if (t < nTiles) {
-                const int ty = t / tilesW, tx = t - ty * tilesW;
-                const uint32_t r0 = S.cellMask[(size_t)(2 * ty) * nbx + (tx >> 3)], r1 = S.cellMask[(size_t)(2 * ty + 1) * nbx + (tx >> 3)];
-                const int s2 = 2 * (tx & 7);
-                n[e] = 4u - (unsigned)__popc(((r0 >> s2) & 3u) | (((r1 >> s2) & 3u) << 2));       // quadrants whose top-left map pixel is 0 (EC.cpp:8420-8430)
+            for (int p = 0; p < 3; p++) {
+                const uint4* src = reinterpret_cast<const uint4*>(S.r2Raw[p] + (size_t)t * 64);
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (k < (int)chunks) v[p][k] = src[k];
+                ty3[p] = S.r2RawType[p][t];
             }
-            chunks += n[e]; tiles += (n[e] > 0);
         }
         unsigned ic = chunks, it = tiles;
 #pragma unroll
@@ -96,21 +101,15 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGro
             if (grp == r2Groups - 1 && lane == 0) { S.hdr[YK_HD_R2_CHUNKS] = (int)(bc + totC); S.hdr[YK_HD_R2_TILES] = (int)(bt + totT); }
         }
         __syncthreads();
-        unsigned chunkOff = sA[warp] + ic - chunks, tileOff = sB[warp] + it - tiles;
+        if (chunks) {
+            const unsigned chunkOff = sA[warp] + ic - chunks, tileOff = sB[warp] + it - tiles;
 #pragma unroll
-        for (int e = 0; e < YK_R2_PER_THREAD; e++) {
-            if (n[e]) {
-                const size_t t = (size_t)(t0 + e);
+            for (int p = 0; p < 3; p++) {
+                uint4* dst = reinterpret_cast<uint4*>(S.r2Idx[p] + (size_t)chunkOff * 16);
 #pragma unroll
-                for (int p = 0; p < 3; p++) {
-                    const uint4* src = reinterpret_cast<const uint4*>(S.r2Raw[p] + t * 64);
-                    uint4* dst = reinterpret_cast<uint4*>(S.r2Idx[p] + (size_t)chunkOff * 16);
-                    for (unsigned k = 0; k < n[e]; k++) dst[k] = src[k];
-                    const uint32_t ty3 = S.r2RawType[p][t];
-                    uint8_t* td = S.r2Type[p] + (size_t)tileOff * 3;                            // EC.cpp:8503-8505
-                    td[0] = (uint8_t)ty3; td[1] = (uint8_t)(ty3 >> 8); td[2] = (uint8_t)(ty3 >> 16);
-                }
-                chunkOff += n[e]; tileOff += 1;
+                for (int k = 0; k < 4; k++) if (k < (int)chunks) dst[k] = v[p][k];
+                uint8_t* td = S.r2Type[p] + (size_t)tileOff * 3;                                // EC.cpp:8503-8505
+                td[0] = (uint8_t)ty3[p]; td[1] = (uint8_t)(ty3[p] >> 8); td[2] = (uint8_t)(ty3[p] >> 16);
             }
         }
         return;

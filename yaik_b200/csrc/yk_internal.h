@@ -32,11 +32,12 @@ enum {
 };
 
 // TMA descriptor of one int32 plane as a 2-D tensor [h][w] (a CUtensorMap: 128 bytes, 64-byte aligned), encoded on
-// the host by cuTensorMapEncodeTiled.  Box = 68 x 65 samples for the colour planes (a 64x64 region plus its right /
-// bottom corner row), 64 x 64 for alpha; out-of-image samples arrive as zeros and are never used unclamped.
+// the host by cuTensorMapEncodeTiled.  Box = 68 x 17 samples for the colour planes (one macro-tile row of a 64x64
+// region plus its right / bottom corner samples), 64 x 16 for alpha; out-of-image samples arrive as zeros and are
+// never used unclamped.
 struct alignas(64) YkTmap { unsigned long long opaque[16]; };
 #define YK_RAW_PITCH 68         // ints per row of a staged colour box
-#define YK_RAW_ROWS 65
+#define YK_RAW_ROWS 17
 
 // Device-visible description of one slot (one image + all results of its analysis).
 struct alignas(128) YkSlotDev {
@@ -61,7 +62,7 @@ struct alignas(128) YkSlotDev {
     uint8_t*  latRGB;               // [latH][latW][3]  CompressF(Round6(clamped pixel),250) at every lattice point
     uint32_t* emitNib[YK_NPASS];    // per tile in stream order 4 bits: which of TL,TR,BL,BR the tile emits (8 tiles per word)
     // ---- range stage R2 (DynamicTileCompressor)
-    unsigned long long* r2Status;   // per group of 1024 tiles (row-major tile order): look-back word (chunks << 32 | codedTiles << 2 | flag)
+    unsigned long long* r2Status;   // per group of 256 tiles (row-major tile order): look-back word (chunks << 32 | codedTiles << 2 | flag)
     uint8_t*  r2Raw[3];         // [h/8][w/8][64] index bytes of every coded tile at a fixed place (written by the analysis kernel)
     uint32_t* r2RawType[3];     // [h/8][w/8] color0 | minCol << 8 | delta << 16
     uint8_t*  r2Idx[3];         // the streams in the reference's order (gathered by yk_k_emit)
