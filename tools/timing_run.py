@@ -18,7 +18,7 @@ N = 5
 for _ in range(N):
     ctx.reset_state(0); ctx.analyze(st); ctx.sync()
 lib.yk_debug_timing(out, 0)
-names = {0: "prod: region init", 1: "prod: wait raw free", 2: "prod: issue TMA",
-         8: "cons(w0): queue+wait raw", 9: "cons(w0): pack", 10: "cons(w0): cascade+range", 11: "cons(w0): finalize"}
+names = {0: "prod: lookahead+free wait", 6: "prod: shfl ticket", 7: "prod: issue ticket atomic", 3: "prod: decode", 2: "prod: fence + expect_tx + 4x TMA issue",
+         8: "cons(w0): queue+wait raw", 9: "cons(w0): pack", 10: "cons(w0): cascade+range"}
 for i, n in names.items():
     print(f"{n:34s} {out[i] / N / 148:12.0f} cycles per CTA per launch")

@@ -14,20 +14,22 @@
 //                                                            the pixels already in shared memory, into a fixed per-tile
 //                                                            place; yk_k_emit moves them to their stream offsets
 //
-// Structure: one CTA per SM, persistent.  One producer warp takes regions by ticket and issues TMA box loads
-// (cp.async.bulk.tensor, one per plane) of one macro-tile row of a region (17 x 68 int32 samples per colour plane, 16 x 64
-// alpha) into a ring of raw staging buffers, completion on an mbarrier per buffer.  23 consumer warps take
-// (region, macro tile) items from a block-local queue: a warp packs its macro tile's 17x17x3 samples to bytes into a
-// warp-private tile (clamped the way Plane::GetPixelValue clamps), tests its alpha tile, releases the raw buffer, then
-// runs the cascade and the range stage out of the private tile.  Load latency and the very uneven cost of macro tiles
-// overlap; the warp that finishes the last macro tile of a region writes the region's results.  No block-wide barrier
-// after start-up; every wait is an mbarrier try_wait (the hardware suspends the warp).
+// Structure: one CTA per SM, persistent.  The unit of work is one macro-tile row of a region (64 x 16 pixels, four macro
+// tiles), taken by global ticket.  One producer warp takes tickets — never more than a few units ahead of the consumers,
+// so the CTAs finish together — and issues the TMA box loads (cp.async.bulk.tensor, one per plane: 17 x 68 int32 samples
+// per colour plane, 16 x 64 alpha) into a ring of raw staging buffers, completion on an mbarrier per buffer.
+// 23 consumer warps take macro tiles from a block-local queue: a warp packs its macro tile's 17x17x3 samples to bytes
+// into a warp-private tile (clamped the way Plane::GetPixelValue clamps), tests its alpha tile, releases the raw buffer,
+// then runs the cascade and the range stage out of the private tile and writes the macro tile's results straight to
+// global memory (accept bits, claimed cells and touch words by atomic OR).  Per-pass counters are summed per CTA.
+// No block-wide barrier after start-up; every wait is an mbarrier try_wait (the hardware suspends the warp).
 //
 // No tensor cores: the work is integer min/max reductions over bytes, bounded by HBM and the integer pipes.
 #include "yk_device.h"
 
 #define YKA_NR 8                    // raw int32 staging buffers (TMA destinations), one macro-tile row of a region each
-#define YKA_NBS 16                  // region states in flight
+#define YKA_TICKETS 4               // tickets a CTA holds ahead of the unit it is issuing
+#define YKA_LOOKAHEAD 7             // units the producer may run ahead of the unit the consumers are taking items from
 #define YKA_CONS_WARPS 23
 #define YKA_THREADS ((YKA_CONS_WARPS + 1) * 32)
 #define YKA_RAW_PLANE_INTS 1184     // 17 rows x 68 ints = 1156, rounded so every plane starts 128-byte aligned
@@ -40,33 +42,41 @@
 // a consumer waits on the phase parity of a raw buffer's barrier: the items in flight (one per consumer warp, consecutive
 // in the queue, four per raw buffer) must span fewer raw buffers than the ring holds
 static_assert((YKA_CONS_WARPS + 2) / 4 + 2 <= YKA_NR, "work items in flight must not wrap the raw ring");
-static_assert(YKA_CONS_WARPS <= 16 * (YKA_NBS - 1), "work items in flight must not wrap the region-state ring");
+static_assert(YKA_LOOKAHEAD < YKA_NR, "look-ahead is bounded by the raw ring");
 
-struct YkaRegion {                  // state of one region being analysed
-    uint32_t cell[16];              // claimed 4x4 cells, one 16-bit row per entry (cells outside the image count as claimed)
-    uint32_t bits[YK_NPASS][8];     // accept bits of the region in swizzled order (EC.cpp:4026)
-    int      stat[YK_NPASS][YK_ST_STRIDE];
-    uint32_t touch[17 * 17];        // touch words of the region's lattice points
-    uint32_t alpha;                 // bit ty*4+tx: 16x16 tile has a non-zero alpha sample
-    int      done;                  // macro tiles finished
-    int      slot;                  // absolute slot index of the image
-    int      bx, by, X0, Y0, w, h, yOrg, latW, latH, lastX, lastY, doAlpha;    // of the region / its image
+struct YkaUnit {                    // what the producer says about the unit staged in raw buffer i
+    int slot, bx, by, k, alpha;
+};
+
+// the fields of a slot descriptor a consumer warp needs (its own copy, refreshed when its items move to another image)
+struct YkaSlotC {
+    int slot, w, h, nbx, yOrg, latW, latH, pad;
     const int32_t* rowBelow[3];
+    uint32_t* cellMask32;           // claimed cells, two 16-bit rows per word
+    uint32_t* touchMap;
+    uint8_t*  alphaKept;
+    int*      hdr;
+    uint32_t* bitmap32[YK_NPASS];
     uint8_t*  latRGB;
     uint8_t*  r2Raw[3];
     uint32_t* r2RawType[3];
-    int*      hdr;
 };
+
+#define YKA_NSTAT YK_HD_INTS                         // per-pass counters + alpha box / count, laid out like the image header
 
 struct YkaShared {
     uint32_t pretestTab[41];
-    int      queueHead;             // next (region sequence number * 16 + macro tile) to hand out
-    int      endSeq;                // first region sequence number that does not exist
+    int      queueHead;             // next (unit sequence number * 4 + macro tile) to hand out
+    int      endSeq;                // first unit sequence number that does not exist
+    int      statSlot;              // the image whose counters are summed in `stat` (other images go straight to global memory)
+    int      consLeft;              // consumer warps still running (the last one flushes `stat`)
+    int      stat[YKA_NSTAT];
     YkRun    run;
-    unsigned long long rawFull[YKA_NR];     // raw buffer i: its TMA boxes have landed (and the region state is initialised)
+    unsigned long long rawFull[YKA_NR];     // raw buffer i: its TMA boxes have landed
     unsigned long long rawFree[YKA_NR];     // raw buffer i: the four macro tiles of the row have been packed out of it
-    unsigned long long freed[YKA_NBS];      // region state j: its region has been finalised
-    YkaRegion reg[YKA_NBS];
+    YkaUnit  unit[YKA_NR];
+    uint32_t touch[YKA_CONS_WARPS][25];     // touch words of the 5x5 lattice points of the macro tile a warp works on
+    YkaSlotC slotc[YKA_CONS_WARPS];
 };
 
 #define YKA_SMEM_RAW   (YKA_NR * YKA_RAW_STAGE_INTS * 4)
@@ -74,7 +84,6 @@ struct YkaShared {
 #define YKA_SMEM_HIST  (YKA_CONS_WARPS * 3 * 256)
 #define YKA_SMEM_BYTES (YKA_SMEM_RAW + YKA_SMEM_PIX + YKA_SMEM_HIST + 1024 + (int)sizeof(YkaShared))
 static_assert(YKA_SMEM_PIX % 128 == 0 && (YKA_CONS_WARPS * 3 * 256) % 128 == 0, "shared-memory carving keeps 128-byte alignment");
-
 
 // ------------------------------------------------------------------------------------------------------------------
 // mbarrier / TMA / shared-flag primitives (inline PTX), with stand-ins for the CPU logic emulation (tests/emu)
@@ -159,35 +168,37 @@ static __device__ __forceinline__ uint32_t yka_pretest_entry(int ti) {
     return (uint32_t)(offX | (offY << 4) | (shx << 8) | (shy << 11) | (((offY >> 2) * 4 + (offX >> 2)) << 14));
 }
 
-// Producer warp, once per region: claimed cells and the fields the consumers need from the slot descriptor.
-static __device__ void yka_region_init(const YkSlotDev& S, YkaRegion& R, int slot, int bx, int by, bool doAlpha, int lane) {
-    const int X0 = bx * 64, Y0 = by * 64;
-    if (lane < 16) {
-        const int cy = (Y0 >> 2) + lane;
-        uint32_t v = 0xFFFFu;
-        if (cy * 4 < S.h) {
-            v = S.cellMask[(size_t)cy * S.nbx + bx];
-            const int cellsIn = (S.w - X0) >> 2;
-            if (cellsIn < 16) v |= (0xFFFFu << cellsIn) & 0xFFFFu;
-        }
-        R.cell[lane] = v;
-    } else if (lane == 16) {
-        R.slot = slot; R.bx = bx; R.by = by; R.X0 = X0; R.Y0 = Y0; R.w = S.w; R.h = S.h; R.yOrg = S.y0;
-        R.latW = S.latW; R.latH = S.latH; R.lastX = bx == S.nbx - 1; R.lastY = by == S.nby - 1; R.doAlpha = doAlpha;
-        R.latRGB = S.latRGB; R.hdr = S.hdr;
-    } else if (lane >= 20 && lane < 23) {
-        const int p = lane - 20;
-        R.r2Raw[p] = S.r2Raw[p]; R.r2RawType[p] = S.r2RawType[p]; R.rowBelow[p] = S.rowBelow[p];
+// per-pass counters / alpha box: summed in shared memory for the CTA's main image, else straight in the image's header.
+// Slot k of a group of five: 0 = count (added), 1..4 = min x, min y (stored as extent - value), max x, max y (maxima).
+static __device__ __forceinline__ void yka_stat5(YkaShared& sh, const YkaSlotC& C, int idx0, int n, int a, int b, int c, int d) {
+    if (C.slot == sh.statSlot) {
+        atomicAdd(&sh.stat[idx0], n); atomicMax(&sh.stat[idx0 + 1], a); atomicMax(&sh.stat[idx0 + 2], b);
+        atomicMax(&sh.stat[idx0 + 3], c); atomicMax(&sh.stat[idx0 + 4], d);
+    } else {
+        atomicAdd(&C.hdr[idx0], n); atomicMax(&C.hdr[idx0 + 1], a); atomicMax(&C.hdr[idx0 + 2], b);
+        atomicMax(&C.hdr[idx0 + 3], c); atomicMax(&C.hdr[idx0 + 4], d);
     }
+}
+
+// Consumer warp: its copy of the slot descriptor fields (refreshed when the warp's items move to another image)
+static __device__ void yka_slot_refresh(const YkSlotDev& S, YkaSlotC& C, int slot) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) { C.slot = slot; C.w = S.w; C.h = S.h; C.nbx = S.nbx; C.yOrg = S.y0; C.latW = S.latW; C.latH = S.latH; }
+    else if (lane == 1) { C.cellMask32 = reinterpret_cast<uint32_t*>(S.cellMask); C.touchMap = S.touchMap; C.alphaKept = S.alphaKept; C.hdr = S.hdr; C.latRGB = S.latRGB; }
+    else if (lane >= 2 && lane < 5) { const int p = lane - 2; C.rowBelow[p] = S.rowBelow[p]; C.r2Raw[p] = S.r2Raw[p]; C.r2RawType[p] = S.r2RawType[p]; }
+    else if (lane >= 8 && lane < 8 + YK_NPASS) C.bitmap32[lane - 8] = reinterpret_cast<uint32_t*>(S.bitmap[lane - 8]);
+    __syncwarp();
 }
 
 // Consumer warp: the 17x17 samples of macro tile (mx, row k) of the region, three colour planes, from the raw int32
 // rows staged by TMA into the warp-private byte tile, clamped the way Plane::GetPixelValue clamps (framework.h:116-121);
-// then the alpha-zero test of the 16x16 tile (EC.cpp:357-430 restated per tile).
-static __device__ __forceinline__ void yka_pack_macro_tile(const int32_t* __restrict__ raw, uint8_t* __restrict__ priv, YkaRegion& R, int mx, int k) {
+// then the alpha-zero test of the 16x16 tile (EC.cpp:357-430 restated per tile).  Returns (uniformly) whether the tile
+// has a non-zero alpha sample.
+static __device__ __forceinline__ bool yka_pack_macro_tile(const int32_t* __restrict__ raw, uint8_t* __restrict__ priv, const YkaSlotC& C,
+                                                           int X0, int Yk, int mx, bool doAlpha) {
     const int lane = threadIdx.x & 31;
-    const int w = R.w, h = R.h;
-    const int Xm = R.X0 + 16 * mx, Yk = R.Y0 + 16 * k;
+    const int w = C.w, h = C.h;
+    const int Xm = X0 + 16 * mx;
     unsigned bad = 0;
     if (Xm + 20 <= w && Yk + YK_RAW_ROWS <= h) {
         // interior: 17 rows x 5 int4 (columns 0..19 of the macro tile, 17 needed) per plane, all inside the image
@@ -209,27 +220,28 @@ static __device__ __forceinline__ void yka_pack_macro_tile(const int32_t* __rest
     } else if (Yk < h && Xm < w) {
         // at the right / bottom edge: clamp inside the image; in strip mode the row under the strip is the real image
         // row (rowBelow), not a clamp
-        const int wmax = w - 1 - R.X0, hmax = min(16, h - 1 - Yk);
+        const int wmax = w - 1 - X0, hmax = min(16, h - 1 - Yk);
         for (int idx = lane; idx < 17 * 17; idx += 32) {
             const int lr = idx / 17, lx = idx - lr * 17;
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 int s;
-                if (lr > hmax && R.rowBelow[c]) s = __ldg(R.rowBelow[c] + min(Xm + lx, w - 1));
+                if (lr > hmax && C.rowBelow[c]) s = __ldg(C.rowBelow[c] + min(Xm + lx, w - 1));
                 else s = raw[c * YKA_RAW_PLANE_INTS + min(lr, hmax) * YK_RAW_PITCH + min(16 * mx + lx, wmax)];
                 bad |= (unsigned)s;
                 priv[c * YKP_CH + lr * YKP_RS + lx] = (uint8_t)s;
             }
         }
     }
-    if (bad & ~255u) atomicOr(&R.hdr[YK_HD_ERR], 1);
-    if (R.doAlpha) {
+    if (bad & ~255u) atomicOr(&C.hdr[YK_HD_ERR], 1);
+    bool kept = false;
+    if (doAlpha) {
         // samples outside the image arrive as zeros
         const int4* __restrict__ a = reinterpret_cast<const int4*>(raw + 3 * YKA_RAW_PLANE_INTS) + 4 * mx;
         const int4 v0 = a[(lane >> 2) * 16 + (lane & 3)], v1 = a[((lane >> 2) + 8) * 16 + (lane & 3)];
-        const bool nz = (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0;
-        if (__any_sync(YK_FULL, nz) && lane == 0) atomicOr(&R.alpha, 1u << (k * 4 + mx));
+        kept = __any_sync(YK_FULL, (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0);
     }
+    return kept;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -296,10 +308,11 @@ static __device__ __forceinline__ void yka_channel(const YkaTile& T, unsigned w0
 }
 
 // The accept test of FittingQuadSmooth (EC.cpp:3810-3998) for the tile this lane belongs to.  The lanes in `gmask` share
-// the tile; each holds one or two quads of one pixel row of it in `wd` (quad 0 at dx0, quad 1 at dx0 + 4, row dy).
+// the tile; each holds one or two quads of one pixel row of it (quad 0 at dx0, quad 1 at dx0 + 4, row dy): both words of
+// `pw`, or for a 4-pixel-wide tile one of them (`second`).
 // Returns, uniformly over the group, whether any of the six variants (3 corner families x rounded / truncated) keeps
 // every pixel of every channel within the reject factor.
-static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__ corner, const YkaTile& T, const unsigned (&wd)[3][2],
+static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__ corner, const YkaTile& T, const uint2 (&pw)[3], bool second,
                                                      unsigned gmask, bool active) {
     const int N = 1 << T.sh, TW = 1 << T.shx, THp = YKP_RS << T.shy;
     const int hiT = (2 * T.R + 1) * N;                  // |cur - S/N| <= R            <=>  0 <= U < hiT
@@ -314,14 +327,14 @@ static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__
     bool resolved = !active;
     // ---- raw corners
     int umin = INT_MAX, umax = INT_MIN;
-    yka_channel(T, wd[0][0], wd[0][1], cr[0][0], cr[0][1], cr[0][2], cr[0][3], umin, umax);
+    yka_channel(T, second ? pw[0].y : pw[0].x, pw[0].y, cr[0][0], cr[0][1], cr[0][2], cr[0][3], umin, umax);
     {   // one channel with the raw corners proves most non-gradient tiles hopeless for every variant
         const unsigned bH = __ballot_sync(YK_FULL, (umin < loWide) || (umax >= hiWide));
         if (bH & gmask) resolved = true;
         if (!__any_sync(YK_FULL, !resolved)) return false;
     }
-    yka_channel(T, wd[1][0], wd[1][1], cr[1][0], cr[1][1], cr[1][2], cr[1][3], umin, umax);
-    yka_channel(T, wd[2][0], wd[2][1], cr[2][0], cr[2][1], cr[2][2], cr[2][3], umin, umax);
+    yka_channel(T, second ? pw[1].y : pw[1].x, pw[1].y, cr[1][0], cr[1][1], cr[1][2], cr[1][3], umin, umax);
+    yka_channel(T, second ? pw[2].y : pw[2].x, pw[2].y, cr[2][0], cr[2][1], cr[2][2], cr[2][3], umin, umax);
     const unsigned bT = __ballot_sync(YK_FULL, (umin < 0) || (umax >= hiT));
     const unsigned bR = __ballot_sync(YK_FULL, (umin < loR) || (umax >= hiT + loR));
     const unsigned bH = __ballot_sync(YK_FULL, (umin < loWide) || (umax >= hiWide));
@@ -333,7 +346,7 @@ static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__
         int umin1 = INT_MAX, umax1 = INT_MIN;
 #pragma unroll
         for (int c = 0; c < 3; c++)
-            yka_channel(T, wd[c][0], wd[c][1], yk_round6(cr[c][0]), yk_round6(cr[c][1]), yk_round6(cr[c][2]), yk_round6(cr[c][3]), umin1, umax1);
+            yka_channel(T, second ? pw[c].y : pw[c].x, pw[c].y, yk_round6(cr[c][0]), yk_round6(cr[c][1]), yk_round6(cr[c][2]), yk_round6(cr[c][3]), umin1, umax1);
         const unsigned bT1 = __ballot_sync(YK_FULL, (umin1 < 0) || (umax1 >= hiT));
         const unsigned bR1 = __ballot_sync(YK_FULL, (umin1 < loR) || (umax1 >= hiT + loR));
         if (!resolved && (((bT1 & gmask) == 0u) || ((bR1 & gmask) == 0u))) { accepted = true; resolved = true; }
@@ -344,7 +357,7 @@ static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__
         int umin2 = INT_MAX, umax2 = INT_MIN;
 #pragma unroll
         for (int c = 0; c < 3; c++)
-            yka_channel(T, wd[c][0], wd[c][1], yk_round6p(cr[c][0]), yk_round6p(cr[c][1]), yk_round6p(cr[c][2]), yk_round6p(cr[c][3]), umin2, umax2);
+            yka_channel(T, second ? pw[c].y : pw[c].x, pw[c].y, yk_round6p(cr[c][0]), yk_round6p(cr[c][1]), yk_round6p(cr[c][2]), yk_round6p(cr[c][3]), umin2, umax2);
         const unsigned bT2 = __ballot_sync(YK_FULL, (umin2 < 0) || (umax2 >= hiT));
         const unsigned bR2 = __ballot_sync(YK_FULL, (umin2 < loR) || (umax2 >= hiT + loR));
         if (!resolved && (((bT2 & gmask) == 0u) || ((bR2 & gmask) == 0u))) accepted = true;
@@ -352,31 +365,29 @@ static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__
     return accepted;
 }
 
-// Side effects of an accepted tile (EC.cpp:3998-4132) that are local to the region: bitmap bit, TileDone / bounding box,
-// the four lattice points it touches with its role at each.  (lx0, ly0) = tile origin inside the region.
-static __device__ __forceinline__ void yka_commit(YkaRegion& R, const YkGeomS& g, int pid, int rp, int lx0, int ly0) {
+// Side effects of an accepted tile (EC.cpp:3998-4132): bitmap bit, TileDone / bounding box, the four lattice points it
+// touches with its role at each.  (gx0, gy0) = tile origin in the image, (tlx, tly) = inside the macro tile.
+static __device__ __forceinline__ void yka_commit(YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch, const YkGeomS& g, int pid, int rp,
+                                                  int gx0, int gy0, int tlx, int tly) {
     const int TW = 1 << g.shx, TH = 1 << g.shy;
-    const int sub = (ly0 >> g.lbh) * (64 >> g.lbw) + (lx0 >> g.lbw);
-    const int li = sub * g.bits + (((ly0 & ((1 << g.lbh) - 1)) >> g.shy) << (g.lbw - g.shx)) + ((lx0 & ((1 << g.lbw) - 1)) >> g.shx);
-    atomicOr(&R.bits[pid][li >> 5], 1u << (li & 31));                          // EC.cpp:4026
-    atomicAdd(&R.stat[pid][YK_ST_TILEDONE], 1);                                // EC.cpp:4039-4044 (mins stored as extent - value)
-    atomicMax(&R.stat[pid][YK_ST_MINX], R.w - (R.X0 + lx0));
-    atomicMax(&R.stat[pid][YK_ST_MINY], INT_MAX / 2 - (R.yOrg + R.Y0 + ly0));
-    atomicMax(&R.stat[pid][YK_ST_MAXX], R.X0 + lx0 + TW);
-    atomicMax(&R.stat[pid][YK_ST_MAXY], R.yOrg + R.Y0 + ly0 + TH);
-    const int i0 = lx0 >> 2, j0 = ly0 >> 2;                                    // mappedRGB claim, EC.cpp:4001-4021
-    atomicOr(&R.touch[j0 * 17 + i0], 1u << (4 * rp + 0));
-    atomicOr(&R.touch[j0 * 17 + i0 + (TW >> 2)], 1u << (4 * rp + 1));
-    atomicOr(&R.touch[(j0 + (TH >> 2)) * 17 + i0], 1u << (4 * rp + 2));
-    atomicOr(&R.touch[(j0 + (TH >> 2)) * 17 + i0 + (TW >> 2)], 1u << (4 * rp + 3));
+    const int nSwzX = (C.w + (1 << g.lbw) - 1) >> g.lbw;
+    const int pos = yk_pos_s(g, nSwzX, gx0 >> g.shx, gy0 >> g.shy);
+    atomicOr(&C.bitmap32[pid][pos >> 5], 1u << (pos & 31));                    // EC.cpp:4026
+    // EC.cpp:4039-4044 (mins stored as extent - value)
+    yka_stat5(sh, C, YK_HD_PASS0 + pid * YK_ST_STRIDE, 1, C.w - gx0, INT_MAX / 2 - (C.yOrg + gy0), gx0 + TW, C.yOrg + gy0 + TH);
+    const int i0 = tlx >> 2, j0 = tly >> 2;                                    // mappedRGB claim, EC.cpp:4001-4021
+    atomicOr(&touch[j0 * 5 + i0], 1u << (4 * rp + 0));
+    atomicOr(&touch[j0 * 5 + i0 + (TW >> 2)], 1u << (4 * rp + 1));
+    atomicOr(&touch[(j0 + (TH >> 2)) * 5 + i0], 1u << (4 * rp + 2));
+    atomicOr(&touch[(j0 + (TH >> 2)) * 5 + i0 + (TW >> 2)], 1u << (4 * rp + 3));
 }
 
 // One FittingQuadSmooth pass over one 16x16 macro tile, by one warp.  Lane (row = lane >> 1, half = lane & 1) owns the
-// eight pixels (8*half .. 8*half+7, row) of the macro tile in every pass — they are loaded once into `pw` — so a tile
+// eight pixels (8*half .. 8*half+7, row) of the macro tile in every pass, so a tile
 // of 8 or 16 pixels width is shared by the lanes of its rows, and a 4-pixel-wide pass is run as two sub-passes (left and
 // right quad of every lane).  `claimed` (16 bits, bit = 4*cellY + cellX) is warp-uniform and returned updated.
-static __device__ __forceinline__ unsigned yka_macro_pass(const uint8_t* __restrict__ priv, YkaRegion& Rg, int pid, int rp, int mlx, int mly,
-                                                          unsigned claimed, unsigned poss, const uint2 (&pw)[3], int rej) {
+static __device__ __forceinline__ unsigned yka_macro_pass(const uint8_t* __restrict__ priv, YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch,
+                                                          int pid, int rp, int gmx, int gmy, unsigned claimed, unsigned poss, int rej) {
     const YkGeomS g = yk_geom_s(pid);
     const int lane = threadIdx.x & 31, row = lane >> 1, half = lane & 1;
     const int shx = g.shx, shy = g.shy, TH = 1 << shy;
@@ -396,13 +407,13 @@ static __device__ __forceinline__ unsigned yka_macro_pass(const uint8_t* __restr
         const int cellX = lxT >> 2, cellY = lyT >> 2;
         const bool active = ((poss >> t) & 1u) && !((claimed >> (cellY * 4 + cellX)) & 1u);      // EC.cpp:3818, 3826, 3871-3875
         if (!__any_sync(YK_FULL, active)) continue;
-        unsigned wd[3][2];
+        uint2 pw[3];                                        // this lane's eight pixels of the macro tile, three channels
 #pragma unroll
-        for (int c = 0; c < 3; c++) { wd[c][0] = (shx == 2 && sub) ? pw[c].y : pw[c].x; wd[c][1] = pw[c].y; }
-        const bool acc = yka_tile_test(priv + lyT * YKP_RS + lxT, T, wd, gmask, active);
+        for (int c = 0; c < 3; c++) pw[c] = *reinterpret_cast<const uint2*>(priv + c * YKP_CH + row * YKP_RS + 8 * half);
+        const bool acc = yka_tile_test(priv + lyT * YKP_RS + lxT, T, pw, shx == 2 && sub, gmask, active);
         unsigned mine = 0;
         if (acc && leader) {
-            yka_commit(Rg, g, pid, rp, mlx + lxT, mly + lyT);
+            yka_commit(sh, C, touch, g, pid, rp, gmx + lxT, gmy + lyT, lxT, lyT);
             // EC.cpp:4029-4037: the tile's cells become claimed
             const unsigned cols = ((1u << (1 << (shx - 2))) - 1u) << cellX;
             const unsigned rowsPat = (0x1111u & ((1u << (4 << (shy - 2))) - 1u)) << (4 * cellY);
@@ -416,7 +427,7 @@ static __device__ __forceinline__ unsigned yka_macro_pass(const uint8_t* __restr
 // DynamicTileCompressor (EC.cpp:8398-8522) for the 8x8 tile at (lx8, ly8) of the macro tile; q = its quadrants to code
 // (bit0 TL, 1 TR, 2 BL, 3 BR: top-left map pixel 0, EC.cpp:8420-8430 == 4x4 cell unclaimed).  Lane = two pixels; the
 // three planes side by side.  Output goes to the tile's fixed place in r2Raw / r2RawType.
-static __device__ __forceinline__ void yka_range_tile(const uint8_t* __restrict__ priv, const YkaRegion& Rg, uint8_t* __restrict__ hist,
+static __device__ __forceinline__ void yka_range_tile(const uint8_t* __restrict__ priv, const YkaSlotC& Rg, uint8_t* __restrict__ hist,
                                                       const uint32_t* __restrict__ magicTab, size_t tile, int lx8, int ly8, unsigned q) {
     const int lane = threadIdx.x & 31;
     const int r = lane >> 2, c0 = (lane & 3) * 2;           // pixel row / first column of this lane inside the tile
@@ -482,134 +493,85 @@ static __device__ __forceinline__ void yka_range_tile(const uint8_t* __restrict_
     __syncwarp();       // the histogram entries are clean again before the next tile fills them
 }
 
-// One (region, macro tile) work item after its pixels have been packed: the cascade of Convert()'s passes
-// (EC.cpp:9057-9093), the corner colours of its lattice points, then the range stage.
-static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaRegion& R, const YkRun& run, const uint32_t* sTab, uint8_t* hist,
-                                      const uint32_t* magicTab, int m) {
+// One macro tile after its pixels have been packed: the cascade of Convert()'s passes (EC.cpp:9057-9093), its results,
+// the corner colours of its lattice points, then the range stage.  (gmx, gmy) = origin of the macro tile in the image.
+static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch, uint8_t* hist,
+                                      const uint32_t* magicTab, int gmx, int gmy) {
     const int lane = threadIdx.x & 31;
-    const int mx = m & 3, my = m >> 2, mlx = 16 * mx, mly = 16 * my;
+    const YkRun& run = sh.run;
+    const int wIn = C.w - gmx, hIn = C.h - gmy;              // image extent seen from the macro tile's origin
+    if (wIn <= 0 || hIn <= 0) return;
+    // claimed 4x4 cells of the macro tile (bit = 4*cellY + cellX); cells outside the image count as claimed
     unsigned claimed = 0;
-#pragma unroll
-    for (int r = 0; r < 4; r++) claimed |= ((R.cell[my * 4 + r] >> (4 * mx)) & 15u) << (4 * r);
+    const int cx0 = gmx >> 2, cy0 = gmy >> 2, cellWord = cx0 >> 4, cellShift = cx0 & 15;
+    if (!run.fresh) {
+        unsigned rowBits = 0;
+        if (lane < 4 && 4 * lane < hIn) {
+            const int e = (cy0 + lane) * C.nbx + cellWord;
+            rowBits = ((__ldg(&C.cellMask32[e >> 1]) >> (16 * (e & 1) + cellShift)) & 15u) << (4 * lane);
+        }
+        claimed = __reduce_or_sync(YK_FULL, rowBits);
+    }
+    {
+        const int cw = min(4, wIn >> 2), chh = min(4, hIn >> 2);
+        const unsigned inside = (((1u << cw) - 1u) * 0x1111u) & ((1u << (4 * chh)) - 1u);
+        claimed |= ~inside & 0xFFFFu;
+    }
     const unsigned claimed0 = claimed;
     const int nPasses = run.nPasses;
-    const int wIn = R.w - R.X0 - mlx, hIn = R.h - R.Y0 - mly;       // image extent seen from the macro tile's origin
-    if (nPasses > 0 && claimed != 0xFFFFu) {
-        uint2 pw[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-            pw[c] = *reinterpret_cast<const uint2*>(priv + c * YKP_CH + (lane >> 1) * YKP_RS + 8 * (lane & 1));
-        // the 16x16 pass usually runs first and straight away (most macro tiles of illustration-like content end there);
-        // the other shapes are pre-tested together, once, the first time one of them comes up
-        unsigned long long P = (wIn >= 16 && hIn >= 16) ? 1ull : 0ull;
-        bool pretested = false;
-        const int rej = run.rejectFactor;
-        for (int rp = 0; rp < nPasses && claimed != 0xFFFFu; rp++) {
-            const int pid = run.passId[rp];
-            if (pid != 0 && !pretested) { P = yka_pretest(priv, sTab, wIn, hIn, claimed, rej); pretested = true; }
-            const YkGeomS g = yk_geom_s(pid);
-            const unsigned poss = (unsigned)(P >> g.start) & ((1u << (256 >> (g.shx + g.shy))) - 1u);
-            if (poss) claimed = yka_macro_pass(priv, R, pid, rp, mlx, mly, claimed, poss, pw, rej);
+    if (nPasses > 0) {
+        if (lane < 25) touch[lane] = 0;
+        __syncwarp();
+        if (claimed != 0xFFFFu) {
+            // the 16x16 pass usually runs first and straight away (most macro tiles of illustration-like content end there);
+            // the other shapes are pre-tested together, once, the first time one of them comes up
+            unsigned long long P = (wIn >= 16 && hIn >= 16) ? 1ull : 0ull;
+            bool pretested = false;
+            const int rej = run.rejectFactor;
+            for (int rp = 0; rp < nPasses && claimed != 0xFFFFu; rp++) {
+                const int pid = run.passId[rp];
+                if (pid != 0 && !pretested) { P = yka_pretest(priv, sh.pretestTab, wIn, hIn, claimed, rej); pretested = true; }
+                const YkGeomS g = yk_geom_s(pid);
+                const unsigned poss = (unsigned)(P >> g.start) & ((1u << (256 >> (g.shx + g.shy))) - 1u);
+                if (poss) claimed = yka_macro_pass(priv, sh, C, touch, pid, rp, gmx, gmy, claimed, poss, rej);
+            }
+            // EC.cpp:4029-4037: newly claimed cells
+            const unsigned fresh4 = ((claimed & ~claimed0) >> (4 * (lane & 3))) & 15u;
+            if (lane < 4 && fresh4) {
+                const int e = (cy0 + lane) * C.nbx + cellWord;
+                atomicOr(&C.cellMask32[e >> 1], fresh4 << (16 * (e & 1) + cellShift));
+            }
         }
-        if (lane < 4 && claimed != claimed0) atomicOr(&R.cell[my * 4 + lane], ((claimed >> (4 * lane)) & 15u) << (4 * mx));
-    }
-    if (nPasses > 0 && lane < 25) {
-        // corner colours at the 4-pixel lattice points of the macro tile (what an accepted tile would emit, EC.cpp:4115-4132);
-        // the points on its right / bottom edge belong to the next macro tile unless the image ends there
-        const int jj = lane / 5, i = lane - jj * 5;
-        const int gx = ((R.X0 + mlx) >> 2) + i, gy = ((R.Y0 + mly) >> 2) + jj;
-        if (wIn > 0 && hIn > 0 && (i < 4 || wIn <= 16) && (jj < 4 || hIn <= 16) && gx < R.latW && gy < R.latH) {
-            uint8_t* d = R.latRGB + ((size_t)gy * R.latW + gx) * 3;
+        __syncwarp();
+        if (lane < 25) {
+            // the macro tile's 5x5 lattice points: their touch words, and the corner colour an accepted tile would emit
+            // there (EC.cpp:4115-4132); the points on the right / bottom edge belong to the next macro tile unless the image ends there
+            const int jj = lane / 5, i = lane - jj * 5;
+            const int gx = cx0 + i, gy = cy0 + jj;
+            if (gx < C.latW && gy < C.latH) {
+                const uint32_t tv = touch[lane];
+                if (tv) atomicOr(&C.touchMap[(size_t)gy * C.latW + gx], tv);
+                if ((i < 4 || wIn <= 16) && (jj < 4 || hIn <= 16)) {
+                    uint8_t* d = C.latRGB + ((size_t)gy * C.latW + gx) * 3;
 #pragma unroll
-            for (int c = 0; c < 3; c++) d[c] = (uint8_t)yk_compress250(yk_round6(priv[c * YKP_CH + (4 * jj) * YKP_RS + 4 * i]));
+                    for (int c = 0; c < 3; c++) d[c] = (uint8_t)yk_compress250(yk_round6(priv[c * YKP_CH + (4 * jj) * YKP_RS + 4 * i]));
+                }
+            }
         }
     }
     if (run.doR2 && claimed != 0xFFFFu) {
-        const int tilesW = R.w >> 3;
+        const int tilesW = C.w >> 3;
 #pragma unroll 1
         for (int t8 = 0; t8 < 4; t8++) {
             const int qx = t8 & 1, qy = t8 >> 1;
             const unsigned c4 = claimed >> (8 * qy + 2 * qx);
             const unsigned q = (~((c4 & 3u) | (((c4 >> 4) & 3u) << 2))) & 15u;
             if (q) {
-                const size_t tile = (size_t)((R.Y0 + mly + 8 * qy) >> 3) * tilesW + ((R.X0 + mlx + 8 * qx) >> 3);
-                yka_range_tile(priv, R, hist, magicTab, tile, 8 * qx, 8 * qy, q);
+                const size_t tile = (size_t)((gmy + 8 * qy) >> 3) * tilesW + ((gmx + 8 * qx) >> 3);
+                yka_range_tile(priv, C, hist, magicTab, tile, 8 * qx, 8 * qy, q);
             }
         }
     }
-}
-
-// Results of a finished region, by one warp: accept bitmaps, claimed cells, touch words of its lattice points, alpha
-// tiles, per-pass counters.  Leaves the region state zeroed for the next region that uses it.
-static __device__ void yka_finalize(const YkSlotDev& S, YkaRegion& R, const YkRun& run) {
-    const int lane = threadIdx.x & 31;
-    const int w = R.w, h = R.h, X0 = R.X0, Y0 = R.Y0, nbx = S.nbx, bx = R.bx;
-    // accept bitmaps in the reference's swizzled layout: 16-bit units of each sub-block
-    for (int i = lane; i < run.nPasses * 16; i += 32) {
-        const int pid = run.passId[i >> 4], u = i & 15;
-        const YkGeomS g = yk_geom_s(pid);
-        const int nsub = (64 >> g.lbw) * (64 >> g.lbh);
-        if (u * 16 < nsub * g.bits) {
-            const int sub = (u * 16) / g.bits, within = (u * 16) % g.bits;
-            const int sx = X0 + ((sub % (64 >> g.lbw)) << g.lbw), sy = Y0 + ((sub / (64 >> g.lbw)) << g.lbh);
-            if (sx < w && sy < h) {
-                const int nSwzX = (w + (1 << g.lbw) - 1) >> g.lbw;
-                const int gb = (sy >> g.lbh) * nSwzX + (sx >> g.lbw);
-                const uint32_t v = (R.bits[pid][(u * 16) >> 5] >> ((u * 16) & 31)) & 0xFFFFu;
-                reinterpret_cast<uint16_t*>(S.bitmap[pid])[((size_t)gb * g.bits + within) >> 4] = (uint16_t)v;
-            }
-        }
-    }
-    if (lane < 16 && run.nPasses > 0) {
-        const int cy = (Y0 >> 2) + lane;
-        if (cy * 4 < h) S.cellMask[(size_t)cy * nbx + bx] = (uint16_t)R.cell[lane];
-    }
-    // touch words of the lattice points (interior points are exclusive to the region, border points are shared)
-    if (run.nPasses > 0) {
-        const int latW = R.latW, latH = R.latH;
-        uint32_t* __restrict__ touchMap = S.touchMap;
-        for (int idx = lane; idx < 17 * 17; idx += 32) {
-            const uint32_t tv = R.touch[idx];
-            if (tv) {
-                const int jj = idx / 17, i = idx - jj * 17;
-                const int gx = (X0 >> 2) + i, gy = (Y0 >> 2) + jj;
-                if (gx < latW && gy < latH) atomicOr(&touchMap[(size_t)gy * latW + gx], tv);
-                R.touch[idx] = 0;
-            }
-        }
-    }
-    if (R.doAlpha) {
-        const int tx = lane & 3, ty = (lane >> 2) & 3;
-        const int px = X0 + 16 * tx, py = Y0 + 16 * ty;
-        const bool in = lane < 16 && px < w && py < h;
-        const bool kept = in && ((R.alpha >> lane) & 1u);
-        if (in) S.alphaKept[(size_t)(py >> 4) * ((w + 15) >> 4) + (px >> 4)] = kept ? 1 : 0;
-        // bounding box of kept tiles (EC.cpp:416-422), mins stored as extent - value so the header can be memset to 0
-        const int big = INT_MAX / 2;
-        const int mnx = __reduce_max_sync(YK_FULL, kept ? w - px : 0);
-        const int mny = __reduce_max_sync(YK_FULL, kept ? big - (R.yOrg + py) : 0);
-        const int mxx = __reduce_max_sync(YK_FULL, kept ? min(px + 16, w) : 0);
-        const int mxy = __reduce_max_sync(YK_FULL, kept ? R.yOrg + min(py + 16, h) : 0);
-        const int cnt = __popc(__ballot_sync(YK_FULL, kept));
-        if (lane == 0 && cnt) {
-            atomicMax(&R.hdr[YK_HD_ALPHA_MINX], mnx); atomicMax(&R.hdr[YK_HD_ALPHA_MINY], mny);
-            atomicMax(&R.hdr[YK_HD_ALPHA_MAXX], mxx); atomicMax(&R.hdr[YK_HD_ALPHA_MAXY], mxy);
-            atomicAdd(&R.hdr[YK_HD_ALPHA_KEPT], cnt);
-        }
-    }
-    if (lane < YK_NPASS) {
-        const int pid = lane;
-        if (R.stat[pid][YK_ST_TILEDONE] > 0) {
-            int* d = R.hdr + YK_HD_PASS0 + pid * YK_ST_STRIDE;
-            atomicAdd(&d[YK_ST_TILEDONE], R.stat[pid][YK_ST_TILEDONE]);
-            atomicMax(&d[YK_ST_MINX], R.stat[pid][YK_ST_MINX]); atomicMax(&d[YK_ST_MINY], R.stat[pid][YK_ST_MINY]);
-            atomicMax(&d[YK_ST_MAXX], R.stat[pid][YK_ST_MAXX]); atomicMax(&d[YK_ST_MAXY], R.stat[pid][YK_ST_MAXY]);
-        }
-    }
-    __syncwarp();
-    for (int i = lane; i < YK_NPASS * 8; i += 32) (&R.bits[0][0])[i] = 0;
-    for (int i = lane; i < YK_NPASS * YK_ST_STRIDE; i += 32) (&R.stat[0][0])[i] = 0;
-    if (lane == 0) { R.alpha = 0; R.done = 0; }
 }
 
 #ifdef YK_TIMING
@@ -641,7 +603,7 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRe
     YkaShared& sh = *reinterpret_cast<YkaShared*>(smem + YKA_SMEM_RAW + YKA_SMEM_PIX + YKA_SMEM_HIST + 1024);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int total = nSlots * nRegions;
+    const int unitsPerSlot = nRegions * 4, total = nSlots * unitsPerSlot;
 
     // ---- start-up (the only block-wide barriers)
     for (int i = tid; i < (int)(sizeof(YkaShared) / 4); i += YKA_THREADS) reinterpret_cast<uint32_t*>(&sh)[i] = 0;
@@ -649,11 +611,13 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRe
     if (tid < 256) sMagic[tid] = tid ? ((1u << 20) + (unsigned)tid - 1u) / (unsigned)tid : 0u;
     __syncthreads();
     if (tid < 41) sh.pretestTab[tid] = yka_pretest_entry(tid);
-    if (tid == 64) {
+    if (tid >= 64 && tid < 64 + YKA_CONS_WARPS) sh.slotc[tid - 64].slot = -1;
+    if (tid == 96) {
         sh.run = runArg;
         sh.endSeq = INT_MAX;
+        sh.statSlot = -1;
+        sh.consLeft = YKA_CONS_WARPS;
         for (int i = 0; i < YKA_NR; i++) { yka_mbar_init(&sh.rawFull[i], 1); yka_mbar_init(&sh.rawFree[i], 4); }
-        for (int j = 0; j < YKA_NBS; j++) yka_mbar_init(&sh.freed[j], 1);
 #ifndef YK_EMULATE
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
@@ -661,94 +625,120 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRe
     __syncthreads();
     const YkRun& run = sh.run;
 
-    if (warp == YKA_CONS_WARPS) {
-        // ================================================== producer ==================================================
-        // unit u = macro-tile row (u & 3) of this CTA's (u >> 2)-th region; raw buffer u % YKA_NR, region state (u >> 2) % YKA_NBS
+    if (warp == 0) {
+        // ================================================== producer (warp 0: the oldest warp of its scheduler) ==================================================
+        // u-th unit of this CTA -> raw buffer u % YKA_NR
         int* ticket = slots[slot0].hdr + YK_HD_TICKET_ANALYZE;
         const bool wantAlpha = run.doAlpha != 0;
-        int lastSlot = -1, nextItem = -1;
-        // of the current region (lane 0 issues; every lane keeps them so the region state can be initialised together)
+        // tickets: lane 0 holds YKA_TICKETS tickets in separate registers (the loop is unrolled by that many units), each
+        // fetched YKA_TICKETS units ahead, so that the latency of the global atomic is never on the path of a unit
+        int tk[YKA_TICKETS];
+        // of the image the current unit belongs to (kept in registers while the slot does not change)
+        int curSlot = -1, alpha = 0;
         const YkSlotDev* S = nullptr;
-        int bx = 0, by = 0, alpha = 0;
-        if (lane == 0) { const int t = atomicAdd(ticket, 1); nextItem = t < total ? t : -1; }
-        nextItem = __shfl_sync(YK_FULL, nextItem, 0);
+        // every image of a launch has the same size: region -> (bx, by) by a multiply-high (exact for region * nbx < 2^32)
+        const int nbx = slots[slot0].nbx;
+        const unsigned nbxMagic = nbx > 1 ? 0xFFFFFFFFu / (unsigned)nbx + 1u : 0u;
+#pragma unroll
+        for (int r = 0; r < YKA_TICKETS; r++) { tk[r] = total; if (lane == 0) tk[r] = atomicAdd(ticket, 1); }
         YKT_DECL;
-        for (int u = 0;; u++) {
-            const int i = u % YKA_NR, n = u >> 2, k = u & 3, j = n % YKA_NBS;
-            if (k == 0) {
-                // next region: its ticket was fetched one region ahead
-                const int item = nextItem;
-                if (item < 0) { if (lane == 0) yka_flag_st(&sh.endSeq, n); break; }
-                if (lane == 0) { const int t = atomicAdd(ticket, 1); nextItem = t < total ? t : -1; }
-                const int slot = slot0 + item / nRegions, region = item % nRegions;
-                S = &slots[slot];
-                if (slot != lastSlot) {
-                    if (lane < S->nPlanes) yka_tmap_acquire(&S->tmap[lane]);
-                    lastSlot = slot;
-                }
-                const int nbx = S->nbx;
-                bx = region % nbx; by = region / nbx;
-                alpha = wantAlpha && S->nPlanes == 4;
-                if (n >= YKA_NBS) yka_mbar_wait(&sh.freed[j], (unsigned)((n / YKA_NBS - 1) & 1));
-                yka_region_init(*S, sh.reg[j], slot, bx, by, alpha, lane);
-                __threadfence_block();
-                __syncwarp();
+        for (int u0 = 0;; u0 += YKA_TICKETS) {
+#pragma unroll
+            for (int r = 0; r < YKA_TICKETS; r++) {
+                const int u = u0 + r, i = u % YKA_NR;
+                // never more than YKA_LOOKAHEAD units ahead of the consumers: the CTAs then run out of work together
+                while (u - (yka_flag_ld(&sh.queueHead) >> 2) > YKA_LOOKAHEAD) yk_spin();
+                if (u >= YKA_NR) yka_mbar_wait(&sh.rawFree[i], (unsigned)((u / YKA_NR - 1) & 1));
                 if (lane == 0) YKT(0);
+                const int item = __shfl_sync(YK_FULL, tk[r], 0);
+                if (lane == 0) YKT(6);
+                if (item >= total) { if (lane == 0) yka_flag_st(&sh.endSeq, u); return; }
+                if (lane == 0) tk[r] = atomicAdd(ticket, 1);            // not looked at before the unit that uses it
+                if (lane == 0) YKT(7);
+                int slot = slot0, rem = item;
+                if (nSlots > 1) { const int q = item / unitsPerSlot; slot += q; rem -= q * unitsPerSlot; }
+                if (slot != curSlot) {
+                    S = &slots[slot];
+                    if (lane < S->nPlanes) yka_tmap_acquire(&S->tmap[lane]);
+                    alpha = wantAlpha && S->nPlanes == 4;
+                    curSlot = slot;
+                    if (u == 0 && lane == 0) sh.statSlot = slot;
+                }
+                const int region = rem >> 2, k = rem & 3;
+                const int by = nbx > 1 ? (int)__umulhi((unsigned)region, nbxMagic) : region, bx = region - by * nbx;
+                if (lane == 0) {
+                    YKT(3);
+                    YkaUnit& U = sh.unit[i];
+                    U.slot = slot; U.bx = bx; U.by = by; U.k = k; U.alpha = alpha;
+                    int32_t* dst = raw + i * YKA_RAW_STAGE_INTS;
+                    yka_fence_async();
+                    yka_mbar_expect_tx(&sh.rawFull[i], YKA_COLOR_TX + (alpha ? YKA_ALPHA_TX : 0u));
+                    for (int c = 0; c < 3; c++)
+                        yka_tma_box(dst + c * YKA_RAW_PLANE_INTS, &S->tmap[c], bx * 64, by * 64 + 16 * k, YK_RAW_PITCH, YK_RAW_ROWS, &sh.rawFull[i], !alpha && c == 2);
+                    if (alpha) yka_tma_box(dst + 3 * YKA_RAW_PLANE_INTS, &S->tmap[3], bx * 64, by * 64 + 16 * k, 64, 16, &sh.rawFull[i], 1);
+                    YKT(2);
+                }
             }
-            if (u >= YKA_NR) yka_mbar_wait(&sh.rawFree[i], (unsigned)((u / YKA_NR - 1) & 1));
-            if (lane == 0) {
-                YKT(1);
-                int32_t* dst = raw + i * YKA_RAW_STAGE_INTS;
-                yka_fence_async();
-                yka_mbar_expect_tx(&sh.rawFull[i], YKA_COLOR_TX + (alpha ? YKA_ALPHA_TX : 0u));
-                for (int c = 0; c < 3; c++)
-                    yka_tma_box(dst + c * YKA_RAW_PLANE_INTS, &S->tmap[c], bx * 64, by * 64 + 16 * k, YK_RAW_PITCH, YK_RAW_ROWS, &sh.rawFull[i], !alpha && c == 2);
-                if (alpha) yka_tma_box(dst + 3 * YKA_RAW_PLANE_INTS, &S->tmap[3], bx * 64, by * 64 + 16 * k, 64, 16, &sh.rawFull[i], 1);
-                YKT(2);
-            }
-            if (k == 3) nextItem = __shfl_sync(YK_FULL, nextItem, 0);
         }
         return;
     }
 
     // ===================================================== consumers =====================================================
-    uint8_t* hist = histAll + warp * 3 * 256;
-    uint8_t* priv = privAll + warp * YKP_TILE;
+    const int cw = warp - 1;                                 // consumer index
+    uint8_t* hist = histAll + cw * 3 * 256;
+    uint8_t* priv = privAll + cw * YKP_TILE;
+    uint32_t* touch = sh.touch[cw];
+    YkaSlotC& C = sh.slotc[cw];
     YKT_DECL;
     for (;;) {
         int q = 0;
         if (lane == 0) q = atomicAdd(&sh.queueHead, 1);
         q = __shfl_sync(YK_FULL, q, 0);
-        const int n = q >> 4, m = q & 15, j = n % YKA_NBS;
-        const int u = 4 * n + (m >> 2), i = u % YKA_NR;
-        YkaRegion& R = sh.reg[j];
+        const int u = q >> 2, mx = q & 3, i = u % YKA_NR;
         bool alive = true;
-        // the macro-tile row of this item has landed (the wait suspends the warp; it wakes up now and then to see
-        // whether the CTA has run out of regions)
+        // the unit of this item has landed (the wait suspends the warp; it wakes up now and then to see whether the
+        // CTA has run out of units)
         while (!yka_mbar_try_wait(&sh.rawFull[i], (unsigned)((u / YKA_NR) & 1))) {
-            if (yka_flag_ld(&sh.endSeq) <= n) { alive = false; break; }
+            if (yka_flag_ld(&sh.endSeq) <= u) { alive = false; break; }
         }
         alive = __all_sync(YK_FULL, alive);
-        if (tid == 0) YKT(8);
+        if (tid == 32) YKT(8);
         if (!alive) break;
-        yka_pack_macro_tile(raw + i * YKA_RAW_STAGE_INTS, priv, R, m & 3, m >> 2);
+        const YkaUnit U = sh.unit[i];
+        const int cachedSlot = C.slot;
+        __syncwarp();                                       // every lane has read the cached id before lane 0 may rewrite it
+        if (cachedSlot != U.slot) yka_slot_refresh(slots[U.slot], C, U.slot);
+        const int X0 = U.bx * 64, Yk = U.by * 64 + 16 * U.k;
+        const bool kept = yka_pack_macro_tile(raw + i * YKA_RAW_STAGE_INTS, priv, C, X0, Yk, mx, U.alpha != 0);
         __syncwarp();
         if (lane == 0) yka_mbar_arrive(&sh.rawFree[i]);      // this warp is done with the raw rows
-        if (tid == 0) YKT(9);
-        yka_macro_tile(priv, R, run, sh.pretestTab, hist, sMagic, m);
-        __threadfence_block();
+        if (tid == 32) YKT(9);
+        const int gmx = X0 + 16 * mx;
+        if (U.alpha && gmx < C.w && Yk < C.h && lane == 0) {
+            C.alphaKept[(size_t)(Yk >> 4) * ((C.w + 15) >> 4) + (gmx >> 4)] = kept ? 1 : 0;
+            if (kept) {
+                // bounding box of kept tiles (EC.cpp:416-422), mins stored as extent - value so that zero means "none"
+                yka_stat5(sh, C, YK_HD_ALPHA_KEPT0, 1, C.w - gmx, INT_MAX / 2 - (C.yOrg + Yk), min(gmx + 16, C.w), C.yOrg + min(Yk + 16, C.h));
+            }
+        }
+        yka_macro_tile(priv, sh, C, touch, hist, sMagic, gmx, Yk);
         __syncwarp();
-        if (tid == 0) YKT(10);
-        int d = 0;
-        if (lane == 0) d = atomicAdd(&R.done, 1);
-        d = __shfl_sync(YK_FULL, d, 0);
-        if (d == 15) {
-            __threadfence_block();
-            yka_finalize(slots[R.slot], R, run);
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) yka_mbar_arrive(&sh.freed[j]);
-            if (tid == 0) YKT(11);
+        if (tid == 32) YKT(10);
+    }
+    // the last consumer warp of the CTA adds the CTA's counters to the image's header
+    __threadfence_block();
+    int left = 0;
+    if (lane == 0) left = atomicSub(&sh.consLeft, 1);
+    left = __shfl_sync(YK_FULL, left, 0);
+    if (left == 1 && sh.statSlot >= 0) {
+        __threadfence_block();
+        int* hdr = slots[sh.statSlot].hdr;
+        for (int idx = YK_HD_ALPHA_KEPT0 + lane; idx < YK_HD_INTS; idx += 32) {
+            const int v = sh.stat[idx];
+            if (v) {
+                const int f = idx < YK_HD_PASS0 ? idx - YK_HD_ALPHA_KEPT0 : (idx - YK_HD_PASS0) % YK_ST_STRIDE;
+                if (f == 0) atomicAdd(&hdr[idx], v); else atomicMax(&hdr[idx], v);
+            }
         }
     }
 }
@@ -778,7 +768,7 @@ int yk_analyze_setup(int* numSMs) {
 #endif
 }
 void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, int gridCtas, const YkRun& run, cudaStream_t st) {
-    const int total = nSlots * nRegions;
+    const int total = nSlots * nRegions * 4;                 // units: macro-tile rows of regions
     const int grid = gridCtas < total ? gridCtas : total;
     YK_LAUNCH(yk_k_analyze, dim3(grid), dim3(YKA_THREADS), YKA_SMEM_BYTES, st, slotsDev, slot0, nSlots, nRegions, run);
 }

@@ -45,6 +45,7 @@ struct YkSlotHost {
     bool r2Valid = false;
     bool zeroAClean = false;     // part A of the zero area is still all zero (nothing launched since the reset)
     bool touchDirty = false;     // the touch map holds claims of an earlier launch (needs folding before the next one)
+    bool cellsClean = false;     // no gradient pass has run since the state was reset (nothing claimed, bitmaps all zero)
     bool pendingHarvest = false; // a run's header has not been copied back yet
     int  lastRunPasses = 0;      // bit p: pass p was in the last run; bit 8: alpha
     int  rangeErr = 0;
@@ -194,8 +195,14 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
     }
     const size_t offR2 = off; off += up(((W / 8) * (H / 8) / 256 + 2) * sizeof(unsigned long long));
     c->zeroABytes = off;
-    const size_t offCell = off; off += up((H / 4 + 1) * nbx * sizeof(uint16_t));
+    const size_t offCell = off; off += up((H / 4 + 1) * nbx * sizeof(uint16_t) + 4);
     const size_t offTouch = off; off += up(latW * latH * sizeof(uint32_t));
+    size_t offBitmap[YK_NPASS];          // accept bits are OR-ed in by yk_k_analyze: zero before the first pass of an image
+    for (int p = 0; p < YK_NPASS; p++) {
+        const YkPassGeom& g = kGeom[p];
+        offBitmap[p] = off;
+        off += up(((W + g.bw - 1) / g.bw) * ((H + g.bh - 1) / g.bh) * (size_t)g.bits / 8 + 8);
+    }
     c->zeroStride = off;
     CK(cudaMalloc((void**)&c->zeroArea, c->zeroStride * maxSlots));
     CK(cudaMemset(c->zeroArea, 0, c->zeroStride * maxSlots));
@@ -214,8 +221,7 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
         if ((rc = dev_alloc(s, &s.d.alphaKept, ((H + 15) / 16) * ((W + 15) / 16)))) return rc;
         for (int p = 0; p < YK_NPASS; p++) {
             const YkPassGeom& g = kGeom[p];
-            size_t nu = ((W + g.bw - 1) / g.bw) * ((H + g.bh - 1) / g.bh);
-            if ((rc = dev_alloc(s, &s.d.bitmap[p], nu * g.bits / 8))) return rc;
+            s.d.bitmap[p] = za + offBitmap[p];
             if ((rc = dev_alloc(s, &s.d.rgb[p], 3 * ((W >> g.shx) + 1) * ((H >> g.shy) + 1)))) return rc;
         }
         if ((rc = dev_alloc(s, &s.d.latRGB, latW * latH * 3))) return rc;
@@ -306,7 +312,7 @@ extern "C" int yk_reset_state(yk_ctx* c, int slot) {
     if (!s.haveImage) return YK_ERR_STATE;
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * slot, 0, c->zeroStride, c->stream));
-    s.zeroAClean = true; s.touchDirty = false;
+    s.zeroAClean = true; s.touchDirty = false; s.cellsClean = true;
     if (s.d.alphaReset || s.d.alphaValid) s.dirty = true;
     s.d.alphaReset = 0; s.d.alphaValid = 0;
     s.k1Ran = s.alphaRan = s.alphaFetched = s.prepared = s.r2Valid = s.pendingHarvest = false;
@@ -385,7 +391,7 @@ static int fetch_hdr(yk_ctx* c, YkSlotHost& s) {
         if (tmp[YK_HD_ERR] & 1) s.rangeErr = 1;
         for (int p = 0; p < YK_NPASS; p++)
             if (s.lastRunPasses & (1 << p)) memcpy(s.hdr + YK_HD_PASS0 + p * YK_ST_STRIDE, tmp + YK_HD_PASS0 + p * YK_ST_STRIDE, YK_ST_STRIDE * sizeof(int));
-        if (s.lastRunPasses & 256) memcpy(s.hdr + YK_HD_ALPHA_MINX, tmp + YK_HD_ALPHA_MINX, 5 * sizeof(int));
+        if (s.lastRunPasses & 256) memcpy(s.hdr + YK_HD_ALPHA_KEPT0, tmp + YK_HD_ALPHA_KEPT0, 5 * sizeof(int));
         s.hdr[YK_HD_R2_CHUNKS] = tmp[YK_HD_R2_CHUNKS]; s.hdr[YK_HD_R2_TILES] = tmp[YK_HD_R2_TILES];
     }
     return s.rangeErr ? YK_ERR_RANGE : YK_OK;
@@ -407,11 +413,25 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
         s.zeroAClean = false;
         if (s.touchDirty && run.nPasses > 0) needFold = true;
     }
+    bool fresh = true;
+    for (int i = slot0; i < slot0 + nSlots; i++) {
+        YkSlotHost& s = c->slots[i];
+        if (!s.cellsClean) {
+            fresh = false;
+            // a pass that runs again on a used state starts from an empty bitmap (FittingQuadSmooth allocates pFillBitMap per call, EC.cpp:3770-3777)
+            for (int p = 0; p < run.nPasses; p++) {
+                const YkPassGeom& g = kGeom[run.passId[p]];
+                const size_t nb = (size_t)((s.d.w + g.bw - 1) / g.bw) * ((s.d.h + g.bh - 1) / g.bh) * g.bits / 8;
+                CK(cudaMemsetAsync(s.d.bitmap[run.passId[p]], 0, nb, c->stream));
+            }
+        }
+    }
     if ((rc = upload_slots(c, slot0, nSlots))) return rc;
     if (needFold) { yk_launch_fold_touch(c->slotsDev, slot0, nSlots, a.d.latW * a.d.latH, c->stream); c->launches++; }
     const bool r2Domain = doR2 && !(a.d.w & 7) && !(a.d.h & 7);
     YkRun krun = run;
     krun.doR2 = r2Domain ? 1 : 0;
+    krun.fresh = fresh ? 1 : 0;
     if (krun.nPasses > 0 || krun.doAlpha || krun.doR2) {
         YkTimed t(c, 0);
         yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, c->numSMs, krun, c->stream); c->launches++;
@@ -437,7 +457,7 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
         s.k1Ran = true; s.pendingHarvest = true; s.lastRunPasses = (run.doAlpha ? 256 : 0);
         for (int p = 0; p < run.nPasses; p++) s.lastRunPasses |= 1 << run.passId[p];
         if (run.doAlpha && s.d.nPlanes == 4) { s.alphaRan = true; s.alphaFetched = false; }
-        if (run.nPasses > 0) { s.r2Valid = false; s.touchDirty = true; }
+        if (run.nPasses > 0) { s.r2Valid = false; s.touchDirty = true; s.cellsClean = false; }
         if (doR2) s.r2Valid = true;
     }
     return YK_OK;
@@ -472,7 +492,7 @@ static int alpha_finish(yk_ctx* c, YkSlotHost& s) {
     if (rc) return rc;
     const int w = s.d.w, h = s.d.h, big = INT_MAX / 2;
     const int tw = (w + 15) / 16, th = (h + 15) / 16;
-    if (s.hdr[YK_HD_ALPHA_KEPT] == 0) return YK_ERR_ARG;        // fully transparent: outside the reference's domain (sentinel bbox)
+    if (s.hdr[YK_HD_ALPHA_KEPT0] == 0) return YK_ERR_ARG;        // fully transparent: outside the reference's domain (sentinel bbox)
     const int L = w - s.hdr[YK_HD_ALPHA_MINX], T = big - s.hdr[YK_HD_ALPHA_MINY];
     const int R = s.hdr[YK_HD_ALPHA_MAXX], B = s.hdr[YK_HD_ALPHA_MAXY];
     s.bound[0] = L; s.bound[1] = T; s.bound[2] = R; s.bound[3] = B;

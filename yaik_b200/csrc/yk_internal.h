@@ -23,7 +23,8 @@ enum { YK_ST_TILEDONE = 0, YK_ST_MINX, YK_ST_MINY, YK_ST_MAXX, YK_ST_MAXY, YK_ST
 // per-slot header ints (device memory, zeroed/initialised before each run)
 enum {
     YK_HD_ERR = 0,                 // bit0: sample outside 0..255
-    YK_HD_ALPHA_MINX, YK_HD_ALPHA_MINY, YK_HD_ALPHA_MAXX, YK_HD_ALPHA_MAXY, YK_HD_ALPHA_KEPT,
+    YK_HD_ALPHA_KEPT0,             // alpha stage: kept tiles, then their box (count first, like a pass's counters)
+    YK_HD_ALPHA_MINX, YK_HD_ALPHA_MINY, YK_HD_ALPHA_MAXX, YK_HD_ALPHA_MAXY,
     YK_HD_R2_CHUNKS, YK_HD_R2_TILES,        // totals from the scan: 16-byte chunks per plane, coded tiles per plane
     YK_HD_R1_NIB0, YK_HD_R1_NIB1, YK_HD_R1_NIB2, YK_HD_R1_DEF0, YK_HD_R1_DEF1, YK_HD_R1_DEF2,
     YK_HD_TICKET_EMIT, YK_HD_TICKET_ANALYZE, // work tickets: emission groups in stream order / regions of the persistent analysis kernel
@@ -83,6 +84,7 @@ struct YkRun {
     int rejectFactor;
     int doAlpha;
     int doR2;                   // code the DynamicTileCompressor tiles of every region after its cascade
+    int fresh;                  // no cell is claimed yet (first gradient launch after yk_reset_state): cellMask need not be read
 };
 
 #ifdef __cplusplus
