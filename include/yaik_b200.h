@@ -150,17 +150,47 @@ long long yk_launch_count(yk_ctx* ctx);
 int  yk_profile(yk_ctx* ctx, int enable);
 int  yk_profile_read(yk_ctx* ctx, double ms[8], long long count[8]);
 
-/* ---- multi-GPU: tile-row strips of one large image ------------------------------------
- * A strip context holds rows [y0, y0+h) of an image of height imgH (h a multiple of 64 except for the last
- * strip).  It needs (i) one pixel row below the strip (the clamped bottom corners of its last tile row) and
- * (ii) per pass the accept bits of the neighbours' adjacent tile rows, so both sides agree on who owns the
- * boundary lattice row.  Both are plain device buffers that the neighbour fills over NVLink P2P
- * (cudaMemcpyPeer / cudaIpc*), no collective. */
+/* ---- multi-GPU: tile-row strips of one large image (BASELINE.json configs[3]) -------------
+ * The reference has no counterpart (Convert() walks one image on one thread); this is the partition of
+ * FittingQuadSmooth / DynamicTileCompressor over GPUs.  A strip holds rows [y0, y0+h) of an image of height
+ * imgH (y0 a multiple of 64 = the largest swizzle block, h a multiple of 64 except for the last strip), as
+ * an ordinary image of its own context (yk_set_image), then:
+ *   yk_strip_config      declares the strip's place and allocates its halo-in buffer
+ *   (exchange 1)         every strip copies its first pixel row (3 planes) into the halo of the strip above:
+ *                        the clamped bottom corners of that strip's last tile row become the real samples
+ *   yk_strip_phase 0     accept decisions + range stage of the strip (yk_k_analyze)
+ *   (exchange 2)         every strip copies the touch words of its top / bottom boundary lattice row into
+ *                        the halo of the strip above / below, so both sides agree on who emits those corners
+ *                        (a tile of the upper strip precedes every tile of the lower strip in a pass's stream)
+ *   yk_strip_phase 1     corner ownership + rgbStream emission + range-stream gather
+ * and the per-pass getters return the strip's part: bitmaps are consecutive byte ranges of the image's
+ * bitmaps, rgb / range streams concatenate in strip order, TileDone adds up, boxes merge (they are in image
+ * coordinates).  The two exchanges are plain device-to-device copies (NVLink P2P through CUDA IPC between
+ * the per-GPU processes), never a collective.  Only the fused 7-pass form on a fresh state is provided. */
+typedef struct yk_strip_halo {
+    void*  haloIn;                 /* one device allocation of this strip, written by its neighbours */
+    size_t haloBytes;
+    size_t pixelRowInOffset, pixelRowBytes;      /* 3 planes x w int32: first pixel row of the strip below */
+    size_t touchInTopOffset, touchInBottomOffset, touchBytes;   /* latW u32 each: boundary touch words of the strip above / below */
+    const void* pixelRowOut[3];    /* this strip's first pixel row, per colour plane (planeRowBytes each) */
+    size_t planeRowBytes;
+    const void* touchOutTop;       /* this strip's touch words of its top / bottom boundary lattice row */
+    const void* touchOutBottom;
+} yk_strip_halo;
 int  yk_strip_config(yk_ctx* ctx, int slot, int imgH, int y0);
-int  yk_strip_halo_ptrs(yk_ctx* ctx, int slot, void** pixelRowBelow /* 3*w int32 */, size_t* pixelRowBytes,
-                        void** acceptOut /* this strip's boundary bits */, void** acceptAbove, void** acceptBelow,
-                        size_t* acceptBytes);
+int  yk_strip_halo_ptrs(yk_ctx* ctx, int slot, yk_strip_halo* out);
 int  yk_strip_phase(yk_ctx* ctx, int slot, int phase, int rejectFactor);  /* 0 = accept phase, 1 = emission phase */
+
+/* Plumbing for the exchanges: CUDA IPC handle of a device allocation (64 bytes, to be sent to the neighbour's
+ * process by any host channel), mapping it in this process, and an asynchronous device-to-device copy on the
+ * context's stream (peer access is enabled lazily by the mapping).  yk_copy_to_host / yk_copy_from_host are the
+ * host-staged alternative when the GPUs have no peer access. */
+int  yk_ipc_export(const void* devPtr, unsigned char handle[64]);
+int  yk_ipc_open(yk_ctx* ctx, const unsigned char handle[64], void** devPtr);
+int  yk_ipc_close(yk_ctx* ctx, void* devPtr);
+int  yk_copy_async(yk_ctx* ctx, void* dst, const void* src, size_t bytes);
+int  yk_copy_to_host(yk_ctx* ctx, void* hostDst, const void* devSrc, size_t bytes);
+int  yk_copy_from_host(yk_ctx* ctx, void* devDst, const void* hostSrc, size_t bytes);
 
 #ifdef __cplusplus
 }

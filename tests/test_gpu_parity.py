@@ -138,3 +138,33 @@ def test_out_of_range_sample_is_reported(ctx):
     with pytest.raises(capi.YaikError) as e:
         ctx.gradient_pass(4, 4)
     assert e.value.code == -4
+
+
+# ---- tile-row strips of one large image (BASELINE.json configs[3]) --------------------------------
+@pytest.mark.parametrize("w,h,n", [(256, 512, 2), (256, 512, 4), (192, 328, 3), (2048, 1024, 4)])
+def test_strips_on_one_gpu_match_whole_image(lib, w, h, n):
+    """The strip protocol (pixel-row halo, boundary touch words, merge) with every strip in its own context on this GPU,
+    halo copies device to device: the merged streams must be what the oracle gives for the whole image."""
+    from strips_check import check_against_oracle
+    from yaik_b200 import strips
+    planes = make_image(w, h, 3, SEED_BASE + 3) if w > 256 else cases._patchy(w, h, 43, 4, 3)
+    ctxs = [capi.Context(w, h, planes=3, slots=1, lib=lib) for _ in range(n)]
+    try:
+        merged = strips.LocalTransport(ctxs).run(planes, n_strips=n)
+        check_against_oracle(merged, planes)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_strips_two_ranks_ipc_peer_copies():
+    """Two processes (two GPUs when the box has them, else both on GPU 0), halo exchange by CUDA IPC + peer copies."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29600 + os.getpid() % 300))
+    procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "strips_rank.py"), "--rank", str(r), "--world", "2",
+                               "--backend", "gloo", "--mode", "ipc", "--w", "512", "--h", "1024"],
+                              env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "strips ok" in outs[0]

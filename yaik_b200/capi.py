@@ -26,7 +26,17 @@ EXPORTS = [
     "yk_gradient_pass", "yk_range1d", "yk_range_dyn", "yk_download_state", "yk_result_bytes", "yk_launch_count",
     "yk_profile", "yk_profile_read",
     "yk_strip_config", "yk_strip_halo_ptrs", "yk_strip_phase",
+    "yk_ipc_export", "yk_ipc_open", "yk_ipc_close", "yk_copy_async", "yk_copy_to_host", "yk_copy_from_host",
 ]
+
+
+class StripHalo(C.Structure):
+    """yk_strip_halo of include/yaik_b200.h."""
+    _fields_ = [("haloIn", C.c_void_p), ("haloBytes", C.c_size_t),
+                ("pixelRowInOffset", C.c_size_t), ("pixelRowBytes", C.c_size_t),
+                ("touchInTopOffset", C.c_size_t), ("touchInBottomOffset", C.c_size_t), ("touchBytes", C.c_size_t),
+                ("pixelRowOut", C.c_void_p * 3), ("planeRowBytes", C.c_size_t),
+                ("touchOutTop", C.c_void_p), ("touchOutBottom", C.c_void_p)]
 
 
 class YaikError(RuntimeError):
@@ -74,6 +84,15 @@ def load_library(path: str | None = None):
                                C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
     L.yk_download_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)]
     L.yk_result_bytes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
+    L.yk_strip_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.yk_strip_halo_ptrs.argtypes = [C.c_void_p, C.c_int, C.POINTER(StripHalo)]
+    L.yk_strip_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.yk_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+    L.yk_ipc_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.yk_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+    L.yk_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.yk_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.yk_copy_from_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     return L
 
 
@@ -191,6 +210,43 @@ class Context:
         arr = lambda lst: (C.c_void_p * 3)(*[a.ctypes.data for a in lst])
         self._ck(self.L.yk_download_state(self.ctx, slot, _p(smooth), arr(mst), arr(mrgb), _p(mask), arr(rec) if recon else None), "yk_download_state")
         return dict(smoothMap=smooth, mapSmoothTile=mst, mappedRGB=mrgb, mipmapMask=mask, recon=rec)
+
+    # ---- strips (one large image over several GPUs / contexts) ----
+    def strip_config(self, img_h, y0, slot=0):
+        self._ck(self.L.yk_strip_config(self.ctx, slot, img_h, y0), "yk_strip_config")
+
+    def strip_halo(self, slot=0) -> "StripHalo":
+        h = StripHalo()
+        self._ck(self.L.yk_strip_halo_ptrs(self.ctx, slot, C.byref(h)), "yk_strip_halo_ptrs")
+        return h
+
+    def strip_phase(self, phase, slot=0, reject=3):
+        self._ck(self.L.yk_strip_phase(self.ctx, slot, phase, reject), "yk_strip_phase")
+
+    def copy_async(self, dst, src, nbytes):
+        self._ck(self.L.yk_copy_async(self.ctx, C.c_void_p(dst), C.c_void_p(src), nbytes), "yk_copy_async")
+
+    def copy_to_host(self, dev_src, nbytes) -> np.ndarray:
+        out = np.empty(nbytes, np.uint8)
+        self._ck(self.L.yk_copy_to_host(self.ctx, _p(out), C.c_void_p(dev_src), nbytes), "yk_copy_to_host")
+        return out
+
+    def copy_from_host(self, dev_dst, data: np.ndarray):
+        data = np.ascontiguousarray(data).view(np.uint8).ravel()
+        self._ck(self.L.yk_copy_from_host(self.ctx, C.c_void_p(dev_dst), _p(data), data.size), "yk_copy_from_host")
+
+    def ipc_export(self, dev_ptr) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.yk_ipc_export(C.c_void_p(dev_ptr), buf), "yk_ipc_export")
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        out = C.c_void_p()
+        self._ck(self.L.yk_ipc_open(self.ctx, handle, C.byref(out)), "yk_ipc_open")
+        return out.value
+
+    def ipc_close(self, dev_ptr):
+        self._ck(self.L.yk_ipc_close(self.ctx, C.c_void_p(dev_ptr)), "yk_ipc_close")
 
     def result_bytes(self, slot=0):
         out = (C.c_longlong * 6)()

@@ -55,6 +55,8 @@ struct YkSlotHost {
     int bound[4] = { 0, 0, 0, 0 }, remaining = 0, wroteChunk = 0, chunkBBox[4] = { 0, 0, 0, 0 };
     std::vector<uint8_t> alphaBitmap;
     void* devAllocs[64]; int nAllocs = 0;
+    // strip mode: one allocation [3 * w int32 pixel row][latW touch words from above][latW touch words from below]
+    uint8_t* haloIn = nullptr; size_t haloBytes = 0;
 };
 
 struct yk_ctx {
@@ -247,7 +249,7 @@ extern "C" void yk_destroy(yk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto& s : c->slots) for (int i = 0; i < s.nAllocs; i++) cudaFree(s.devAllocs[i]);
+    for (auto& s : c->slots) { for (int i = 0; i < s.nAllocs; i++) cudaFree(s.devAllocs[i]); if (s.haloIn) cudaFree(s.haloIn); }
     cudaFree(c->slotsDev); cudaFree(c->zeroArea);
     if (c->lutDev) cudaFree(c->lutDev);
     if (c->ownStream) cudaStreamDestroy(c->stream);
@@ -299,7 +301,7 @@ static int configure_slot(yk_ctx* c, int slot, int nPlanes, int w, int h) {
     YkSlotHost& s = c->slots[slot];
     s.d.w = w; s.d.h = h; s.d.nPlanes = nPlanes;
     s.d.nbx = (w + 63) / 64; s.d.nby = (h + 63) / 64;
-    s.d.imgH = h; s.d.y0 = 0;
+    s.d.imgH = h; s.d.y0 = 0; s.d.hasAbove = 0; s.d.hasBelow = 0; s.d.touchInTop = nullptr; s.d.touchInBottom = nullptr;
     s.d.latW = w / 4 + 1; s.d.latH = h / 4 + 1;
     for (int p = 0; p < 3; p++) s.d.rowBelow[p] = nullptr;
     s.haveImage = true; s.dirty = true;
@@ -398,7 +400,7 @@ static int fetch_hdr(yk_ctx* c, YkSlotHost& s) {
 }
 
 // Enqueue analysis kernels for a run (list of gradient passes, optional alpha), then the emission + scan + R2 tail.
-static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEmit, bool doR2) {
+static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEmit, bool doR2, int phases = 3) {
     int rc = check_batch(c, slot0, nSlots);
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
@@ -407,14 +409,14 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     for (int i = slot0; i < slot0 + nSlots; i++)            // the header is about to be cleared: keep the previous run's numbers
         if (c->slots[i].pendingHarvest) { rc = fetch_hdr(c, c->slots[i]); if (rc && rc != YK_ERR_RANGE) return rc; }
     bool needFold = false;
-    for (int i = slot0; i < slot0 + nSlots; i++) {
+    for (int i = slot0; i < slot0 + nSlots && (phases & 1); i++) {
         YkSlotHost& s = c->slots[i];
         if (!s.zeroAClean) CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * i, 0, c->zeroABytes, c->stream));
         s.zeroAClean = false;
         if (s.touchDirty && run.nPasses > 0) needFold = true;
     }
     bool fresh = true;
-    for (int i = slot0; i < slot0 + nSlots; i++) {
+    for (int i = slot0; i < slot0 + nSlots && (phases & 1); i++) {
         YkSlotHost& s = c->slots[i];
         if (!s.cellsClean) {
             fresh = false;
@@ -432,11 +434,11 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     YkRun krun = run;
     krun.doR2 = r2Domain ? 1 : 0;
     krun.fresh = fresh ? 1 : 0;
-    if (krun.nPasses > 0 || krun.doAlpha || krun.doR2) {
+    if ((phases & 1) && (krun.nPasses > 0 || krun.doAlpha || krun.doR2)) {
         YkTimed t(c, 0);
         yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, c->numSMs, krun, c->stream); c->launches++;
     }
-    {
+    if (phases & 2) {
         // ownership of the touched lattice points, then one scan/compaction kernel: rgbStream emission of the run's
         // passes + gather of the range stage's per-tile output into stream order
         int gradGroups = 0;
@@ -524,6 +526,7 @@ extern "C" int yk_alpha_reject(yk_ctx* c, int slot, uint8_t* bitmap, int bitmapC
     YkSlotHost& s = c->slots[slot];
     if (!s.haveImage) return YK_ERR_STATE;
     if (s.d.nPlanes != 4) return YK_ERR_ARG;
+    if (s.d.hasAbove || s.d.hasBelow) return YK_ERR_UNSUPPORTED;    // the alpha bitmap of a strip set is not assembled here
     if (!s.alphaRan) {
         YkRun run; memset(&run, 0, sizeof run); run.doAlpha = 1; run.rejectFactor = 3;
         int rc = enqueue(c, slot, 1, run, false, false);
@@ -747,7 +750,124 @@ extern "C" int yk_result_bytes(yk_ctx* c, int slot, long long out[6]) {
     return YK_OK;
 }
 
-// ---- not built yet (declared so the boundary is complete; see DESIGN.md "status") --------------------------
-extern "C" int yk_strip_config(yk_ctx*, int, int, int) { return YK_ERR_UNSUPPORTED; }
-extern "C" int yk_strip_halo_ptrs(yk_ctx*, int, void**, size_t*, void**, void**, void**, size_t*) { return YK_ERR_UNSUPPORTED; }
-extern "C" int yk_strip_phase(yk_ctx*, int, int, int) { return YK_ERR_UNSUPPORTED; }
+// ---- multi-GPU: tile-row strips of one large image ----------------------------------------
+extern "C" int yk_strip_config(yk_ctx* c, int slot, int imgH, int y0) {
+    if (!slot_ok(c, slot)) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    const int w = s.d.w, h = s.d.h;
+    if (imgH < h || y0 < 0 || y0 + h > imgH || (y0 & 63)) return YK_ERR_ARG;
+    if (y0 + h < imgH && (h & 63)) return YK_ERR_ARG;            // only the last strip may end off the 64-row grid
+    CK(cudaSetDevice(c->device));
+    const size_t need = (size_t)3 * w * sizeof(int32_t) + 2 * (size_t)s.d.latW * sizeof(uint32_t);
+    if (s.haloBytes < need) {
+        if (s.haloIn) cudaFree(s.haloIn);
+        s.haloIn = nullptr; s.haloBytes = 0;
+        CK(cudaMalloc((void**)&s.haloIn, need));
+        s.haloBytes = need;
+    }
+    CK(cudaMemsetAsync(s.haloIn, 0, need, c->stream));
+    s.d.imgH = imgH; s.d.y0 = y0;
+    s.d.hasAbove = y0 > 0; s.d.hasBelow = y0 + h < imgH;
+    int32_t* row = (int32_t*)s.haloIn;
+    for (int p = 0; p < 3; p++) s.d.rowBelow[p] = s.d.hasBelow ? row + (size_t)p * w : nullptr;
+    s.d.touchInTop = (const uint32_t*)(s.haloIn + (size_t)3 * w * sizeof(int32_t));
+    s.d.touchInBottom = s.d.touchInTop + s.d.latW;
+    s.dirty = true;
+    return YK_OK;
+}
+
+extern "C" int yk_strip_halo_ptrs(yk_ctx* c, int slot, yk_strip_halo* out) {
+    if (!slot_ok(c, slot) || !out) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage || !s.haloIn) return YK_ERR_STATE;
+    const int w = s.d.w;
+    memset(out, 0, sizeof *out);
+    out->haloIn = s.haloIn; out->haloBytes = s.haloBytes;
+    out->pixelRowInOffset = 0; out->pixelRowBytes = (size_t)3 * w * sizeof(int32_t);
+    out->touchInTopOffset = out->pixelRowBytes;
+    out->touchBytes = (size_t)s.d.latW * sizeof(uint32_t);
+    out->touchInBottomOffset = out->touchInTopOffset + out->touchBytes;
+    for (int p = 0; p < 3; p++) out->pixelRowOut[p] = s.d.plane[p];                      // first pixel row of each colour plane
+    out->planeRowBytes = (size_t)w * sizeof(int32_t);
+    out->touchOutTop = s.d.touchMap;                                                         // lattice row 0
+    out->touchOutBottom = s.d.touchMap + (size_t)(s.d.latH - 1) * s.d.latW;                  // lattice row h/4
+    return YK_OK;
+}
+
+extern "C" int yk_strip_phase(yk_ctx* c, int slot, int phase, int rejectFactor) {
+    if (!slot_ok(c, slot) || (phase != 0 && phase != 1) || rejectFactor < 0 || rejectFactor > 64) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage || !s.haloIn) return YK_ERR_STATE;
+    YkRun run; memset(&run, 0, sizeof run);
+    run.rejectFactor = rejectFactor;
+    run.doAlpha = s.d.nPlanes == 4;
+    run.nPasses = YK_NPASS; for (int i = 0; i < YK_NPASS; i++) run.passId[i] = i;
+    if (phase == 0) {
+        if (s.prepared || s.nextPass || !s.cellsClean) return YK_ERR_STATE;         // needs a fresh state
+        return enqueue(c, slot, 1, run, true, true, 1);
+    }
+    if (s.cellsClean || s.prepared) return YK_ERR_STATE;                            // phase 0 first, once
+    const int rc = enqueue(c, slot, 1, run, true, true, 2);
+    if (rc) return rc;
+    s.prepared = true; s.preparedReject = rejectFactor; s.nextPass = 0;
+    return YK_OK;
+}
+
+// ---- peer-to-peer plumbing for the halo exchange: CUDA IPC handles of the halo buffers and plain async copies
+// (device to device, peer access over NVLink when the two GPUs allow it; no collective)
+extern "C" int yk_ipc_export(const void* devPtr, unsigned char handle[64]) {
+    if (!devPtr || !handle) return YK_ERR_ARG;
+#ifdef YK_EMULATE
+    memset(handle, 0, 64); memcpy(handle, &devPtr, sizeof devPtr);
+    return YK_OK;
+#else
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, (void*)devPtr));
+    memcpy(handle, &h, 64);
+    return YK_OK;
+#endif
+}
+extern "C" int yk_ipc_open(yk_ctx* c, const unsigned char handle[64], void** devPtr) {
+    if (!c || !handle || !devPtr) return YK_ERR_ARG;
+#ifdef YK_EMULATE
+    memcpy(devPtr, handle, sizeof *devPtr);
+    return YK_OK;
+#else
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(devPtr, h, cudaIpcMemLazyEnablePeerAccess));
+    return YK_OK;
+#endif
+}
+extern "C" int yk_ipc_close(yk_ctx* c, void* devPtr) {
+    if (!c || !devPtr) return YK_ERR_ARG;
+#ifndef YK_EMULATE
+    CK(cudaSetDevice(c->device));
+    CK(cudaIpcCloseMemHandle(devPtr));
+#endif
+    return YK_OK;
+}
+extern "C" int yk_copy_async(yk_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c || !dst || !src) return YK_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->stream));
+    return YK_OK;
+}
+// host <-> device copies of halo data for transports that stage through the host (and for tests)
+extern "C" int yk_copy_to_host(yk_ctx* c, void* hostDst, const void* devSrc, size_t bytes) {
+    if (!c || !hostDst || !devSrc) return YK_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(hostDst, devSrc, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return YK_OK;
+}
+extern "C" int yk_copy_from_host(yk_ctx* c, void* devDst, const void* hostSrc, size_t bytes) {
+    if (!c || !devDst || !hostSrc) return YK_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(devDst, hostSrc, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return YK_OK;
+}

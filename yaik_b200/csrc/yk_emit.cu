@@ -14,28 +14,40 @@
 //                the same scan + look-back.
 #include "yk_device.h"
 
+// Strips (one large image split into tile-row strips over several GPUs): the lattice row on a strip
+// boundary is touched by tiles of both strips.  Each strip ORs in the words its neighbour computed (touchInTop /
+// touchInBottom); a tile of the upper strip always precedes a tile of the lower strip in a pass's stream, and only the
+// strip that holds the owner tile marks it.
 __global__ void __launch_bounds__(256)
 yk_k_owner(const YkSlotDev* __restrict__ slots, int slot0, int nPoints, YkRun run) {
     const YkSlotDev& S = slots[slot0 + blockIdx.y];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nPoints) return;
-    const uint32_t word = __ldg(&S.touchMap[idx]);
-    if (word == 0u || (word & 0x80000000u)) return;                 // untouched / claimed by an earlier launch
+    uint32_t word = __ldg(&S.touchMap[idx]);
     const int gy = idx / S.latW, gx = idx - gy * S.latW;
+    if (S.hasAbove && gy == 0) word |= __ldg(&S.touchInTop[gx]);
+    if (S.hasBelow && gy == S.latH - 1) word |= __ldg(&S.touchInBottom[gx]);
+    if (word == 0u || (word & 0x80000000u)) return;                 // untouched / claimed by an earlier launch
     const int rp = (__ffs((int)(word & 0x0FFFFFFFu)) - 1) >> 2;     // first pass of this launch that touches the point
     const unsigned nib = (word >> (4 * rp)) & 15u;                  // roles present in that pass
     const int pid = run.passId[rp];
     const YkGeomS g = yk_geom_s(pid);
     const int nSwzX = (S.w + (1 << g.lbw) - 1) >> g.lbw;
     const int LX = (4 * gx) >> g.shx, LY = (4 * gy) >> g.shy;       // the point in tile units of that pass
+    const int tileRows = S.h >> g.shy;
     int best = INT_MAX, bestK = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if ((nib >> k) & 1u) {                                      // an accepted tile has the point as its corner k
-            const int pos = yk_pos_s(g, nSwzX, LX - (k & 1), LY - (k >> 1));
+            const int ty = LY - (k >> 1);
+            int pos;
+            if (ty < 0) pos = k - 5;                                // a tile of the strip above: before every tile of this strip (BR's tile before BL's)
+            else if (ty >= tileRows) pos = INT_MAX - 1;             // a tile of the strip below: after every tile of this strip
+            else pos = yk_pos_s(g, nSwzX, LX - (k & 1), ty);
             if (pos < best) { best = pos; bestK = k; }
         }
     }
+    if (best < 0 || best == INT_MAX - 1) return;                    // the neighbouring strip holds the owner
     atomicOr(&S.emitNib[pid][best >> 3], 1u << (4 * (best & 7) + bestK));
 }
 

@@ -48,6 +48,9 @@ struct alignas(128) YkSlotDev {
     int w, h, nPlanes;
     int nbx, nby;               // 64x64 regions
     int imgH, y0;               // strip mode: height of the whole image / first row of this strip (else h, 0)
+    int hasAbove, hasBelow;     // strip mode: there is a strip above / below this one
+    const uint32_t* touchInTop;     // strip mode: touch words of the boundary lattice row as the strip above / below saw them
+    const uint32_t* touchInBottom;  //   (latW words each, written by the neighbour over NVLink P2P between the two phases)
     int latW, latH;             // lattice of 4-pixel points: w/4+1, h/4+1
     // ---- compact state (replaces the reference's int32 state planes, EncoderContext.h:300-323)
     uint16_t* cellMask;         // [h/4][nbx]   bit i = 4x4 cell (16*bx+i) claimed   == smoothMap / mapSmoothTile != 0
