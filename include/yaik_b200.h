@@ -67,6 +67,10 @@ void  yk_host_free(void* p);
  * copies Plane::GetPixels() of nPlanes (3 = RGB, 4 = RGBA) planes host -> device into `slot` and resets
  * the slot's analysis state (the reference allocates its state planes lazily per image, EC.cpp:3739-3749). */
 int  yk_set_image(yk_ctx* ctx, int slot, const int32_t* const* planes, int nPlanes, int w, int h);
+/* How yk_set_image moves the samples: packedU8 != 0 (default) packs the int32 Plane samples to bytes on the host
+ * (threads; a sample outside 0..255 makes the call's analysis return YK_ERR_RANGE) and uploads a quarter of the bytes;
+ * 0 uploads the int32 planes as they are.  Results are identical. */
+int  yk_set_upload_format(yk_ctx* ctx, int packedU8);
 /* Same, planes already resident in device memory (borrowed, not copied; row pitch == w). */
 int  yk_set_image_device(yk_ctx* ctx, int slot, const int32_t* const* devPlanes, int nPlanes, int w, int h);
 /* Device pointer of plane `p` of `slot` (so a caller can fill it in place); NULL on error. */
@@ -138,6 +142,19 @@ int  yk_range_dyn(yk_ctx* ctx, int slot, int plane, int mode3BitOnly, uint8_t* n
 int  yk_download_state(yk_ctx* ctx, int slot, int32_t* smoothMap, int32_t* const* mapSmoothTile,
                        int32_t* const* mappedRGB, int32_t* mipmapMask, int32_t* const* recon);
 
+/* Every result of the last run on `slot` with two synchronisations and no per-stream call: the pointers lead into a
+ * pinned host arena owned by the context and stay valid until the next run / image on that slot.  Passes that were not
+ * part of the run have NULL pointers; the alpha block is filled when the alpha stage ran (alphaValid).  Same contents
+ * as the per-stage getters above. */
+typedef struct yk_results {
+    const uint8_t* bitmap[YK_NUM_PASSES]; int bitmapBytes[YK_NUM_PASSES];
+    const uint8_t* rgb[YK_NUM_PASSES];    int rgbBytes[YK_NUM_PASSES];
+    int tileDone[YK_NUM_PASSES]; int bbox[YK_NUM_PASSES][4];
+    const uint8_t* r2Idx[3]; const uint8_t* r2Type[3]; int r2IdxBytes, r2TypeBytes;      /* per plane */
+    int alphaValid; const uint8_t* alphaBitmap; int alphaBitmapBytes; int alphaBound[4]; int alphaRemaining, alphaWroteChunk; int alphaChunkBBox[4];
+} yk_results;
+int  yk_fetch_all(yk_ctx* ctx, int slot, yk_results* out);
+
 /* Bytes of result streams the last yk_analyze left in HBM for `slot` (for the roofline's algorithmic
  * byte count): [0] bitmaps, [1] rgb streams, [2] R2 idx, [3] R2 type, [4] alpha tile bitmap, [5] R1. */
 int  yk_result_bytes(yk_ctx* ctx, int slot, long long out[6]);
@@ -170,7 +187,8 @@ int  yk_profile_read(yk_ctx* ctx, double ms[8], long long count[8]);
 typedef struct yk_strip_halo {
     void*  haloIn;                 /* one device allocation of this strip, written by its neighbours */
     size_t haloBytes;
-    size_t pixelRowInOffset, pixelRowBytes;      /* 3 planes x w int32: first pixel row of the strip below */
+    size_t pixelRowInOffset, pixelRowBytes;      /* 3 planes x w samples (int32, or bytes after a packed upload): first pixel row of the strip below */
+    size_t pixelRowStride;                       /* plane p of that row starts at pixelRowInOffset + p * pixelRowStride */
     size_t touchInTopOffset, touchInBottomOffset, touchBytes;   /* latW u32 each: boundary touch words of the strip above / below */
     const void* pixelRowOut[3];    /* this strip's first pixel row, per colour plane (planeRowBytes each) */
     size_t planeRowBytes;

@@ -170,6 +170,9 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new yk_emu_event{0}; return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+#define cudaEventDisableTiming 2
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new yk_emu_event{0}; return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 #define cudaStreamNonBlocking 1
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 8

@@ -140,6 +140,26 @@ def test_out_of_range_sample_is_reported(ctx):
     assert e.value.code == -4
 
 
+def test_alternative_data_paths(lib):
+    """Upload formats (packed bytes / int32), device-resident int32 planes (what bench.py's `value` runs on), yk_fetch_all."""
+    import paths_check
+    c = capi.Context(256, 256, planes=4, slots=1, lib=lib)
+    try:
+        paths_check.check_upload_formats(c)
+        paths_check.check_out_of_range(c)
+        paths_check.check_fetch_all(c)
+
+        def to_device(planes):
+            ptrs = []
+            for i in range(planes.shape[0]):
+                ptrs.append(c.device_plane(0, i))
+                c.copy_from_host(ptrs[-1], np.ascontiguousarray(planes[i], dtype=np.int32))
+            return ptrs
+        paths_check.check_device_resident_planes(c, to_device)
+    finally:
+        c.close()
+
+
 # ---- tile-row strips of one large image (BASELINE.json configs[3], SURVEY.md 8e) --------------------------------
 @pytest.mark.parametrize("w,h,n", [(256, 512, 2), (256, 512, 4), (192, 328, 3), (2048, 1024, 4)])
 def test_strips_on_one_gpu_match_whole_image(lib, w, h, n):

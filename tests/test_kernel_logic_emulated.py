@@ -42,3 +42,22 @@ def test_emulated_stage_by_stage_calls(emu_lib):
         check_image(ctx, planes, ("grad", "r2"), fused=False)
     finally:
         ctx.close()
+
+
+def test_emulated_alternative_data_paths(emu_lib):
+    """Upload formats (packed bytes / int32), device-resident planes, yk_fetch_all, the range check of both uploads."""
+    import numpy as np
+    import paths_check
+    ctx = capi.Context(256, 256, planes=4, slots=1, lib=emu_lib)
+    keep = []
+    try:
+        paths_check.check_upload_formats(ctx)
+        paths_check.check_out_of_range(ctx)
+        paths_check.check_fetch_all(ctx)
+
+        def to_device(planes):       # the emulated "device" is host memory
+            keep.append(np.ascontiguousarray(planes, dtype=np.int32))
+            return [keep[-1][i].ctypes.data for i in range(planes.shape[0])]
+        paths_check.check_device_resident_planes(ctx, to_device)
+    finally:
+        ctx.close()

@@ -21,19 +21,28 @@ STAGE_ALPHA, STAGE_GRADIENT, STAGE_RANGE1D, STAGE_RANGEDYN, STAGE_RANGEDYN3 = 1,
 
 EXPORTS = [
     "yk_abi_version", "yk_error_string", "yk_last_cuda_error", "yk_device_count", "yk_create", "yk_destroy",
-    "yk_set_stream", "yk_sync", "yk_host_alloc", "yk_host_free", "yk_set_image", "yk_set_image_device",
+    "yk_set_stream", "yk_sync", "yk_host_alloc", "yk_host_free", "yk_set_image", "yk_set_image_device", "yk_set_upload_format",
     "yk_device_plane", "yk_reset_state", "yk_analyze", "yk_alpha_reject", "yk_prepare_quad_smooth",
-    "yk_gradient_pass", "yk_range1d", "yk_range_dyn", "yk_download_state", "yk_result_bytes", "yk_launch_count",
+    "yk_gradient_pass", "yk_range1d", "yk_range_dyn", "yk_download_state", "yk_fetch_all", "yk_result_bytes", "yk_launch_count",
     "yk_profile", "yk_profile_read",
     "yk_strip_config", "yk_strip_halo_ptrs", "yk_strip_phase",
     "yk_ipc_export", "yk_ipc_open", "yk_ipc_close", "yk_copy_async", "yk_copy_to_host", "yk_copy_from_host",
 ]
 
 
+class Results(C.Structure):
+    """yk_results of include/yaik_b200.h (pointers into the context's pinned arena)."""
+    _fields_ = [("bitmap", C.c_void_p * 7), ("bitmapBytes", C.c_int * 7), ("rgb", C.c_void_p * 7), ("rgbBytes", C.c_int * 7),
+                ("tileDone", C.c_int * 7), ("bbox", (C.c_int * 4) * 7),
+                ("r2Idx", C.c_void_p * 3), ("r2Type", C.c_void_p * 3), ("r2IdxBytes", C.c_int), ("r2TypeBytes", C.c_int),
+                ("alphaValid", C.c_int), ("alphaBitmap", C.c_void_p), ("alphaBitmapBytes", C.c_int), ("alphaBound", C.c_int * 4),
+                ("alphaRemaining", C.c_int), ("alphaWroteChunk", C.c_int), ("alphaChunkBBox", C.c_int * 4)]
+
+
 class StripHalo(C.Structure):
     """yk_strip_halo of include/yaik_b200.h."""
     _fields_ = [("haloIn", C.c_void_p), ("haloBytes", C.c_size_t),
-                ("pixelRowInOffset", C.c_size_t), ("pixelRowBytes", C.c_size_t),
+                ("pixelRowInOffset", C.c_size_t), ("pixelRowBytes", C.c_size_t), ("pixelRowStride", C.c_size_t),
                 ("touchInTopOffset", C.c_size_t), ("touchInBottomOffset", C.c_size_t), ("touchBytes", C.c_size_t),
                 ("pixelRowOut", C.c_void_p * 3), ("planeRowBytes", C.c_size_t),
                 ("touchOutTop", C.c_void_p), ("touchOutBottom", C.c_void_p)]
@@ -73,6 +82,7 @@ def load_library(path: str | None = None):
     L.yk_set_image.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
     L.yk_set_image_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
     L.yk_reset_state.argtypes = [C.c_void_p, C.c_int]
+    L.yk_set_upload_format.argtypes = [C.c_void_p, C.c_int]
     L.yk_analyze.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.yk_prepare_quad_smooth.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.yk_alpha_reject.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -84,6 +94,7 @@ def load_library(path: str | None = None):
                                C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
     L.yk_download_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)]
     L.yk_result_bytes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
+    L.yk_fetch_all.argtypes = [C.c_void_p, C.c_int, C.POINTER(Results)]
     L.yk_strip_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.yk_strip_halo_ptrs.argtypes = [C.c_void_p, C.c_int, C.POINTER(StripHalo)]
     L.yk_strip_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -138,6 +149,9 @@ class Context:
         self.dims[slot] = (c, h, w)
         self._ck(self.L.yk_set_image(self.ctx, slot, ptrs, c, w, h), "yk_set_image")
         self.sync()      # the source array may be pageable numpy memory
+
+    def set_upload_format(self, packed_u8: bool):
+        self._ck(self.L.yk_set_upload_format(self.ctx, int(packed_u8)), "yk_set_upload_format")
 
     def set_image_ptrs(self, host_ptrs, c, w, h, slot=0):
         """Pinned host plane pointers (yk_host_alloc); asynchronous."""
@@ -247,6 +261,28 @@ class Context:
 
     def ipc_close(self, dev_ptr):
         self._ck(self.L.yk_ipc_close(self.ctx, C.c_void_p(dev_ptr)), "yk_ipc_close")
+
+    def fetch_all(self, slot=0, copy=True):
+        """Everything of the last run with one call (yk_fetch_all).  copy=False returns the raw Results struct whose pointers
+        lead into the context's pinned arena."""
+        r = Results()
+        self._ck(self.L.yk_fetch_all(self.ctx, slot, C.byref(r)), "yk_fetch_all")
+        if not copy:
+            return r
+
+        def arr(ptr, n):
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,)).copy() if ptr and n else np.zeros(0, np.uint8)
+        out = {"passes": [], "r2": [], "alpha": None}
+        for p in range(7):
+            out["passes"].append(None if not r.bitmap[p] else dict(bitmap=arr(r.bitmap[p], r.bitmapBytes[p]), rgb=arr(r.rgb[p], r.rgbBytes[p]),
+                                                                  tiledone=r.tileDone[p], bbox=list(r.bbox[p])))
+        for pl in range(3):
+            if r.r2Idx[pl]:
+                out["r2"].append(dict(idx=arr(r.r2Idx[pl], r.r2IdxBytes), type=arr(r.r2Type[pl], r.r2TypeBytes)))
+        if r.alphaValid:
+            out["alpha"] = dict(bitmap=arr(r.alphaBitmap, r.alphaBitmapBytes), bound=list(r.alphaBound), remaining=r.alphaRemaining,
+                                wrote=r.alphaWroteChunk, chunk_bbox=list(r.alphaChunkBBox) if r.alphaWroteChunk else [])
+        return out
 
     def result_bytes(self, slot=0):
         out = (C.c_longlong * 6)()

@@ -36,6 +36,10 @@
 #define YKA_RAW_STAGE_INTS (3 * YKA_RAW_PLANE_INTS + 16 * 64)
 #define YKA_COLOR_TX (3u * YK_RAW_ROWS * YK_RAW_PITCH * 4u)
 #define YKA_ALPHA_TX (16u * 64u * 4u)
+#define YKA_RAWB_PLANE 1408         // packed upload: 17 rows x 80 bytes = 1360, rounded to a multiple of 128
+#define YKA_RAWB_STAGE (3 * YKA_RAWB_PLANE + 16 * 64)
+#define YKA_COLORB_TX (3u * YK_RAW_ROWS * YK_U8_BOX)
+#define YKA_ALPHAB_TX (16u * 64u)
 #define YKP_RS 24                   // row pitch in bytes of a warp-private 17x17 byte tile
 #define YKP_CH (17 * YKP_RS)        // bytes of one channel of it
 #define YKP_TILE 1232               // 3 channels, rounded to a multiple of 16
@@ -51,7 +55,7 @@ struct YkaUnit {                    // what the producer says about the unit sta
 // the fields of a slot descriptor a consumer warp needs (its own copy, refreshed when its items move to another image)
 struct YkaSlotC {
     int slot, w, h, nbx, yOrg, latW, latH, pad;
-    const int32_t* rowBelow[3];
+    const void* rowBelow[3];
     uint32_t* cellMask32;           // claimed cells, two 16-bit rows per word
     uint32_t* touchMap;
     uint8_t*  alphaKept;
@@ -105,10 +109,15 @@ static inline void yka_mbar_arrive(unsigned long long* b) {
     }
 }
 static inline void yka_tma_box(void* dst, const YkTmap* tm, int x, int y, int bw, int bh, unsigned long long* b, int last) {
-    const int32_t* base = (const int32_t*)tm->opaque[0]; const int w = (int)tm->opaque[1], h = (int)tm->opaque[2];
-    int32_t* d = (int32_t*)dst;
-    for (int r = 0; r < bh; r++) for (int c = 0; c < bw; c++)
-        d[r * bw + c] = (y + r < h && x + c < w) ? base[(size_t)(y + r) * w + x + c] : 0;
+    // emulated descriptor: base, width, height, element size, row pitch in elements
+    const unsigned char* base = (const unsigned char*)tm->opaque[0];
+    const int w = (int)tm->opaque[1], h = (int)tm->opaque[2], es = (int)tm->opaque[3];
+    const size_t pitch = (size_t)tm->opaque[4];
+    unsigned char* d = (unsigned char*)dst;
+    for (int r = 0; r < bh; r++) for (int c = 0; c < bw; c++) {
+        if (y + r < h && x + c < w) memcpy(d + ((size_t)r * bw + c) * es, base + ((size_t)(y + r) * pitch + x + c) * es, es);
+        else memset(d + ((size_t)r * bw + c) * es, 0, es);
+    }
     if (last) yka_mbar_arrive(b);                                               // all boxes of the stage have landed: the phase completes
 }
 static inline void yka_fence_async() {}
@@ -190,30 +199,38 @@ static __device__ void yka_slot_refresh(const YkSlotDev& S, YkaSlotC& C, int slo
     __syncwarp();
 }
 
-// Consumer warp: the 17x17 samples of macro tile (mx, row k) of the region, three colour planes, from the raw int32
-// rows staged by TMA into the warp-private byte tile, clamped the way Plane::GetPixelValue clamps (framework.h:116-121);
-// then the alpha-zero test of the 16x16 tile (EC.cpp:357-430 restated per tile).  Returns (uniformly) whether the tile
-// has a non-zero alpha sample.
-static __device__ __forceinline__ bool yka_pack_macro_tile(const int32_t* __restrict__ raw, uint8_t* __restrict__ priv, const YkaSlotC& C,
+// Consumer warp: the 17x17 samples of macro tile (mx, row k) of the region, three colour planes, from the raw rows
+// staged by TMA (int32 samples, or bytes when the image was uploaded packed) into the warp-private byte tile, clamped
+// the way Plane::GetPixelValue clamps (framework.h:116-121); then the alpha-zero test of the 16x16 tile (EC.cpp:357-430
+// restated per tile).  Returns (uniformly) whether the tile has a non-zero alpha sample.
+template <bool U8>
+static __device__ __forceinline__ bool yka_pack_macro_tile(const void* __restrict__ rawv, uint8_t* __restrict__ priv, const YkaSlotC& C,
                                                            int X0, int Yk, int mx, bool doAlpha) {
     const int lane = threadIdx.x & 31;
     const int w = C.w, h = C.h;
     const int Xm = X0 + 16 * mx;
     unsigned bad = 0;
+    const int32_t* __restrict__ raw = reinterpret_cast<const int32_t*>(rawv);
+    const uint8_t* __restrict__ rawb = reinterpret_cast<const uint8_t*>(rawv);
     if (Xm + 20 <= w && Yk + YK_RAW_ROWS <= h) {
-        // interior: 17 rows x 5 int4 (columns 0..19 of the macro tile, 17 needed) per plane, all inside the image
+        // interior: 17 rows x 20 samples (columns 0..19 of the macro tile, 17 needed) per plane, all inside the image
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const int4* __restrict__ src = reinterpret_cast<const int4*>(raw + c * YKA_RAW_PLANE_INTS) + 4 * mx;
             uint8_t* __restrict__ d = priv + c * YKP_CH;
 #pragma unroll
             for (int it = 0; it < 3; it++) {
-                const int idx = it * 32 + lane;                 // 85 = 17 rows x 5
+                const int idx = it * 32 + lane;                 // 85 = 17 rows x 5 groups of four samples
                 if (idx < 85) {
                     const int lr = idx / 5, q = idx - lr * 5;
-                    const int4 v = src[lr * (YK_RAW_PITCH / 4) + q];
-                    bad |= (unsigned)(v.x | v.y | v.z | v.w);
-                    *reinterpret_cast<unsigned*>(d + lr * YKP_RS + 4 * q) = yka_pack4(v);
+                    unsigned packed;
+                    if (U8) {
+                        packed = *reinterpret_cast<const unsigned*>(rawb + c * YKA_RAWB_PLANE + lr * YK_U8_BOX + 16 * mx + 4 * q);
+                    } else {
+                        const int4 v = (reinterpret_cast<const int4*>(raw + c * YKA_RAW_PLANE_INTS) + 4 * mx)[lr * (YK_RAW_PITCH / 4) + q];
+                        bad |= (unsigned)(v.x | v.y | v.z | v.w);
+                        packed = yka_pack4(v);
+                    }
+                    *reinterpret_cast<unsigned*>(d + lr * YKP_RS + 4 * q) = packed;
                 }
             }
         }
@@ -226,8 +243,13 @@ static __device__ __forceinline__ bool yka_pack_macro_tile(const int32_t* __rest
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 int s;
-                if (lr > hmax && C.rowBelow[c]) s = __ldg(C.rowBelow[c] + min(Xm + lx, w - 1));
-                else s = raw[c * YKA_RAW_PLANE_INTS + min(lr, hmax) * YK_RAW_PITCH + min(16 * mx + lx, wmax)];
+                if (lr > hmax && C.rowBelow[c]) {
+                    const int x = min(Xm + lx, w - 1);
+                    s = U8 ? (int)__ldg(reinterpret_cast<const uint8_t*>(C.rowBelow[c]) + x) : __ldg(reinterpret_cast<const int32_t*>(C.rowBelow[c]) + x);
+                } else {
+                    const int rr = min(lr, hmax), cc = min(16 * mx + lx, wmax);
+                    s = U8 ? (int)rawb[c * YKA_RAWB_PLANE + rr * YK_U8_BOX + cc] : raw[c * YKA_RAW_PLANE_INTS + rr * YK_RAW_PITCH + cc];
+                }
                 bad |= (unsigned)s;
                 priv[c * YKP_CH + lr * YKP_RS + lx] = (uint8_t)s;
             }
@@ -237,9 +259,16 @@ static __device__ __forceinline__ bool yka_pack_macro_tile(const int32_t* __rest
     bool kept = false;
     if (doAlpha) {
         // samples outside the image arrive as zeros
-        const int4* __restrict__ a = reinterpret_cast<const int4*>(raw + 3 * YKA_RAW_PLANE_INTS) + 4 * mx;
-        const int4 v0 = a[(lane >> 2) * 16 + (lane & 3)], v1 = a[((lane >> 2) + 8) * 16 + (lane & 3)];
-        kept = __any_sync(YK_FULL, (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0);
+        bool nz;
+        if (U8) {
+            const uint2 v = *reinterpret_cast<const uint2*>(rawb + 3 * YKA_RAWB_PLANE + (lane >> 1) * 64 + 16 * mx + 8 * (lane & 1));
+            nz = (v.x | v.y) != 0u;
+        } else {
+            const int4* __restrict__ a = reinterpret_cast<const int4*>(raw + 3 * YKA_RAW_PLANE_INTS) + 4 * mx;
+            const int4 v0 = a[(lane >> 2) * 16 + (lane & 3)], v1 = a[((lane >> 2) + 8) * 16 + (lane & 3)];
+            nz = (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0;
+        }
+        kept = __any_sync(YK_FULL, nz);
     }
     return kept;
 }
@@ -587,8 +616,8 @@ extern "C" void yk_debug_timing(unsigned long long* out, int reset) {
 #define YKT(i)
 #endif
 
-__global__ void __launch_bounds__(YKA_THREADS, 1)
-yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRegions, YkRun runArg) {
+template <bool U8>
+static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRegions, const YkRun& runArg) {
     // one dynamic shared-memory block, carved by constant offsets from the array itself so that every access stays in
     // the shared address space (LDS / STS / ATOMS, no generic loads)
 #ifdef YK_EMULATE
@@ -596,7 +625,9 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRe
 #else
     extern __shared__ __align__(128) unsigned char smem[];
 #endif
-    int32_t* raw = reinterpret_cast<int32_t*>(smem);
+    unsigned char* raw = smem;
+    constexpr int STAGE_BYTES = U8 ? YKA_RAWB_STAGE : YKA_RAW_STAGE_INTS * 4;
+    constexpr int PLANE_BYTES = U8 ? YKA_RAWB_PLANE : YKA_RAW_PLANE_INTS * 4;
     uint8_t* privAll = smem + YKA_SMEM_RAW;
     uint8_t* histAll = smem + YKA_SMEM_RAW + YKA_SMEM_PIX;
     uint32_t* sMagic = reinterpret_cast<uint32_t*>(smem + YKA_SMEM_RAW + YKA_SMEM_PIX + YKA_SMEM_HIST);    // ceil(2^20 / d): exact floor(n / d) for n < 4112, d <= 255
@@ -670,12 +701,12 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRe
                     YKT(3);
                     YkaUnit& U = sh.unit[i];
                     U.slot = slot; U.bx = bx; U.by = by; U.k = k; U.alpha = alpha;
-                    int32_t* dst = raw + i * YKA_RAW_STAGE_INTS;
+                    unsigned char* dst = raw + i * STAGE_BYTES;
                     yka_fence_async();
-                    yka_mbar_expect_tx(&sh.rawFull[i], YKA_COLOR_TX + (alpha ? YKA_ALPHA_TX : 0u));
+                    yka_mbar_expect_tx(&sh.rawFull[i], (U8 ? YKA_COLORB_TX : YKA_COLOR_TX) + (alpha ? (U8 ? YKA_ALPHAB_TX : YKA_ALPHA_TX) : 0u));
                     for (int c = 0; c < 3; c++)
-                        yka_tma_box(dst + c * YKA_RAW_PLANE_INTS, &S->tmap[c], bx * 64, by * 64 + 16 * k, YK_RAW_PITCH, YK_RAW_ROWS, &sh.rawFull[i], !alpha && c == 2);
-                    if (alpha) yka_tma_box(dst + 3 * YKA_RAW_PLANE_INTS, &S->tmap[3], bx * 64, by * 64 + 16 * k, 64, 16, &sh.rawFull[i], 1);
+                        yka_tma_box(dst + c * PLANE_BYTES, &S->tmap[c], bx * 64, by * 64 + 16 * k, U8 ? YK_U8_BOX : YK_RAW_PITCH, YK_RAW_ROWS, &sh.rawFull[i], !alpha && c == 2);
+                    if (alpha) yka_tma_box(dst + 3 * PLANE_BYTES, &S->tmap[3], bx * 64, by * 64 + 16 * k, 64, 16, &sh.rawFull[i], 1);
                     YKT(2);
                 }
             }
@@ -709,7 +740,7 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRe
         __syncwarp();                                       // every lane has read the cached id before lane 0 may rewrite it
         if (cachedSlot != U.slot) yka_slot_refresh(slots[U.slot], C, U.slot);
         const int X0 = U.bx * 64, Yk = U.by * 64 + 16 * U.k;
-        const bool kept = yka_pack_macro_tile(raw + i * YKA_RAW_STAGE_INTS, priv, C, X0, Yk, mx, U.alpha != 0);
+        const bool kept = yka_pack_macro_tile<U8>(raw + i * STAGE_BYTES, priv, C, X0, Yk, mx, U.alpha != 0);
         __syncwarp();
         if (lane == 0) yka_mbar_arrive(&sh.rawFree[i]);      // this warp is done with the raw rows
         if (tid == 32) YKT(9);
@@ -743,6 +774,26 @@ yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRe
     }
 }
 
+__global__ void __launch_bounds__(YKA_THREADS, 1)
+yk_k_analyze(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRegions, YkRun run) {
+    yk_analyze_body<false>(slots, slot0, nSlots, nRegions, run);
+}
+// the same over planes uploaded packed to bytes by yk_set_image (a quarter of the HBM and PCIe traffic)
+__global__ void __launch_bounds__(YKA_THREADS, 1)
+yk_k_analyze_u8(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRegions, YkRun run) {
+    yk_analyze_body<true>(slots, slot0, nSlots, nRegions, run);
+}
+
+// packed planes -> int32 planes, for the kernels outside the hot path that read Plane-style samples
+__global__ void __launch_bounds__(256)
+yk_k_expand(const YkSlotDev* __restrict__ slots, int slot, int w, int h, int32_t* d0, int32_t* d1, int32_t* d2, int32_t* d3) {
+    const YkSlotDev& S = slots[slot];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    int32_t* d[4] = { d0, d1, d2, d3 };
+    for (int p = 0; p < S.nPlanes; p++) if (d[p]) d[p][(size_t)y * w + x] = S.planeU8[p][(size_t)y * S.pitchU8 + x];
+}
+
 // A new launch on a state that already holds claims: every touched lattice point becomes "claimed before" (bit 31).
 __global__ void __launch_bounds__(256)
 yk_k_fold_touch(const YkSlotDev* __restrict__ slots, int slot0, int nWords) {
@@ -764,13 +815,19 @@ int yk_analyze_setup(int* numSMs) {
     e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return (int)e;
     if (numSMs) *numSMs = n;
-    return (int)cudaFuncSetAttribute(yk_k_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, YKA_SMEM_BYTES);
+    e = cudaFuncSetAttribute(yk_k_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, YKA_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaFuncSetAttribute(yk_k_analyze_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, YKA_SMEM_BYTES);
 #endif
 }
-void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, int gridCtas, const YkRun& run, cudaStream_t st) {
+void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, int gridCtas, bool packedU8, const YkRun& run, cudaStream_t st) {
     const int total = nSlots * nRegions * 4;                 // units: macro-tile rows of regions
     const int grid = gridCtas < total ? gridCtas : total;
-    YK_LAUNCH(yk_k_analyze, dim3(grid), dim3(YKA_THREADS), YKA_SMEM_BYTES, st, slotsDev, slot0, nSlots, nRegions, run);
+    if (packedU8) YK_LAUNCH(yk_k_analyze_u8, dim3(grid), dim3(YKA_THREADS), YKA_SMEM_BYTES, st, slotsDev, slot0, nSlots, nRegions, run);
+    else YK_LAUNCH(yk_k_analyze, dim3(grid), dim3(YKA_THREADS), YKA_SMEM_BYTES, st, slotsDev, slot0, nSlots, nRegions, run);
+}
+void yk_launch_expand(const YkSlotDev* slotsDev, int slot, int nPlanes, int w, int h, int32_t* const* dst, cudaStream_t st) {
+    YK_LAUNCH(yk_k_expand, dim3((w + 255) / 256, h), dim3(256), 0, st, slotsDev, slot, w, h, dst[0], dst[1], dst[2], nPlanes > 3 ? dst[3] : (int32_t*)nullptr);
 }
 void yk_launch_fold_touch(const YkSlotDev* slotsDev, int slot0, int nSlots, int nWords, cudaStream_t st) {
     YK_LAUNCH(yk_k_fold_touch, dim3((nWords + 255) / 256, nSlots), dim3(256), 0, st, slotsDev, slot0, nWords);

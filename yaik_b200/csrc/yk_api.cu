@@ -15,6 +15,13 @@
 #include <cuda.h>               // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
 #endif
 
+// yk_hostpack.cpp
+struct YkHostPacker;
+YkHostPacker* yk_hostpack_create(int threads);
+void yk_hostpack_destroy(YkHostPacker* p);
+int yk_hostpack_threads(const YkHostPacker* p);
+unsigned yk_hostpack_plane(YkHostPacker* p, const int32_t* src, uint8_t* dst, int w, int h, size_t pitch);
+
 static thread_local std::string g_lastCuda;
 
 #define CK(call)                                                                            \
@@ -37,6 +44,14 @@ struct YkSlotHost {
     YkSlotDev d;
     bool haveImage = false, borrowed = false, dirty = true;
     int32_t* owned[4] = { 0, 0, 0, 0 };
+    uint8_t* ownedU8[4] = { 0, 0, 0, 0 };     // packed upload: device planes, pinned staging, "staging is free again" event
+    uint8_t* stageHost = nullptr; size_t stageBytes = 0;
+    cudaEvent_t stageFree = nullptr; bool stageBusy = false;
+    bool int32Valid = true;      // owned[] holds the int32 samples (false after a packed upload until yk_k_expand ran)
+    uint8_t* arena = nullptr; size_t arenaBytes = 0;     // pinned host copy of every result stream of the last run
+    bool harvested = false;
+    size_t arBitmap[YK_NPASS], arRgb[YK_NPASS], arIdx[3], arType[3], arKept = 0;
+    int arMask = 0; bool arR2 = false, arHasKept = false;
     // what is valid on the device for the current image
     bool k1Ran = false;          // r2Seg / latRGB are current
     bool alphaRan = false, alphaFetched = false;
@@ -69,6 +84,8 @@ struct yk_ctx {
     uint8_t* zeroArea = nullptr; size_t zeroStride = 0, zeroABytes = 0;
     int* lutDev = nullptr;       // R1 tables
     int numSMs = 1;              // grid of the persistent analysis kernel
+    YkHostPacker* packer = nullptr;
+    bool packedUpload = true;    // yk_set_image packs Plane samples to bytes on the host before the copy
     long long launches = 0;
     size_t planeCap = 0;
     // optional per-kernel timing with CUDA events on the launching stream (yk_profile)
@@ -128,10 +145,11 @@ template <class T> static int dev_alloc(YkSlotHost& s, T** out, size_t count) {
 }
 
 // TMA descriptor of one int32 plane [h][w] with a boxW x boxH box (yk_k_analyze stages regions with it).
-static int encode_plane_tmap(YkTmap* tm, const int32_t* plane, int w, int h, int boxW, int boxH) {
+static int encode_plane_tmap(YkTmap* tm, const void* plane, int elemBytes, size_t pitchElems, int w, int h, int boxW, int boxH) {
 #ifdef YK_EMULATE
     memset(tm, 0, sizeof *tm);
     tm->opaque[0] = (unsigned long long)(uintptr_t)plane; tm->opaque[1] = (unsigned long long)w; tm->opaque[2] = (unsigned long long)h;
+    tm->opaque[3] = (unsigned long long)elemBytes; tm->opaque[4] = (unsigned long long)pitchElems;
     (void)boxW; (void)boxH;
     return YK_OK;
 #else
@@ -147,10 +165,10 @@ static int encode_plane_tmap(YkTmap* tm, const int32_t* plane, int w, int h, int
     }
     static_assert(sizeof(YkTmap) == sizeof(CUtensorMap), "YkTmap must be a CUtensorMap");
     const cuuint64_t dims[2] = { (cuuint64_t)w, (cuuint64_t)h };
-    const cuuint64_t strides[1] = { (cuuint64_t)w * sizeof(int32_t) };
+    const cuuint64_t strides[1] = { (cuuint64_t)pitchElems * (cuuint64_t)elemBytes };
     const cuuint32_t box[2] = { (cuuint32_t)boxW, (cuuint32_t)boxH };
     const cuuint32_t estr[2] = { 1, 1 };
-    const CUresult r = encode(reinterpret_cast<CUtensorMap*>(tm), CU_TENSOR_MAP_DATA_TYPE_INT32, 2, (void*)plane, dims, strides, box, estr,
+    const CUresult r = encode(reinterpret_cast<CUtensorMap*>(tm), elemBytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_INT32, 2, (void*)plane, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_lastCuda = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r); return YK_ERR_CUDA; }
     return YK_OK;
@@ -159,7 +177,9 @@ static int encode_plane_tmap(YkTmap* tm, const int32_t* plane, int w, int h, int
 
 static int encode_slot_tmaps(YkSlotHost& s) {
     for (int p = 0; p < s.d.nPlanes; p++) {
-        const int rc = encode_plane_tmap(&s.d.tmap[p], s.d.plane[p], s.d.w, s.d.h, p < 3 ? YK_RAW_PITCH : 64, p < 3 ? YK_RAW_ROWS : 16);
+        const int rc = s.d.isU8
+            ? encode_plane_tmap(&s.d.tmap[p], s.d.planeU8[p], 1, (size_t)s.d.pitchU8, s.d.w, s.d.h, p < 3 ? YK_U8_BOX : 64, p < 3 ? YK_RAW_ROWS : 16)
+            : encode_plane_tmap(&s.d.tmap[p], s.d.plane[p], 4, (size_t)s.d.w, s.d.w, s.d.h, p < 3 ? YK_RAW_PITCH : 64, p < 3 ? YK_RAW_ROWS : 16);
         if (rc) return rc;
     }
     return YK_OK;
@@ -214,6 +234,7 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
         int rc;
         uint8_t* za = c->zeroArea + c->zeroStride * i;
         for (int p = 0; p < maxPlanes; p++) if ((rc = dev_alloc(s, &s.owned[p], W * H))) return rc;
+        for (int p = 0; p < maxPlanes; p++) if ((rc = dev_alloc(s, &s.ownedU8[p], ((W + 15) / 16 * 16) * H + 256))) return rc;
         s.d.hdr = (int*)za;
         for (int p = 0; p < YK_NPASS; p++) s.d.emitStatus[p] = (uint32_t*)(za + offStatus[p]);
         for (int p = 0; p < YK_NPASS; p++) s.d.emitNib[p] = (uint32_t*)(za + offNib[p]);
@@ -241,6 +262,7 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
             if ((rc = dev_alloc(s, &s.d.r1Defs[p], (W / 8) * (H / 8) + 4))) return rc;
         }
     }
+    { const char* e = getenv("YK_PACK_THREADS"); c->packer = yk_hostpack_create(e ? atoi(e) : 0); }
     *out = c;
     return YK_OK;
 }
@@ -249,7 +271,14 @@ extern "C" void yk_destroy(yk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto& s : c->slots) { for (int i = 0; i < s.nAllocs; i++) cudaFree(s.devAllocs[i]); if (s.haloIn) cudaFree(s.haloIn); }
+    for (auto& s : c->slots) {
+        for (int i = 0; i < s.nAllocs; i++) cudaFree(s.devAllocs[i]);
+        if (s.haloIn) cudaFree(s.haloIn);
+        if (s.stageHost) cudaFreeHost(s.stageHost);
+        if (s.arena) cudaFreeHost(s.arena);
+        if (s.stageFree) cudaEventDestroy(s.stageFree);
+    }
+    if (c->packer) yk_hostpack_destroy(c->packer);
     cudaFree(c->slotsDev); cudaFree(c->zeroArea);
     if (c->lutDev) cudaFree(c->lutDev);
     if (c->ownStream) cudaStreamDestroy(c->stream);
@@ -294,6 +323,7 @@ extern "C" int yk_profile_read(yk_ctx* c, double ms[8], long long count[8]) {
 }
 
 static int slot_ok(yk_ctx* c, int slot) { return c && slot >= 0 && slot < c->maxSlots; }
+static int upload_slots_fwd(yk_ctx* c, int slot0, int nSlots);
 
 static int configure_slot(yk_ctx* c, int slot, int nPlanes, int w, int h) {
     if (nPlanes < 3 || nPlanes > 4 || w < 4 || h < 4 || (w & 3) || (h & 3)) return YK_ERR_ARG;
@@ -314,12 +344,18 @@ extern "C" int yk_reset_state(yk_ctx* c, int slot) {
     if (!s.haveImage) return YK_ERR_STATE;
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * slot, 0, c->zeroStride, c->stream));
-    s.zeroAClean = true; s.touchDirty = false; s.cellsClean = true;
+    s.zeroAClean = true; s.touchDirty = false; s.cellsClean = true; s.harvested = false;
     if (s.d.alphaReset || s.d.alphaValid) s.dirty = true;
     s.d.alphaReset = 0; s.d.alphaValid = 0;
     s.k1Ran = s.alphaRan = s.alphaFetched = s.prepared = s.r2Valid = s.pendingHarvest = false;
     s.nextPass = 0; s.rangeErr = 0; s.lastRunPasses = 0;
     memset(s.hdr, 0, sizeof s.hdr);
+    return YK_OK;
+}
+
+extern "C" int yk_set_upload_format(yk_ctx* c, int packedU8) {
+    if (!c) return YK_ERR_ARG;
+    c->packedUpload = packedU8 != 0;
     return YK_OK;
 }
 
@@ -329,15 +365,59 @@ extern "C" int yk_set_image(yk_ctx* c, int slot, const int32_t* const* planes, i
     if (rc) return rc;
     YkSlotHost& s = c->slots[slot];
     CK(cudaSetDevice(c->device));
-    for (int p = 0; p < nPlanes; p++) {
-        if (!planes[p]) return YK_ERR_ARG;
-        CK(cudaMemcpyAsync(s.owned[p], planes[p], (size_t)w * h * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        s.d.plane[p] = s.owned[p];
+    for (int p = 0; p < nPlanes; p++) if (!planes[p]) return YK_ERR_ARG;
+    unsigned bad = 0;
+    if (c->packedUpload) {
+        // Plane samples are 0..255 on this path: pack them to bytes on the host (threads, range check included) and move a
+        // quarter of the bytes over PCIe; yk_k_analyze_u8 stages the packed planes with byte TMA boxes
+        const size_t pitch = ((size_t)w + 15) / 16 * 16, planeBytes = pitch * h, need = planeBytes * nPlanes;
+        if (s.stageBytes < need) {
+            if (s.stageBusy) { CK(cudaEventSynchronize(s.stageFree)); s.stageBusy = false; }
+            if (s.stageHost) cudaFreeHost(s.stageHost);
+            s.stageHost = nullptr; s.stageBytes = 0;
+            CK(cudaMallocHost((void**)&s.stageHost, need));
+            s.stageBytes = need;
+        }
+        if (!s.stageFree) CK(cudaEventCreateWithFlags(&s.stageFree, cudaEventDisableTiming));
+        if (s.stageBusy) { CK(cudaEventSynchronize(s.stageFree)); s.stageBusy = false; }     // the previous upload has left the staging buffer
+        for (int p = 0; p < nPlanes; p++) {
+            bad |= yk_hostpack_plane(c->packer, planes[p], s.stageHost + p * planeBytes, w, h, pitch);
+            CK(cudaMemcpyAsync(s.ownedU8[p], s.stageHost + p * planeBytes, planeBytes, cudaMemcpyHostToDevice, c->stream));      // overlaps the packing of the next plane
+            s.d.planeU8[p] = s.ownedU8[p];
+            s.d.plane[p] = s.owned[p];
+        }
+        CK(cudaEventRecord(s.stageFree, c->stream));
+        s.stageBusy = true;
+        s.d.isU8 = 1; s.d.pitchU8 = (int)pitch;
+        s.int32Valid = false;
+    } else {
+        for (int p = 0; p < nPlanes; p++) {
+            CK(cudaMemcpyAsync(s.owned[p], planes[p], (size_t)w * h * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            s.d.plane[p] = s.owned[p];
+            s.d.planeU8[p] = nullptr;
+        }
+        s.d.isU8 = 0; s.d.pitchU8 = 0;
+        s.int32Valid = true;
     }
-    for (int p = nPlanes; p < 4; p++) s.d.plane[p] = nullptr;
+    for (int p = nPlanes; p < 4; p++) { s.d.plane[p] = nullptr; s.d.planeU8[p] = nullptr; }
     s.borrowed = false;
     if ((rc = encode_slot_tmaps(s))) return rc;
-    return yk_reset_state(c, slot);
+    rc = yk_reset_state(c, slot);
+    if (bad & ~255u) s.rangeErr = 1;
+    return rc;
+}
+
+// the kernels outside the hot path (state download, DynamicTileEncode) read Plane-style int32 samples
+static int ensure_int32(yk_ctx* c, int slot) {
+    YkSlotHost& s = c->slots[slot];
+    if (s.int32Valid) return YK_OK;
+    int rc = upload_slots_fwd(c, slot, 1);
+    if (rc) return rc;
+    yk_launch_expand(c->slotsDev, slot, s.d.nPlanes, s.d.w, s.d.h, s.owned, c->stream);
+    c->launches++;
+    CK(cudaGetLastError());
+    s.int32Valid = true;
+    return YK_OK;
 }
 
 extern "C" int yk_set_image_device(yk_ctx* c, int slot, const int32_t* const* devPlanes, int nPlanes, int w, int h) {
@@ -348,7 +428,9 @@ extern "C" int yk_set_image_device(yk_ctx* c, int slot, const int32_t* const* de
     for (int p = 0; p < nPlanes; p++) {
         if (!devPlanes[p] || ((uintptr_t)devPlanes[p] & 15)) return YK_ERR_ARG;
         s.d.plane[p] = devPlanes[p];
+        s.d.planeU8[p] = nullptr;
     }
+    s.d.isU8 = 0; s.d.pitchU8 = 0; s.int32Valid = true;
     for (int p = nPlanes; p < 4; p++) s.d.plane[p] = nullptr;
     s.borrowed = true;
     if ((rc = encode_slot_tmaps(s))) return rc;
@@ -360,6 +442,8 @@ extern "C" int32_t* yk_device_plane(yk_ctx* c, int slot, int p) {
     return c->slots[slot].owned[p];
 }
 
+static int upload_slots(yk_ctx* c, int slot0, int nSlots);
+static int upload_slots_fwd(yk_ctx* c, int slot0, int nSlots) { return upload_slots(c, slot0, nSlots); }
 static int upload_slots(yk_ctx* c, int slot0, int nSlots) {
     for (int i = slot0; i < slot0 + nSlots; i++) {
         YkSlotHost& s = c->slots[i];
@@ -377,7 +461,7 @@ static int check_batch(yk_ctx* c, int slot0, int nSlots) {
     for (int i = slot0; i < slot0 + nSlots; i++) {
         const YkSlotHost& s = c->slots[i];
         if (!s.haveImage) return YK_ERR_STATE;
-        if (s.d.w != a.d.w || s.d.h != a.d.h) return YK_ERR_ARG;
+        if (s.d.w != a.d.w || s.d.h != a.d.h || s.d.isU8 != a.d.isU8) return YK_ERR_ARG;
     }
     return YK_OK;
 }
@@ -436,7 +520,7 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     krun.fresh = fresh ? 1 : 0;
     if ((phases & 1) && (krun.nPasses > 0 || krun.doAlpha || krun.doR2)) {
         YkTimed t(c, 0);
-        yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, c->numSMs, krun, c->stream); c->launches++;
+        yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, c->numSMs, a.d.isU8 != 0, krun, c->stream); c->launches++;
     }
     if (phases & 2) {
         // ownership of the touched lattice points, then one scan/compaction kernel: rgbStream emission of the run's
@@ -456,7 +540,7 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     CK(cudaGetLastError());
     for (int i = slot0; i < slot0 + nSlots; i++) {
         YkSlotHost& s = c->slots[i];
-        s.k1Ran = true; s.pendingHarvest = true; s.lastRunPasses = (run.doAlpha ? 256 : 0);
+        s.k1Ran = true; s.pendingHarvest = true; s.harvested = false; s.lastRunPasses = (run.doAlpha ? 256 : 0);
         for (int p = 0; p < run.nPasses; p++) s.lastRunPasses |= 1 << run.passId[p];
         if (run.doAlpha && s.d.nPlanes == 4) { s.alphaRan = true; s.alphaFetched = false; }
         if (run.nPasses > 0) { s.r2Valid = false; s.touchDirty = true; s.cellsClean = false; }
@@ -487,6 +571,58 @@ extern "C" int yk_prepare_quad_smooth(yk_ctx* c, int slot, int rejectFactor) {
     return yk_analyze(c, slot, 1, YK_STAGE_GRADIENT, rejectFactor);
 }
 
+// ---- results to the host ---------------------------------------------------------------------------------
+// One pinned arena per slot receives every result stream of the last run with two synchronisations (the header with the
+// stream lengths first, then all streams at their actual sizes); the getters then serve from it.
+static size_t pass_bitmap_bytes(const YkSlotHost& s, int p) {
+    const YkPassGeom& g = kGeom[p];
+    return (size_t)((s.d.w + g.bw - 1) / g.bw) * ((s.d.h + g.bh - 1) / g.bh) * g.bits / 8;
+}
+static int harvest(yk_ctx* c, YkSlotHost& s) {
+    if (s.harvested) return s.rangeErr ? YK_ERR_RANGE : YK_OK;
+    int rc = fetch_hdr(c, s);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    const int mask = s.prepared ? (1 << YK_NPASS) - 1 : (s.lastRunPasses & ((1 << YK_NPASS) - 1));
+    auto up = [](size_t v) { return (v + 63) / 64 * 64; };
+    size_t off = 0;
+    for (int p = 0; p < YK_NPASS; p++) {
+        s.arBitmap[p] = off; if (mask & (1 << p)) off += up(pass_bitmap_bytes(s, p));
+        s.arRgb[p] = off; if (mask & (1 << p)) off += up((size_t)s.hdr[YK_HD_PASS0 + p * YK_ST_STRIDE + YK_ST_RGBBYTES]);
+    }
+    const size_t ni = 16ull * (size_t)s.hdr[YK_HD_R2_CHUNKS], nt = 3ull * (size_t)s.hdr[YK_HD_R2_TILES];
+    for (int pl = 0; pl < 3; pl++) {
+        s.arIdx[pl] = off; if (s.r2Valid) off += up(ni);
+        s.arType[pl] = off; if (s.r2Valid) off += up(nt);
+    }
+    const bool wantKept = s.alphaRan && s.d.nPlanes == 4;
+    const size_t nKept = (size_t)((s.d.w + 15) / 16) * ((s.d.h + 15) / 16);
+    s.arKept = off; if (wantKept) off += up(nKept);
+    if (off > s.arenaBytes) {
+        if (s.arena) cudaFreeHost(s.arena);
+        s.arena = nullptr; s.arenaBytes = 0;
+        const size_t want = off + off / 4 + 4096;
+        CK(cudaMallocHost((void**)&s.arena, want));
+        s.arenaBytes = want;
+    }
+    for (int p = 0; p < YK_NPASS; p++) {
+        if (!(mask & (1 << p))) continue;
+        CK(cudaMemcpyAsync(s.arena + s.arBitmap[p], s.d.bitmap[p], pass_bitmap_bytes(s, p), cudaMemcpyDeviceToHost, c->stream));
+        const size_t nrgb = (size_t)s.hdr[YK_HD_PASS0 + p * YK_ST_STRIDE + YK_ST_RGBBYTES];
+        if (nrgb) CK(cudaMemcpyAsync(s.arena + s.arRgb[p], s.d.rgb[p], nrgb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (s.r2Valid)
+        for (int pl = 0; pl < 3; pl++) {
+            if (ni) CK(cudaMemcpyAsync(s.arena + s.arIdx[pl], s.d.r2Idx[pl], ni, cudaMemcpyDeviceToHost, c->stream));
+            if (nt) CK(cudaMemcpyAsync(s.arena + s.arType[pl], s.d.r2Type[pl], nt, cudaMemcpyDeviceToHost, c->stream));
+        }
+    if (wantKept) CK(cudaMemcpyAsync(s.arena + s.arKept, s.d.alphaKept, nKept, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    s.arMask = mask; s.arR2 = s.r2Valid; s.arHasKept = wantKept;
+    s.harvested = true;
+    return YK_OK;
+}
+
 // ---- alpha ------------------------------------------------------------------------------------------------
 static int alpha_finish(yk_ctx* c, YkSlotHost& s) {
     if (s.alphaFetched) return YK_OK;
@@ -500,9 +636,15 @@ static int alpha_finish(yk_ctx* c, YkSlotHost& s) {
     s.bound[0] = L; s.bound[1] = T; s.bound[2] = R; s.bound[3] = B;
     s.alphaBitmap.clear();
     if (L != 0 || T != 0 || R != w || B != s.d.imgH) {           // EC.cpp:1294
-        std::vector<uint8_t> kept((size_t)tw * th);
-        CK(cudaMemcpyAsync(kept.data(), s.d.alphaKept, kept.size(), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        std::vector<uint8_t> keptBuf;
+        const uint8_t* kept;
+        if (s.harvested && s.arHasKept) kept = s.arena + s.arKept;
+        else {
+            keptBuf.resize((size_t)tw * th);
+            CK(cudaMemcpyAsync(keptBuf.data(), s.d.alphaKept, keptBuf.size(), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            kept = keptBuf.data();
+        }
         const int bx0 = L >> 4, bx1 = (R + 15) >> 4, by0 = T >> 4, by1 = (B + 15) >> 4;
         const int tWB = bx1 - bx0, tHB = by1 - by0;
         s.alphaBitmap.assign((size_t)(tWB * tHB + 7) / 8, 0);
@@ -565,17 +707,14 @@ extern "C" int yk_gradient_pass(yk_ctx* c, int slot, int rejectFactor, int shX, 
         if ((rc = enqueue(c, slot, 1, run, true, false))) return rc;
         s.nextPass = -1;
     }
-    if ((rc = fetch_hdr(c, s))) return rc;
-    const YkPassGeom& g = kGeom[pid];
-    const int w = s.d.w, h = s.d.h;
-    const int nb = ((w + g.bw - 1) / g.bw) * ((h + g.bh - 1) / g.bh) * g.bits / 8;
+    if ((rc = harvest(c, s))) return rc;
+    const int w = s.d.w;
+    const int nb = (int)pass_bitmap_bytes(s, pid);
     const int* st = s.hdr + YK_HD_PASS0 + pid * YK_ST_STRIDE;
     const int nrgb = st[YK_ST_RGBBYTES];
     if (nb > bitmapCap || nrgb > rgbCap) return YK_ERR_CAPACITY;
-    CK(cudaSetDevice(c->device));
-    if (bitmap) CK(cudaMemcpyAsync(bitmap, s.d.bitmap[pid], nb, cudaMemcpyDeviceToHost, c->stream));
-    if (rgb && nrgb) CK(cudaMemcpyAsync(rgb, s.d.rgb[pid], nrgb, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    if (bitmap) memcpy(bitmap, s.arena + s.arBitmap[pid], nb);
+    if (rgb && nrgb) memcpy(rgb, s.arena + s.arRgb[pid], nrgb);
     if (bitmapBytes) *bitmapBytes = nb;
     if (rgbBytes) *rgbBytes = nrgb;
     if (tileDone) *tileDone = st[YK_ST_TILEDONE];
@@ -599,13 +738,11 @@ extern "C" int yk_range1d(yk_ctx* c, int slot, int plane, uint8_t* idx, int idxC
         YkRun run; memset(&run, 0, sizeof run); run.rejectFactor = 3;      // no gradient pass: refresh segments, scan, code
         if ((rc = enqueue(c, slot, 1, run, false, true))) return rc;
     }
-    if ((rc = fetch_hdr(c, s))) return rc;
+    if ((rc = harvest(c, s))) return rc;
     const long long ni = 16ll * s.hdr[YK_HD_R2_CHUNKS], nt = 3ll * s.hdr[YK_HD_R2_TILES];
     if (ni > idxCap || nt > typeCap) return YK_ERR_CAPACITY;
-    CK(cudaSetDevice(c->device));
-    if (idx && ni) CK(cudaMemcpyAsync(idx, s.d.r2Idx[plane], (size_t)ni, cudaMemcpyDeviceToHost, c->stream));
-    if (type && nt) CK(cudaMemcpyAsync(type, s.d.r2Type[plane], (size_t)nt, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    if (idx && ni) memcpy(idx, s.arena + s.arIdx[plane], (size_t)ni);
+    if (type && nt) memcpy(type, s.arena + s.arType[plane], (size_t)nt);
     if (idxBytes) *idxBytes = (int)ni;
     if (typeBytes) *typeBytes = (int)nt;
     return YK_OK;
@@ -655,6 +792,7 @@ extern "C" int yk_range_dyn(yk_ctx* c, int slot, int plane, int mode3BitOnly, ui
     CK(cudaSetDevice(c->device));
     int rc;
     if ((rc = ensure_r1_lut(c))) return rc;
+    if ((rc = ensure_int32(c, slot))) return rc;
     int bound[4] = { 0, 0, w, h };                               // CheckMipmapMask: full image (EC.cpp:2784-2794)
     if (s.alphaRan) { if ((rc = alpha_finish(c, s))) return rc; memcpy(bound, s.bound, sizeof bound); }
     const int cx = (bound[0] >> 3) << 3, cy = (bound[1] >> 3) << 3;              // EC.cpp:4386-4391
@@ -710,6 +848,7 @@ extern "C" int yk_download_state(yk_ctx* c, int slot, int32_t* smoothMap, int32_
     if (s.alphaRan && !s.alphaFetched) { int rc = alpha_finish(c, s); if (rc) return rc; }
     int rc = upload_slots(c, slot, 1);
     if (rc) return rc;
+    if (recon && (rc = ensure_int32(c, slot))) return rc;
     const size_t n = (size_t)s.d.w * s.d.h, n1 = (size_t)(s.d.w + 1) * (s.d.h + 1);
     int32_t *dSmooth = nullptr, *dMask = nullptr, *dMapped = nullptr, *dRec = nullptr;
     const bool wantSmooth = smoothMap || mapSmoothTile, wantRec = recon != nullptr;
@@ -750,6 +889,40 @@ extern "C" int yk_result_bytes(yk_ctx* c, int slot, long long out[6]) {
     return YK_OK;
 }
 
+// ---- everything at once, without further copies -----------------------------------------------------------
+extern "C" int yk_fetch_all(yk_ctx* c, int slot, yk_results* out) {
+    if (!slot_ok(c, slot) || !out) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage || !s.k1Ran) return YK_ERR_STATE;
+    int rc = harvest(c, s);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    const int w = s.d.w;
+    for (int p = 0; p < YK_NPASS; p++) {
+        if (!(s.arMask & (1 << p))) continue;
+        const int* st = s.hdr + YK_HD_PASS0 + p * YK_ST_STRIDE;
+        out->bitmap[p] = s.arena + s.arBitmap[p]; out->bitmapBytes[p] = (int)pass_bitmap_bytes(s, p);
+        out->rgb[p] = s.arena + s.arRgb[p]; out->rgbBytes[p] = st[YK_ST_RGBBYTES];
+        out->tileDone[p] = st[YK_ST_TILEDONE];
+        out->bbox[p][0] = w - st[YK_ST_MINX]; out->bbox[p][1] = st[YK_ST_MINY] ? INT_MAX / 2 - st[YK_ST_MINY] : s.d.imgH;
+        out->bbox[p][2] = st[YK_ST_MAXX]; out->bbox[p][3] = st[YK_ST_MAXY];
+    }
+    if (s.arR2) {
+        out->r2IdxBytes = 16 * s.hdr[YK_HD_R2_CHUNKS]; out->r2TypeBytes = 3 * s.hdr[YK_HD_R2_TILES];
+        for (int pl = 0; pl < 3; pl++) { out->r2Idx[pl] = s.arena + s.arIdx[pl]; out->r2Type[pl] = s.arena + s.arType[pl]; }
+    }
+    if (s.alphaRan && s.d.nPlanes == 4 && !s.d.hasAbove && !s.d.hasBelow) {
+        rc = alpha_finish(c, s);
+        if (rc == YK_OK) {
+            out->alphaValid = 1;
+            out->alphaBitmap = s.alphaBitmap.empty() ? nullptr : s.alphaBitmap.data(); out->alphaBitmapBytes = (int)s.alphaBitmap.size();
+            memcpy(out->alphaBound, s.bound, sizeof s.bound); memcpy(out->alphaChunkBBox, s.chunkBBox, sizeof s.chunkBBox);
+            out->alphaRemaining = s.remaining; out->alphaWroteChunk = s.wroteChunk;
+        }
+    }
+    return YK_OK;
+}
+
 // ---- multi-GPU: tile-row strips of one large image ----------------------------------------
 extern "C" int yk_strip_config(yk_ctx* c, int slot, int imgH, int y0) {
     if (!slot_ok(c, slot)) return YK_ERR_ARG;
@@ -759,7 +932,8 @@ extern "C" int yk_strip_config(yk_ctx* c, int slot, int imgH, int y0) {
     if (imgH < h || y0 < 0 || y0 + h > imgH || (y0 & 63)) return YK_ERR_ARG;
     if (y0 + h < imgH && (h & 63)) return YK_ERR_ARG;            // only the last strip may end off the 64-row grid
     CK(cudaSetDevice(c->device));
-    const size_t need = (size_t)3 * w * sizeof(int32_t) + 2 * (size_t)s.d.latW * sizeof(uint32_t);
+    const size_t es = s.d.isU8 ? 1 : sizeof(int32_t), rowBytes = ((size_t)w * es + 15) / 16 * 16;
+    const size_t need = 3 * rowBytes + 2 * (size_t)s.d.latW * sizeof(uint32_t);
     if (s.haloBytes < need) {
         if (s.haloIn) cudaFree(s.haloIn);
         s.haloIn = nullptr; s.haloBytes = 0;
@@ -769,9 +943,8 @@ extern "C" int yk_strip_config(yk_ctx* c, int slot, int imgH, int y0) {
     CK(cudaMemsetAsync(s.haloIn, 0, need, c->stream));
     s.d.imgH = imgH; s.d.y0 = y0;
     s.d.hasAbove = y0 > 0; s.d.hasBelow = y0 + h < imgH;
-    int32_t* row = (int32_t*)s.haloIn;
-    for (int p = 0; p < 3; p++) s.d.rowBelow[p] = s.d.hasBelow ? row + (size_t)p * w : nullptr;
-    s.d.touchInTop = (const uint32_t*)(s.haloIn + (size_t)3 * w * sizeof(int32_t));
+    for (int p = 0; p < 3; p++) s.d.rowBelow[p] = s.d.hasBelow ? (const void*)(s.haloIn + p * rowBytes) : nullptr;
+    s.d.touchInTop = (const uint32_t*)(s.haloIn + 3 * rowBytes);
     s.d.touchInBottom = s.d.touchInTop + s.d.latW;
     s.dirty = true;
     return YK_OK;
@@ -784,12 +957,13 @@ extern "C" int yk_strip_halo_ptrs(yk_ctx* c, int slot, yk_strip_halo* out) {
     const int w = s.d.w;
     memset(out, 0, sizeof *out);
     out->haloIn = s.haloIn; out->haloBytes = s.haloBytes;
-    out->pixelRowInOffset = 0; out->pixelRowBytes = (size_t)3 * w * sizeof(int32_t);
+    const size_t es = s.d.isU8 ? 1 : sizeof(int32_t), rowBytes = ((size_t)w * es + 15) / 16 * 16;
+    out->pixelRowInOffset = 0; out->pixelRowBytes = 3 * rowBytes; out->pixelRowStride = rowBytes;
     out->touchInTopOffset = out->pixelRowBytes;
     out->touchBytes = (size_t)s.d.latW * sizeof(uint32_t);
     out->touchInBottomOffset = out->touchInTopOffset + out->touchBytes;
-    for (int p = 0; p < 3; p++) out->pixelRowOut[p] = s.d.plane[p];                      // first pixel row of each colour plane
-    out->planeRowBytes = (size_t)w * sizeof(int32_t);
+    for (int p = 0; p < 3; p++) out->pixelRowOut[p] = s.d.isU8 ? (const void*)s.d.planeU8[p] : (const void*)s.d.plane[p];   // first pixel row of each colour plane
+    out->planeRowBytes = (size_t)w * es;
     out->touchOutTop = s.d.touchMap;                                                         // lattice row 0
     out->touchOutBottom = s.d.touchMap + (size_t)(s.d.latH - 1) * s.d.latW;                  // lattice row h/4
     return YK_OK;

@@ -41,10 +41,15 @@ struct alignas(64) YkTmap { unsigned long long opaque[16]; };
 #define YK_RAW_ROWS 17
 
 // Device-visible description of one slot (one image + all results of its analysis).
+#define YK_U8_BOX 80            // bytes per row of a staged colour box of a packed (u8) plane: 64 + corner column, 16-byte granular
+
 struct alignas(128) YkSlotDev {
-    YkTmap tmap[4];             // per plane (R, G, B, alpha)
-    const int32_t* plane[4];    // int32 row-major planes, pitch == w (Plane::GetPixels(), framework.h:81)
-    const int32_t* rowBelow[3]; // strip mode: the pixel row under the strip (3 x w int32), else NULL
+    YkTmap tmap[4];             // per plane (R, G, B, alpha): int32 planes, or the packed u8 planes when isU8
+    const int32_t* plane[4];    // int32 row-major planes, pitch == w (Plane::GetPixels(), framework.h:81); with isU8 they are
+                                //   only filled on demand (yk_k_expand) for the kernels outside the hot path
+    const uint8_t* planeU8[4];  // packed upload (yk_set_image): one byte per sample, row pitch pitchU8
+    int isU8, pitchU8;
+    const void* rowBelow[3];    // strip mode: the pixel row under the strip (w samples, int32 or u8 like the planes), else NULL
     int w, h, nPlanes;
     int nbx, nby;               // 64x64 regions
     int imgH, y0;               // strip mode: height of the whole image / first row of this strip (else h, 0)
@@ -95,7 +100,8 @@ extern "C++" {
 #endif
 // launch wrappers (yk_kernels.cu); `slots` is a device array, grid.y indexes it from slot0
 int  yk_analyze_setup(int* numSMs);      // opt-in shared memory of the persistent kernel; returns a cudaError_t
-void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, int gridCtas, const YkRun& run, cudaStream_t st);
+void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, int gridCtas, bool packedU8, const YkRun& run, cudaStream_t st);
+void yk_launch_expand(const YkSlotDev* slotsDev, int slot, int nPlanes, int w, int h, int32_t* const* dst, cudaStream_t st);
 void yk_launch_fold_touch(const YkSlotDev* slotsDev, int slot0, int nSlots, int nWords, cudaStream_t st);
 void yk_launch_owner(const YkSlotDev* slotsDev, int slot0, int nSlots, int nPoints, const YkRun& run, cudaStream_t st);
 void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int gradGroups, int r2Groups, const YkRun& run, cudaStream_t st);

@@ -26,7 +26,8 @@ static __device__ __forceinline__ int yk_tile_pos(const YkGeomC& g, int w, int g
 static __device__ __forceinline__ int yk_src(const YkSlotDev& S, int c, int x, int y) {
     x = min(x, S.w - 1);
     if (y >= S.h) {
-        if (S.rowBelow[c]) return __ldg(S.rowBelow[c] + x);      // strip mode: the real row below
+        if (S.rowBelow[c])                                       // strip mode: the real row below (typed like the uploaded planes)
+            return S.isU8 ? (int)__ldg(reinterpret_cast<const uint8_t*>(S.rowBelow[c]) + x) : __ldg(reinterpret_cast<const int32_t*>(S.rowBelow[c]) + x);
         y = S.h - 1;
     }
     return __ldg(S.plane[c] + (size_t)y * S.w + x);

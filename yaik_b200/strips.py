@@ -86,7 +86,7 @@ class LocalTransport:
         for k in range(len(rows) - 1):
             src, dst = halos[k + 1], halos[k]
             for p in range(3):
-                ctxs[k + 1].copy_async(dst.haloIn + dst.pixelRowInOffset + p * src.planeRowBytes, src.pixelRowOut[p], src.planeRowBytes)
+                ctxs[k + 1].copy_async(dst.haloIn + dst.pixelRowInOffset + p * dst.pixelRowStride, src.pixelRowOut[p], src.planeRowBytes)
         for ctx in ctxs:
             ctx.sync()
         for ctx in ctxs:
@@ -153,7 +153,7 @@ class DistTransport:
         if self.mode == "ipc":
             if above is not None:
                 for p in range(3):
-                    ctx.copy_async(peers[above] + halo.pixelRowInOffset + p * halo.planeRowBytes, halo.pixelRowOut[p], halo.planeRowBytes)
+                    ctx.copy_async(peers[above] + halo.pixelRowInOffset + p * halo.pixelRowStride, halo.pixelRowOut[p], halo.planeRowBytes)
             if active:
                 ctx.sync()
             dist.barrier()
@@ -161,9 +161,10 @@ class DistTransport:
             mine = None
             if above is not None:
                 mine = np.concatenate([ctx.copy_to_host(halo.pixelRowOut[p], halo.planeRowBytes) for p in range(3)])
-            got = self._sendrecv_host(above, mine, below, halo.pixelRowBytes if below is not None else 0)
+            got = self._sendrecv_host(above, mine, below, 3 * halo.planeRowBytes if below is not None else 0)
             if got is not None:
-                ctx.copy_from_host(halo.haloIn + halo.pixelRowInOffset, got)
+                for p in range(3):
+                    ctx.copy_from_host(halo.haloIn + halo.pixelRowInOffset + p * halo.pixelRowStride, got[p * halo.planeRowBytes:(p + 1) * halo.planeRowBytes])
         if active:
             ctx.strip_phase(0, reject=reject)
             ctx.sync()
