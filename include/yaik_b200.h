@@ -59,6 +59,12 @@ void yk_destroy(yk_ctx* ctx);
 int  yk_set_stream(yk_ctx* ctx, void* cudaStream);
 int  yk_sync(yk_ctx* ctx);
 
+/* The analysis kernel is persistent: `ctas` CTAs (0 = one per SM, the default and the best choice for one image at a
+ * time).  When independent images are pipelined over several contexts / streams, half the SM count per launch lets two
+ * launches run side by side and hides each one's ramp and tail.  yk_sm_count: SMs of the context's device. */
+int  yk_set_analysis_ctas(yk_ctx* ctx, int ctas);
+int  yk_sm_count(yk_ctx* ctx);
+
 /* Pinned host memory for Plane::pixels so uploads run at full PCIe rate (Plane ctor, framework.h:76). */
 void* yk_host_alloc(size_t bytes);
 void  yk_host_free(void* p);

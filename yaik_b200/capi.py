@@ -21,7 +21,7 @@ STAGE_ALPHA, STAGE_GRADIENT, STAGE_RANGE1D, STAGE_RANGEDYN, STAGE_RANGEDYN3 = 1,
 
 EXPORTS = [
     "yk_abi_version", "yk_error_string", "yk_last_cuda_error", "yk_device_count", "yk_create", "yk_destroy",
-    "yk_set_stream", "yk_sync", "yk_host_alloc", "yk_host_free", "yk_set_image", "yk_set_image_device", "yk_set_upload_format",
+    "yk_set_stream", "yk_sync", "yk_set_analysis_ctas", "yk_sm_count", "yk_host_alloc", "yk_host_free", "yk_set_image", "yk_set_image_device", "yk_set_upload_format",
     "yk_device_plane", "yk_reset_state", "yk_analyze", "yk_alpha_reject", "yk_prepare_quad_smooth",
     "yk_gradient_pass", "yk_range1d", "yk_range_dyn", "yk_download_state", "yk_fetch_all", "yk_result_bytes", "yk_launch_count",
     "yk_profile", "yk_profile_read",
@@ -60,7 +60,7 @@ def bitmap_bytes(w, h, shx, shy):
 
 
 def load_library(path: str | None = None):
-    path = path or LIB_PATH
+    path = path or os.environ.get("YK_LIB") or LIB_PATH      # YK_LIB: developer override for A/B builds of the same sources
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: build it with `python -m yaik_b200.build` (nvcc, sm_100a). "
                           "yaik_b200 has no CPU fallback.")
@@ -79,6 +79,8 @@ def load_library(path: str | None = None):
     L.yk_destroy.restype = None
     L.yk_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.yk_sync.argtypes = [C.c_void_p]
+    L.yk_set_analysis_ctas.argtypes = [C.c_void_p, C.c_int]
+    L.yk_sm_count.argtypes = [C.c_void_p]
     L.yk_set_image.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
     L.yk_set_image_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
     L.yk_reset_state.argtypes = [C.c_void_p, C.c_int]
@@ -137,6 +139,12 @@ class Context:
 
     def set_stream(self, cuda_stream: int):
         self._ck(self.L.yk_set_stream(self.ctx, C.c_void_p(cuda_stream)), "yk_set_stream")
+
+    def set_analysis_ctas(self, ctas: int):
+        self._ck(self.L.yk_set_analysis_ctas(self.ctx, ctas), "yk_set_analysis_ctas")
+
+    def sm_count(self) -> int:
+        return int(self.L.yk_sm_count(self.ctx))
 
     def sync(self):
         self._ck(self.L.yk_sync(self.ctx), "yk_sync")

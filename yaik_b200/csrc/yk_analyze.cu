@@ -14,10 +14,11 @@
 //                                                            the pixels already in shared memory, into a fixed per-tile
 //                                                            place; yk_k_emit moves them to their stream offsets
 //
-// Structure: one CTA per SM, persistent.  The unit of work is one macro-tile row of a region (64 x 16 pixels, four macro
-// tiles), taken by global ticket.  One producer warp takes tickets — never more than a few units ahead of the consumers,
-// so the CTAs finish together — and issues the TMA box loads (cp.async.bulk.tensor, one per plane: 17 x 68 int32 samples
-// per colour plane, 16 x 64 alpha) into a ring of raw staging buffers, completion on an mbarrier per buffer.
+// Structure: one CTA per SM, persistent.  The unit of work is one macro-tile row of two neighbouring regions (128 x 16
+// pixels, eight macro tiles; the TMA unit's service time is per box row, about 22 cycles for rows up to 528 bytes, so the
+// boxes are made wide), taken by global ticket.  One producer warp takes tickets — never more than a few units ahead of the consumers,
+// so the CTAs finish together — and issues the TMA box loads (cp.async.bulk.tensor, one per plane: 17 x 132 int32 samples
+// per colour plane, 16 x 128 alpha) into a ring of raw staging buffers, completion on an mbarrier per buffer.
 // 23 consumer warps take macro tiles from a block-local queue: a warp packs its macro tile's 17x17x3 samples to bytes
 // into a warp-private tile (clamped the way Plane::GetPixelValue clamps), tests its alpha tile, releases the raw buffer,
 // then runs the cascade and the range stage out of the private tile and writes the macro tile's results straight to
@@ -27,29 +28,33 @@
 // No tensor cores: the work is integer min/max reductions over bytes, bounded by HBM and the integer pipes.
 #include "yk_device.h"
 
-#define YKA_NR 8                    // raw int32 staging buffers (TMA destinations), one macro-tile row of a region each
+#define YKA_NR 4                    // raw staging buffers (TMA destinations), one unit each
+#define YKA_ITEMS 8                 // macro tiles per unit
+#ifndef YKA_TICKETS
 #define YKA_TICKETS 4               // tickets a CTA holds ahead of the unit it is issuing
-#define YKA_LOOKAHEAD 7             // units the producer may run ahead of the unit the consumers are taking items from
+#endif
+#define YKA_LOOKAHEAD 3             // units the producer may run ahead of the unit the consumers are taking items from
 #define YKA_CONS_WARPS 23
 #define YKA_THREADS ((YKA_CONS_WARPS + 1) * 32)
-#define YKA_RAW_PLANE_INTS 1184     // 17 rows x 68 ints = 1156, rounded so every plane starts 128-byte aligned
-#define YKA_RAW_STAGE_INTS (3 * YKA_RAW_PLANE_INTS + 16 * 64)
+#define YKA_RAW_PLANE_INTS 2272     // 17 rows x 132 ints = 2244, rounded so every plane starts 128-byte aligned
+#define YKA_RAW_STAGE_INTS (3 * YKA_RAW_PLANE_INTS + 16 * YK_UNIT_W)
 #define YKA_COLOR_TX (3u * YK_RAW_ROWS * YK_RAW_PITCH * 4u)
-#define YKA_ALPHA_TX (16u * 64u * 4u)
-#define YKA_RAWB_PLANE 1408         // packed upload: 17 rows x 80 bytes = 1360, rounded to a multiple of 128
-#define YKA_RAWB_STAGE (3 * YKA_RAWB_PLANE + 16 * 64)
+#define YKA_ALPHA_TX (16u * YK_UNIT_W * 4u)
+#define YKA_RAWB_PLANE 2560         // packed upload: 17 rows x 144 bytes = 2448, rounded to a multiple of 128
+#define YKA_RAWB_STAGE (3 * YKA_RAWB_PLANE + 16 * YK_UNIT_W)
 #define YKA_COLORB_TX (3u * YK_RAW_ROWS * YK_U8_BOX)
-#define YKA_ALPHAB_TX (16u * 64u)
+#define YKA_ALPHAB_TX (16u * YK_UNIT_W)
+#ifndef YKA_PRETEST_CHANNELS
+#define YKA_PRETEST_CHANNELS 1
+#endif
 #define YKP_RS 24                   // row pitch in bytes of a warp-private 17x17 byte tile
 #define YKP_CH (17 * YKP_RS)        // bytes of one channel of it
 #define YKP_TILE 1232               // 3 channels, rounded to a multiple of 16
-// a consumer waits on the phase parity of a raw buffer's barrier: the items in flight (one per consumer warp, consecutive
-// in the queue, four per raw buffer) must span fewer raw buffers than the ring holds
-static_assert((YKA_CONS_WARPS + 2) / 4 + 2 <= YKA_NR, "work items in flight must not wrap the raw ring");
 static_assert(YKA_LOOKAHEAD < YKA_NR, "look-ahead is bounded by the raw ring");
 
 struct YkaUnit {                    // what the producer says about the unit staged in raw buffer i
-    int slot, bx, by, k, alpha;
+    int slot, bx, by, k, alpha;     // bx: the first of its two regions
+    int seq;                        // which unit of this CTA it is: a consumer checks it before it trusts the barrier's phase parity
 };
 
 // the fields of a slot descriptor a consumer warp needs (its own copy, refreshed when its items move to another image)
@@ -70,7 +75,7 @@ struct YkaSlotC {
 
 struct YkaShared {
     uint32_t pretestTab[41];
-    int      queueHead;             // next (unit sequence number * 4 + macro tile) to hand out
+    int      queueHead;             // next (unit sequence number * 8 + macro tile) to hand out
     int      endSeq;                // first unit sequence number that does not exist
     int      statSlot;              // the image whose counters are summed in `stat` (other images go straight to global memory)
     int      consLeft;              // consumer warps still running (the last one flushes `stat`)
@@ -199,7 +204,7 @@ static __device__ void yka_slot_refresh(const YkSlotDev& S, YkaSlotC& C, int slo
     __syncwarp();
 }
 
-// Consumer warp: the 17x17 samples of macro tile (mx, row k) of the region, three colour planes, from the raw rows
+// Consumer warp: the 17x17 samples of macro tile mx (0..7) of the unit whose left edge is X0, three colour planes, from the raw rows
 // staged by TMA (int32 samples, or bytes when the image was uploaded packed) into the warp-private byte tile, clamped
 // the way Plane::GetPixelValue clamps (framework.h:116-121); then the alpha-zero test of the 16x16 tile (EC.cpp:357-430
 // restated per tile).  Returns (uniformly) whether the tile has a non-zero alpha sample.
@@ -261,11 +266,11 @@ static __device__ __forceinline__ bool yka_pack_macro_tile(const void* __restric
         // samples outside the image arrive as zeros
         bool nz;
         if (U8) {
-            const uint2 v = *reinterpret_cast<const uint2*>(rawb + 3 * YKA_RAWB_PLANE + (lane >> 1) * 64 + 16 * mx + 8 * (lane & 1));
+            const uint2 v = *reinterpret_cast<const uint2*>(rawb + 3 * YKA_RAWB_PLANE + (lane >> 1) * YK_UNIT_W + 16 * mx + 8 * (lane & 1));
             nz = (v.x | v.y) != 0u;
         } else {
             const int4* __restrict__ a = reinterpret_cast<const int4*>(raw + 3 * YKA_RAW_PLANE_INTS) + 4 * mx;
-            const int4 v0 = a[(lane >> 2) * 16 + (lane & 3)], v1 = a[((lane >> 2) + 8) * 16 + (lane & 3)];
+            const int4 v0 = a[(lane >> 2) * (YK_UNIT_W / 4) + (lane & 3)], v1 = a[((lane >> 2) + 8) * (YK_UNIT_W / 4) + (lane & 3)];
             nz = (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0;
         }
         kept = __any_sync(YK_FULL, nz);
@@ -275,7 +280,7 @@ static __device__ __forceinline__ bool yka_pack_macro_tile(const void* __restric
 
 // ------------------------------------------------------------------------------------------------------------------
 // Cheap rejection of all 41 tiles (1 + 2 + 2 + 4 + 8 + 8 + 16 over the seven shapes) of a 16x16 macro tile: lane = tile,
-// one channel, the quad at the tile centre, raw corners.  A pixel whose raw-family U is outside [loWide, hiWide) cannot
+// the quad at the tile centre of every channel, raw corners.  A pixel whose raw-family U is outside [loWide, hiWide) cannot
 // be accepted by any of the six variants (a family's corners differ from the raw ones by -3..+4), so a cleared bit is a
 // proven rejection; a set bit only means "run the real test".  Bit (start(pid) + t) belongs to tile t of pass id pid.
 static __device__ __forceinline__ unsigned long long yka_pretest(const uint8_t* __restrict__ priv, const uint32_t* sTab, int wIn, int hIn,
@@ -291,17 +296,22 @@ static __device__ __forceinline__ unsigned long long yka_pretest(const uint8_t* 
             const int shx = (e >> 8) & 7, shy = (e >> 11) & 7, sh = shx + shy;
             const int lx0 = e & 15, ly0 = (e >> 4) & 15, TW = 1 << shx, TH = 1 << shy, N = 1 << sh;
             if (!((claimed >> (e >> 14)) & 1u) && lx0 + TW <= wIn && ly0 + TH <= hIn) {
-                const uint8_t* p = priv + ly0 * YKP_RS + lx0;
-                const int tl = p[0], tr = p[TW], bl = p[TH * YKP_RS], br = p[TH * YKP_RS + TW];
                 const int dx0 = (TW >> 1) & ~3, dy = TH >> 1;
-                const unsigned word = *reinterpret_cast<const unsigned*>(p + dy * YKP_RS + dx0);
-                const int B = (tr - tl) << shy, C = (bl - tl) << shx, D = tl - tr - bl + br;
-                const int step = B + D * dy;
-                const int s0 = ((tl + R) << sh) + B * dx0 + dy * (C + D * dx0);
-                const int u0 = s0 - (int)((word & 255u) << sh), u1 = s0 + step - (int)(((word >> 8) & 255u) << sh);
-                const int u2 = s0 + 2 * step - (int)(((word >> 16) & 255u) << sh), u3 = s0 + 3 * step - (int)((word >> 24) << sh);
-                const int umin = __vimin3_s32(min(u0, u1), u2, u3), umax = __vimax3_s32(max(u0, u1), u2, u3);
-                possible = !(umin < -(4 * N + N / 2 - 1) || umax >= (2 * R + 4) * N);
+                const int loW = -(4 * N + N / 2 - 1), hiW = (2 * R + 4) * N;
+                possible = true;
+#pragma unroll
+                for (int c = 0; c < YKA_PRETEST_CHANNELS; c++) {
+                    const uint8_t* p = priv + c * YKP_CH + ly0 * YKP_RS + lx0;
+                    const int tl = p[0], tr = p[TW], bl = p[TH * YKP_RS], br = p[TH * YKP_RS + TW];
+                    const unsigned word = *reinterpret_cast<const unsigned*>(p + dy * YKP_RS + dx0);
+                    const int B = (tr - tl) << shy, C = (bl - tl) << shx, D = tl - tr - bl + br;
+                    const int step = B + D * dy;
+                    const int s0 = ((tl + R) << sh) + B * dx0 + dy * (C + D * dx0);
+                    const int u0 = s0 - (int)((word & 255u) << sh), u1 = s0 + step - (int)(((word >> 8) & 255u) << sh);
+                    const int u2 = s0 + 2 * step - (int)(((word >> 16) & 255u) << sh), u3 = s0 + 3 * step - (int)((word >> 24) << sh);
+                    const int umin = __vimin3_s32(min(u0, u1), u2, u3), umax = __vimax3_s32(max(u0, u1), u2, u3);
+                    possible = possible && !(umin < loW || umax >= hiW);
+                }
             }
         }
         P |= (unsigned long long)__ballot_sync(YK_FULL, possible) << (32 * round);
@@ -634,7 +644,9 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
     YkaShared& sh = *reinterpret_cast<YkaShared*>(smem + YKA_SMEM_RAW + YKA_SMEM_PIX + YKA_SMEM_HIST + 1024);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int unitsPerSlot = nRegions * 4, total = nSlots * unitsPerSlot;
+    // units of one image: (pair of regions, macro-tile row); every image of a launch has the same size
+    const int nbxAll = slots[slot0].nbx, nPairs = (nbxAll + 1) >> 1;
+    const int unitsPerSlot = nPairs * (nRegions / nbxAll) * 4, total = nSlots * unitsPerSlot;
 
     // ---- start-up (the only block-wide barriers)
     for (int i = tid; i < (int)(sizeof(YkaShared) / 4); i += YKA_THREADS) reinterpret_cast<uint32_t*>(&sh)[i] = 0;
@@ -648,7 +660,7 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         sh.endSeq = INT_MAX;
         sh.statSlot = -1;
         sh.consLeft = YKA_CONS_WARPS;
-        for (int i = 0; i < YKA_NR; i++) { yka_mbar_init(&sh.rawFull[i], 1); yka_mbar_init(&sh.rawFree[i], 4); }
+        for (int i = 0; i < YKA_NR; i++) { yka_mbar_init(&sh.rawFull[i], 1); yka_mbar_init(&sh.rawFree[i], YKA_ITEMS); sh.unit[i].seq = -1; }
 #ifndef YK_EMULATE
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
@@ -667,9 +679,8 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         // of the image the current unit belongs to (kept in registers while the slot does not change)
         int curSlot = -1, alpha = 0;
         const YkSlotDev* S = nullptr;
-        // every image of a launch has the same size: region -> (bx, by) by a multiply-high (exact for region * nbx < 2^32)
-        const int nbx = slots[slot0].nbx;
-        const unsigned nbxMagic = nbx > 1 ? 0xFFFFFFFFu / (unsigned)nbx + 1u : 0u;
+        // pair index -> (pair column, by) by a multiply-high (exact for index * nPairs < 2^32)
+        const unsigned pairMagic = nPairs > 1 ? 0xFFFFFFFFu / (unsigned)nPairs + 1u : 0u;
 #pragma unroll
         for (int r = 0; r < YKA_TICKETS; r++) { tk[r] = total; if (lane == 0) tk[r] = atomicAdd(ticket, 1); }
         YKT_DECL;
@@ -678,7 +689,7 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
             for (int r = 0; r < YKA_TICKETS; r++) {
                 const int u = u0 + r, i = u % YKA_NR;
                 // never more than YKA_LOOKAHEAD units ahead of the consumers: the CTAs then run out of work together
-                while (u - (yka_flag_ld(&sh.queueHead) >> 2) > YKA_LOOKAHEAD) yk_spin();
+                while (u - (yka_flag_ld(&sh.queueHead) >> 3) > YKA_LOOKAHEAD) yk_spin();
                 if (u >= YKA_NR) yka_mbar_wait(&sh.rawFree[i], (unsigned)((u / YKA_NR - 1) & 1));
                 if (lane == 0) YKT(0);
                 const int item = __shfl_sync(YK_FULL, tk[r], 0);
@@ -695,18 +706,20 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
                     curSlot = slot;
                     if (u == 0 && lane == 0) sh.statSlot = slot;
                 }
-                const int region = rem >> 2, k = rem & 3;
-                const int by = nbx > 1 ? (int)__umulhi((unsigned)region, nbxMagic) : region, bx = region - by * nbx;
+                const int pr = rem >> 2, k = rem & 3;
+                const int by = nPairs > 1 ? (int)__umulhi((unsigned)pr, pairMagic) : pr, bx = 2 * (pr - by * nPairs);
                 if (lane == 0) {
                     YKT(3);
                     YkaUnit& U = sh.unit[i];
-                    U.slot = slot; U.bx = bx; U.by = by; U.k = k; U.alpha = alpha;
+                    U.slot = slot; U.bx = bx; U.by = by; U.k = k; U.alpha = alpha; U.seq = u;
                     unsigned char* dst = raw + i * STAGE_BYTES;
+#ifndef YKA_NO_PROXY_FENCE
                     yka_fence_async();
+#endif
                     yka_mbar_expect_tx(&sh.rawFull[i], (U8 ? YKA_COLORB_TX : YKA_COLOR_TX) + (alpha ? (U8 ? YKA_ALPHAB_TX : YKA_ALPHA_TX) : 0u));
                     for (int c = 0; c < 3; c++)
                         yka_tma_box(dst + c * PLANE_BYTES, &S->tmap[c], bx * 64, by * 64 + 16 * k, U8 ? YK_U8_BOX : YK_RAW_PITCH, YK_RAW_ROWS, &sh.rawFull[i], !alpha && c == 2);
-                    if (alpha) yka_tma_box(dst + 3 * PLANE_BYTES, &S->tmap[3], bx * 64, by * 64 + 16 * k, 64, 16, &sh.rawFull[i], 1);
+                    if (alpha) yka_tma_box(dst + 3 * PLANE_BYTES, &S->tmap[3], bx * 64, by * 64 + 16 * k, YK_UNIT_W, 16, &sh.rawFull[i], 1);
                     YKT(2);
                 }
             }
@@ -725,11 +738,15 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         int q = 0;
         if (lane == 0) q = atomicAdd(&sh.queueHead, 1);
         q = __shfl_sync(YK_FULL, q, 0);
-        const int u = q >> 2, mx = q & 3, i = u % YKA_NR;
+        const int u = q >> 3, mx = q & 7, i = u % YKA_NR;
         bool alive = true;
-        // the unit of this item has landed (the wait suspends the warp; it wakes up now and then to see whether the
-        // CTA has run out of units)
-        while (!yka_mbar_try_wait(&sh.rawFull[i], (unsigned)((u / YKA_NR) & 1))) {
+        // the unit of this item has been issued into raw buffer i (so the barrier's current phase is this unit's) and has
+        // landed; the second wait suspends the warp.  Both look now and then whether the CTA has run out of units.
+        while (yka_flag_ld(&sh.unit[i].seq) != u) {
+            if (yka_flag_ld(&sh.endSeq) <= u) { alive = false; break; }
+            yk_spin();
+        }
+        while (alive && !yka_mbar_try_wait(&sh.rawFull[i], (unsigned)((u / YKA_NR) & 1))) {
             if (yka_flag_ld(&sh.endSeq) <= u) { alive = false; break; }
         }
         alive = __all_sync(YK_FULL, alive);
@@ -745,7 +762,8 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         if (lane == 0) yka_mbar_arrive(&sh.rawFree[i]);      // this warp is done with the raw rows
         if (tid == 32) YKT(9);
         const int gmx = X0 + 16 * mx;
-        if (U.alpha && gmx < C.w && Yk < C.h && lane == 0) {
+        if (gmx >= C.w) continue;                            // the unit's second region does not exist (odd number of region columns)
+        if (U.alpha && Yk < C.h && lane == 0) {
             C.alphaKept[(size_t)(Yk >> 4) * ((C.w + 15) >> 4) + (gmx >> 4)] = kept ? 1 : 0;
             if (kept) {
                 // bounding box of kept tiles (EC.cpp:416-422), mins stored as extent - value so that zero means "none"

@@ -83,7 +83,8 @@ struct yk_ctx {
     // part B (claimed cells, touch map = the persistent analysis state) only by yk_reset_state
     uint8_t* zeroArea = nullptr; size_t zeroStride = 0, zeroABytes = 0;
     int* lutDev = nullptr;       // R1 tables
-    int numSMs = 1;              // grid of the persistent analysis kernel
+    int numSMs = 1;              // SMs of the device
+    int analysisCtas = 1;        // grid of the persistent analysis kernel (default: one CTA per SM)
     YkHostPacker* packer = nullptr;
     bool packedUpload = true;    // yk_set_image packs Plane samples to bytes on the host before the copy
     long long launches = 0;
@@ -178,8 +179,8 @@ static int encode_plane_tmap(YkTmap* tm, const void* plane, int elemBytes, size_
 static int encode_slot_tmaps(YkSlotHost& s) {
     for (int p = 0; p < s.d.nPlanes; p++) {
         const int rc = s.d.isU8
-            ? encode_plane_tmap(&s.d.tmap[p], s.d.planeU8[p], 1, (size_t)s.d.pitchU8, s.d.w, s.d.h, p < 3 ? YK_U8_BOX : 64, p < 3 ? YK_RAW_ROWS : 16)
-            : encode_plane_tmap(&s.d.tmap[p], s.d.plane[p], 4, (size_t)s.d.w, s.d.w, s.d.h, p < 3 ? YK_RAW_PITCH : 64, p < 3 ? YK_RAW_ROWS : 16);
+            ? encode_plane_tmap(&s.d.tmap[p], s.d.planeU8[p], 1, (size_t)s.d.pitchU8, s.d.w, s.d.h, p < 3 ? YK_U8_BOX : YK_UNIT_W, p < 3 ? YK_RAW_ROWS : 16)
+            : encode_plane_tmap(&s.d.tmap[p], s.d.plane[p], 4, (size_t)s.d.w, s.d.w, s.d.h, p < 3 ? YK_RAW_PITCH : YK_UNIT_W, p < 3 ? YK_RAW_ROWS : 16);
         if (rc) return rc;
     }
     return YK_OK;
@@ -198,6 +199,10 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->ownStream = true;
     { const int e = yk_analyze_setup(&c->numSMs); if (e) { g_lastCuda = std::string("yk_analyze_setup: ") + cudaGetErrorString((cudaError_t)e); return YK_ERR_CUDA; } }
+    // CTAs of the persistent analysis kernel (default: one per SM).  Leaving a few SMs free lets the small ownership /
+    // emission kernels of another stream run beside it when textures are pipelined over several contexts.
+    c->analysisCtas = c->numSMs;
+    { const char* e = getenv("YK_ANALYZE_CTAS"); if (e && atoi(e) > 0 && atoi(e) < c->numSMs) c->analysisCtas = atoi(e); }
     CK(cudaMalloc((void**)&c->slotsDev, sizeof(YkSlotDev) * maxSlots));
     const size_t W = maxW, H = maxH;
     const size_t nbx = (W + 63) / 64, latW = W / 4 + 1, latH = H / 4 + 1;
@@ -300,6 +305,13 @@ extern "C" int yk_sync(yk_ctx* c) {
     return YK_OK;
 }
 extern "C" long long yk_launch_count(yk_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int yk_set_analysis_ctas(yk_ctx* c, int ctas) {
+    if (!c || ctas < 0) return YK_ERR_ARG;
+    c->analysisCtas = (ctas == 0 || ctas > c->numSMs) ? c->numSMs : ctas;
+    return YK_OK;
+}
+extern "C" int yk_sm_count(yk_ctx* c) { return c ? c->numSMs : 0; }
 
 extern "C" int yk_profile(yk_ctx* c, int enable) {
     if (!c) return YK_ERR_ARG;
@@ -520,7 +532,7 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     krun.fresh = fresh ? 1 : 0;
     if ((phases & 1) && (krun.nPasses > 0 || krun.doAlpha || krun.doR2)) {
         YkTimed t(c, 0);
-        yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, c->numSMs, a.d.isU8 != 0, krun, c->stream); c->launches++;
+        yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, c->analysisCtas, a.d.isU8 != 0, krun, c->stream); c->launches++;
     }
     if (phases & 2) {
         // ownership of the touched lattice points, then one scan/compaction kernel: rgbStream emission of the run's

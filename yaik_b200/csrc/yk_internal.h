@@ -33,15 +33,16 @@ enum {
 };
 
 // TMA descriptor of one int32 plane as a 2-D tensor [h][w] (a CUtensorMap: 128 bytes, 64-byte aligned), encoded on
-// the host by cuTensorMapEncodeTiled.  Box = 68 x 17 samples for the colour planes (one macro-tile row of a 64x64
-// region plus its right / bottom corner samples), 64 x 16 for alpha; out-of-image samples arrive as zeros and are
-// never used unclamped.
+// the host by cuTensorMapEncodeTiled.  Box = 132 x 17 samples for the colour planes (one macro-tile row of two
+// neighbouring 64x64 regions plus its right / bottom corner samples: the TMA unit's cost is per box row, so rows are
+// made long), 128 x 16 for alpha; out-of-image samples arrive as zeros and are never used unclamped.
 struct alignas(64) YkTmap { unsigned long long opaque[16]; };
-#define YK_RAW_PITCH 68         // ints per row of a staged colour box
+#define YK_UNIT_W 128           // pixels a unit of the analysis kernel is wide (two regions)
+#define YK_RAW_PITCH 132        // samples per row of a staged colour box
 #define YK_RAW_ROWS 17
 
 // Device-visible description of one slot (one image + all results of its analysis).
-#define YK_U8_BOX 80            // bytes per row of a staged colour box of a packed (u8) plane: 64 + corner column, 16-byte granular
+#define YK_U8_BOX 144           // bytes per row of a staged colour box of a packed (u8) plane: 128 + corner column, 16-byte granular
 
 struct alignas(128) YkSlotDev {
     YkTmap tmap[4];             // per plane (R, G, B, alpha): int32 planes, or the packed u8 planes when isU8
@@ -100,7 +101,7 @@ extern "C++" {
 #endif
 // launch wrappers (yk_kernels.cu); `slots` is a device array, grid.y indexes it from slot0
 int  yk_analyze_setup(int* numSMs);      // opt-in shared memory of the persistent kernel; returns a cudaError_t
-void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, int gridCtas, bool packedU8, const YkRun& run, cudaStream_t st);
+void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, int gridCtas, bool packedU8, const YkRun& run, cudaStream_t st);   // nRegions: of one image (nbx * nby)
 void yk_launch_expand(const YkSlotDev* slotsDev, int slot, int nPlanes, int w, int h, int32_t* const* dst, cudaStream_t st);
 void yk_launch_fold_touch(const YkSlotDev* slotsDev, int slot0, int nSlots, int nWords, cudaStream_t st);
 void yk_launch_owner(const YkSlotDev* slotsDev, int slot0, int nSlots, int nPoints, const YkRun& run, cudaStream_t st);
