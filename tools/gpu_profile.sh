@@ -2,7 +2,7 @@
 # Usage (on the GPU box, from the repo root): tools/gpu_profile.sh TAG [kernel-regex]
 # Plain bench run first (must exit 0), then the ncu launch list and one full capture, as B200_PROFILING.md asks.
 TAG=${1:-rXX}; KRE=${2:-yk_k_}
-B="python bench.py --steps 6 --warmup 3 --e2e-steps 0 --no-cpu --no-prewarm"
+B="python bench.py --steps 8 --warmup 3 --e2e-steps 0 --no-cpu --no-prewarm --roofline-steps 4"
 mkdir -p gpurun_out
 $B > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 40 --csv --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/ncu_list_$TAG.log 2>&1
