@@ -34,7 +34,9 @@
 #define YKA_TICKETS 4               // tickets a CTA holds ahead of the unit it is issuing
 #endif
 #define YKA_LOOKAHEAD 3             // units the producer may run ahead of the unit the consumers are taking items from
+#ifndef YKA_CONS_WARPS
 #define YKA_CONS_WARPS 23
+#endif
 #define YKA_THREADS ((YKA_CONS_WARPS + 1) * 32)
 #define YKA_RAW_PLANE_INTS 2272     // 17 rows x 132 ints = 2244, rounded so every plane starts 128-byte aligned
 #define YKA_RAW_STAGE_INTS (3 * YKA_RAW_PLANE_INTS + 16 * YK_UNIT_W)
