@@ -341,6 +341,8 @@ def main():
         nbytes = W * H * 4
         nthr = max(1, args.e2e_threads)
         per = max(1, args.e2e_steps // nthr)
+        # host threads that pack the Plane samples: share the box's cores between the ranks and their worker threads
+        os.environ.setdefault("YK_PACK_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // max(1, world * nthr) + 1))))
         ectx = [capi.Context(W, H, planes=CH, slots=1, device=local, lib=lib) for _ in range(nthr)]
         hps = []
         for t in range(nthr):
