@@ -176,8 +176,8 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--e2e-steps", type=int, default=48)
-    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one context each) the end-to-end steps are pipelined over")
+    ap.add_argument("--e2e-steps", type=int, default=96)
+    ap.add_argument("--e2e-threads", type=int, default=8, help="host threads (one context each) the end-to-end steps are pipelined over")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--streams", type=int, default=8, help="contexts/streams the steps are pipelined over (1, 2, 4 or 8)")
     ap.add_argument("--analysis-ctas", type=int, default=-1, help="CTAs of the persistent analysis kernel in the pipelined region (-1: half the SMs when streams > 1, else one per SM)")

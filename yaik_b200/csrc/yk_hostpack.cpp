@@ -27,6 +27,8 @@ unsigned pack_row_scalar(const int32_t* src, uint8_t* dst, int n) {
 __attribute__((target("avx2"))) unsigned pack_row_avx2(const int32_t* src, uint8_t* dst, int n) {
     __m256i acc = _mm256_setzero_si256();
     const __m256i perm = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    // the packed bytes are only read back by the DMA engine: write them around the cache when the row is 32-byte aligned
+    const bool stream = (((uintptr_t)dst) & 31u) == 0;
     int i = 0;
     for (; i + 32 <= n; i += 32) {
         const __m256i a = _mm256_loadu_si256((const __m256i*)(src + i)), b = _mm256_loadu_si256((const __m256i*)(src + i + 8));
@@ -36,8 +38,9 @@ __attribute__((target("avx2"))) unsigned pack_row_avx2(const int32_t* src, uint8
         const __m256i ab = _mm256_packus_epi32(_mm256_and_si256(a, _mm256_set1_epi32(255)), _mm256_and_si256(b, _mm256_set1_epi32(255)));
         const __m256i cd = _mm256_packus_epi32(_mm256_and_si256(c, _mm256_set1_epi32(255)), _mm256_and_si256(d, _mm256_set1_epi32(255)));
         const __m256i abcd = _mm256_permutevar8x32_epi32(_mm256_packus_epi16(ab, cd), perm);
-        _mm256_storeu_si256((__m256i*)(dst + i), abcd);
+        if (stream) _mm256_stream_si256((__m256i*)(dst + i), abcd); else _mm256_storeu_si256((__m256i*)(dst + i), abcd);
     }
+    if (stream) _mm_sfence();
     unsigned bad = 0;
     alignas(32) unsigned tmp[8];
     _mm256_store_si256((__m256i*)tmp, acc);
