@@ -747,7 +747,7 @@ extern "C" int yk_range1d(yk_ctx* c, int slot, int plane, uint8_t* idx, int idxC
     if ((s.d.w & 7) || (s.d.h & 7)) return YK_ERR_ARG;          // the reference's own domain (SURVEY.md hazard 11)
     int rc;
     if (!s.r2Valid) {
-        YkRun run; memset(&run, 0, sizeof run); run.rejectFactor = 3;      // no gradient pass: refresh segments, scan, code
+        YkRun run; memset(&run, 0, sizeof run); run.rejectFactor = 3;      // no gradient pass: code the unclaimed tiles, scan, gather
         if ((rc = enqueue(c, slot, 1, run, false, true))) return rc;
     }
     if ((rc = harvest(c, s))) return rc;

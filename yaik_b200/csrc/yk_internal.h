@@ -10,8 +10,8 @@
 #endif
 
 #define YK_NPASS 7
-#define YK_REGION 64            // one CTA analyses one 64x64 region = the largest swizzle block (YAIK_private.h:212-276)
-#define YK_THREADS 256
+#define YK_REGION 64            // the largest swizzle block (YAIK_private.h:212-276): regions tile the image, strips start on them
+#define YK_THREADS 256          // CTA size of the auxiliary kernels (state download, DynamicTileEncode)
 
 // Swizzle geometry of pass id p (HeaderGradientTile::getSwizzleSize, include/YAIK_private.h:212-276),
 // in Convert()'s order (EC.cpp:9057-9093): 16x16 16x8 8x16 8x8 8x4 4x8 4x4.
