@@ -160,6 +160,49 @@ def test_alternative_data_paths(lib):
         c.close()
 
 
+def test_repeatability_under_concurrency(lib):
+    """The persistent kernel's queue / barrier protocol under load: four contexts on four host threads analyse the same
+    1024x1024 textures over and over, with full and half-size analysis launches; every run must give the same streams."""
+    import hashlib, threading
+    imgs = [make_image(1024, 1024, 4, SEED_BASE + 40 + i) for i in range(2)]
+    st = capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D
+
+    def digest(c):
+        r = c.fetch_all(0, copy=True)
+        h = hashlib.sha1()
+        for p in r["passes"]:
+            h.update(p["bitmap"].tobytes()); h.update(p["rgb"].tobytes()); h.update(str((p["tiledone"], p["bbox"])).encode())
+        for q in r["r2"]:
+            h.update(q["idx"].tobytes()); h.update(q["type"].tobytes())
+        return h.hexdigest()
+
+    ref = []
+    c0 = capi.Context(1024, 1024, planes=4, slots=1, lib=lib)
+    for im in imgs:
+        c0.set_image(im); c0.analyze(st); ref.append(digest(c0))
+    c0.close()
+    errors = []
+
+    def worker(t):
+        c = capi.Context(1024, 1024, planes=4, slots=1, lib=lib)
+        try:
+            c.set_analysis_ctas(0 if t % 2 == 0 else c.sm_count() // 2)
+            c.set_upload_format(t < 2)
+            for it in range(40):
+                k = (it + t) % 2
+                c.set_image(imgs[k]); c.analyze(st)
+                if digest(c) != ref[k]:
+                    errors.append((t, it))
+        finally:
+            c.close()
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errors, errors
+
+
 # ---- tile-row strips of one large image (BASELINE.json configs[3], SURVEY.md 8e) --------------------------------
 @pytest.mark.parametrize("w,h,n", [(256, 512, 2), (256, 512, 4), (192, 328, 3), (2048, 1024, 4)])
 def test_strips_on_one_gpu_match_whole_image(lib, w, h, n):
