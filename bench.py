@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--e2e-threads", type=int, default=8, help="host threads (one context each) the end-to-end steps are pipelined over")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--streams", type=int, default=8, help="contexts/streams the steps are pipelined over (1, 2, 4 or 8)")
-    ap.add_argument("--analysis-ctas", type=int, default=-1, help="CTAs of the persistent analysis kernel in the pipelined region (-1: half the SMs when streams > 1, else one per SM)")
+    ap.add_argument("--analysis-ctas", type=int, default=-1, help="CTAs of the persistent analysis kernel in the pipelined region (-1: a quarter of the SMs with 8 streams, half with 2-4, else one per SM)")
     ap.add_argument("--roofline-steps", type=int, default=100, help="launches of the separate pass that times the dominant kernel alone")
     ap.add_argument("--no-prewarm", action="store_true", help="skip the clock-settling loop (profiling runs under ncu)")
     args = ap.parse_args()
@@ -212,9 +212,9 @@ def main():
         c.set_stream(st.cuda_stream)
         c.set_upload_format(False)     # `value` is measured on int32 planes resident in HBM (the reference's Plane representation)
     sms = ctxs[0].sm_count()
-    actas = args.analysis_ctas if args.analysis_ctas >= 0 else (sms // 2 if NCTX > 1 else 0)
+    actas = args.analysis_ctas if args.analysis_ctas >= 0 else (sms // 4 if NCTX >= 8 else (sms // 2 if NCTX > 1 else 0))
     for c in ctxs:
-        c.set_analysis_ctas(actas)     # two half-size launches of neighbouring steps run side by side: ramp and tail of one hide behind the other
+        c.set_analysis_ctas(actas)     # launches of neighbouring steps run side by side on disjoint SMs: ramp and tail of one hide behind the others
     ctx, stream = ctxs[0], streams[0]
 
     # two distinct textures per rank, uploaded alternately into the 8 slots (distinct HBM addresses are what defeats L2)
