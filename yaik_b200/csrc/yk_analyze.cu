@@ -76,6 +76,7 @@ struct YkaSlotC {
 #define YKA_NSTAT YK_HD_INTS                         // per-pass counters + alpha box / count, laid out like the image header
 
 struct YkaShared {
+    uint2    passLane[YK_NPASS][32];    // per pass and lane: lanes sharing its tile (x), packed geometry of the lane in that pass (y)
     uint32_t pretestTab[41];
     int      queueHead;             // next (unit sequence number * 8 + macro tile) to hand out
     int      endSeq;                // first unit sequence number that does not exist
@@ -173,6 +174,23 @@ static __device__ __forceinline__ unsigned yka_pack4(int4 v) {      // low bytes
     return __byte_perm(__byte_perm((unsigned)v.x, (unsigned)v.y, 0x0040), __byte_perm((unsigned)v.z, (unsigned)v.w, 0x0040), 0x5410);
 }
 static __device__ __forceinline__ int yka_byte(unsigned word, int k) { return (int)__byte_perm(word, 0u, 0x4440u | (unsigned)k); }
+
+// Lane geometry of one pass, computed once per CTA.  Lane (row = lane >> 1, half = lane & 1) owns the eight pixels
+// (8*half .. 8*half+7, row) of the macro tile in every pass.  y: lyT | dy << 5 | leader << 9 | lxT(sub 0) << 10 | dx0 << 14 |
+// t(sub 0) << 18 | lxT(sub 1) << 22 | t(sub 1) << 26   (sub 1 only for 4-pixel-wide tiles: the lane's right quad)
+static __device__ __forceinline__ uint2 yka_pass_lane_entry(int pid, int lane) {
+    const YkGeomS g = yk_geom_s(pid);
+    const int row = lane >> 1, half = lane & 1, shx = g.shx, shy = g.shy, TH = 1 << shy;
+    const int ty = row >> shy, lyT = ty << shy, dy = row - lyT;
+    const unsigned rowMask = (shy == 4) ? YK_FULL : (((1u << (2 * TH)) - 1u) << (2 * lyT));
+    const unsigned gmask = (shx == 4) ? rowMask : (rowMask & (0x55555555u << half));
+    const int leader = lane == __ffs((int)gmask) - 1;
+    const int tx0 = (shx == 2) ? (2 * half) : ((8 * half) >> shx), tx1 = 2 * half + 1;
+    const int lxT0 = tx0 << shx, lxT1 = tx1 << 2;
+    const int dx0 = (shx == 2) ? 0 : (8 * half - lxT0);
+    const int t0 = ty * (16 >> shx) + tx0, t1 = ty * 4 + tx1;
+    return make_uint2(gmask, (unsigned)(lyT | (dy << 5) | (leader << 9) | (lxT0 << 10) | (dx0 << 14) | (t0 << 18) | ((lxT1 & 15) << 22) | ((t1 & 15) << 26)));
+}
 
 // table entry of tile ti (0..40) of a macro tile: offX | offY << 4 | shx << 8 | shy << 11 | cell << 14
 static __device__ __forceinline__ uint32_t yka_pretest_entry(int ti) {
@@ -430,34 +448,31 @@ static __device__ __forceinline__ void yka_commit(YkaShared& sh, const YkaSlotC&
 static __device__ __forceinline__ unsigned yka_macro_pass(const uint8_t* __restrict__ priv, YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch,
                                                           int pid, int rp, int gmx, int gmy, unsigned claimed, unsigned poss, int rej) {
     const YkGeomS g = yk_geom_s(pid);
-    const int lane = threadIdx.x & 31, row = lane >> 1, half = lane & 1;
-    const int shx = g.shx, shy = g.shy, TH = 1 << shy;
-    const int ty = row >> shy, lyT = ty << shy;
-    const unsigned rowMask = (shy == 4) ? YK_FULL : (((1u << (2 * TH)) - 1u) << (2 * lyT));
-    const unsigned gmask = (shx == 4) ? rowMask : (rowMask & (0x55555555u << half));
-    const bool leader = lane == __ffs((int)gmask) - 1;
+    const int lane = threadIdx.x & 31;
+    const uint2 e = sh.passLane[pid][lane];
+    const int shx = g.shx, shy = g.shy;
+    const unsigned gmask = e.x;
+    const int lyT = e.y & 31;
+    const bool leader = (e.y >> 9) & 1u;
     const int nSub = (shx == 2) ? 2 : 1;
     YkaTile T;
-    T.shx = shx; T.shy = shy; T.sh = shx + shy; T.negN = -(1 << T.sh); T.dy = row - lyT; T.R = rej; T.two = shx != 2;
+    T.shx = shx; T.shy = shy; T.sh = shx + shy; T.negN = -(1 << T.sh); T.dy = (e.y >> 5) & 15; T.R = rej; T.two = shx != 2;
+    T.dx0 = (e.y >> 14) & 15;
     unsigned newCells = 0;
     for (int sub = 0; sub < nSub; sub++) {
-        const int tx = (shx == 2) ? (2 * half + sub) : ((8 * half) >> shx);
-        const int lxT = tx << shx;
-        T.dx0 = (shx == 2) ? 0 : (8 * half - lxT);
-        const int t = ty * (16 >> shx) + tx;
-        const int cellX = lxT >> 2, cellY = lyT >> 2;
-        const bool active = ((poss >> t) & 1u) && !((claimed >> (cellY * 4 + cellX)) & 1u);      // EC.cpp:3818, 3826, 3871-3875
+        const int lxT = (e.y >> (sub ? 22 : 10)) & 15, t = (e.y >> (sub ? 26 : 18)) & 15;
+        const bool active = (poss >> t) & 1u;               // eligible (EC.cpp:3818, 3826, 3871-3875) and not proven hopeless: see the caller
         if (!__any_sync(YK_FULL, active)) continue;
         uint2 pw[3];                                        // this lane's eight pixels of the macro tile, three channels
 #pragma unroll
-        for (int c = 0; c < 3; c++) pw[c] = *reinterpret_cast<const uint2*>(priv + c * YKP_CH + row * YKP_RS + 8 * half);
-        const bool acc = yka_tile_test(priv + lyT * YKP_RS + lxT, T, pw, shx == 2 && sub, gmask, active);
+        for (int c = 0; c < 3; c++) pw[c] = *reinterpret_cast<const uint2*>(priv + c * YKP_CH + (lane >> 1) * YKP_RS + 8 * (lane & 1));
+        const bool acc = yka_tile_test(priv + lyT * YKP_RS + lxT, T, pw, sub != 0, gmask, active);
         unsigned mine = 0;
         if (acc && leader) {
             yka_commit(sh, C, touch, g, pid, rp, gmx + lxT, gmy + lyT, lxT, lyT);
             // EC.cpp:4029-4037: the tile's cells become claimed
-            const unsigned cols = ((1u << (1 << (shx - 2))) - 1u) << cellX;
-            const unsigned rowsPat = (0x1111u & ((1u << (4 << (shy - 2))) - 1u)) << (4 * cellY);
+            const unsigned cols = ((1u << (1 << (shx - 2))) - 1u) << (lxT >> 2);
+            const unsigned rowsPat = (0x1111u & ((1u << (4 << (shy - 2))) - 1u)) << (lyT & ~3);
             mine = cols * rowsPat;
         }
         newCells |= __reduce_or_sync(YK_FULL, mine);
@@ -573,7 +588,10 @@ static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShare
                 const int pid = run.passId[rp];
                 if (pid != 0 && !pretested) { P = yka_pretest(priv, sh.pretestTab, wIn, hIn, claimed, rej); pretested = true; }
                 const YkGeomS g = yk_geom_s(pid);
-                const unsigned poss = (unsigned)(P >> g.start) & ((1u << (256 >> (g.shx + g.shy))) - 1u);
+                // tiles of this shape that are possible and whose top-left cell is still unclaimed (EC.cpp:3871-3875): lane = tile
+                bool freeTile = false;
+                if (lane < (256 >> (g.shx + g.shy))) freeTile = !((claimed >> (sh.pretestTab[g.start + lane] >> 14)) & 1u);
+                const unsigned poss = (unsigned)(P >> g.start) & __ballot_sync(YK_FULL, freeTile);
                 if (poss) claimed = yka_macro_pass(priv, sh, C, touch, pid, rp, gmx, gmy, claimed, poss, rej);
             }
             // EC.cpp:4029-4037: newly claimed cells
@@ -656,6 +674,7 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
     if (tid < 256) sMagic[tid] = tid ? ((1u << 20) + (unsigned)tid - 1u) / (unsigned)tid : 0u;
     __syncthreads();
     if (tid < 41) sh.pretestTab[tid] = yka_pretest_entry(tid);
+    if (tid >= 128 && tid < 128 + YK_NPASS * 32) sh.passLane[(tid - 128) >> 5][(tid - 128) & 31] = yka_pass_lane_entry((tid - 128) >> 5, (tid - 128) & 31);
     if (tid >= 64 && tid < 64 + YKA_CONS_WARPS) sh.slotc[tid - 64].slot = -1;
     if (tid == 96) {
         sh.run = runArg;
