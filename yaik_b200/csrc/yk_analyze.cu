@@ -695,7 +695,11 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         int* ticket = slots[slot0].hdr + YK_HD_TICKET_ANALYZE;
         const bool wantAlpha = run.doAlpha != 0;
         // tickets: lane 0 holds YKA_TICKETS tickets in separate registers (the loop is unrolled by that many units), each
-        // fetched YKA_TICKETS units ahead, so that the latency of the global atomic is never on the path of a unit
+        // fetched YKA_TICKETS units ahead, so that the latency of the global atomic is never on the path of a unit.
+        // Towards the end of the launch (fewer than `endgame` units left) tickets are taken only when they are needed and
+        // the look-ahead shrinks to one unit, so that the last units go to whichever CTA is free.
+        const int endgame = total - run.endgameUnits * (int)gridDim.x;
+        bool lazy = false;
         int tk[YKA_TICKETS];
         // of the image the current unit belongs to (kept in registers while the slot does not change)
         int curSlot = -1, alpha = 0;
@@ -710,13 +714,15 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
             for (int r = 0; r < YKA_TICKETS; r++) {
                 const int u = u0 + r, i = u % YKA_NR;
                 // never more than YKA_LOOKAHEAD units ahead of the consumers: the CTAs then run out of work together
-                while (u - (yka_flag_ld(&sh.queueHead) >> 3) > YKA_LOOKAHEAD) yk_spin();
+                while (u - (yka_flag_ld(&sh.queueHead) >> 3) > (lazy ? 1 : YKA_LOOKAHEAD)) yk_spin();
                 if (u >= YKA_NR) yka_mbar_wait(&sh.rawFree[i], (unsigned)((u / YKA_NR - 1) & 1));
                 if (lane == 0) YKT(0);
+                if (lane == 0 && tk[r] < 0) tk[r] = atomicAdd(ticket, 1);               // endgame: taken on demand
                 const int item = __shfl_sync(YK_FULL, tk[r], 0);
                 if (lane == 0) YKT(6);
                 if (item >= total) { if (lane == 0) yka_flag_st(&sh.endSeq, u); return; }
-                if (lane == 0) tk[r] = atomicAdd(ticket, 1);            // not looked at before the unit that uses it
+                lazy = item >= endgame;
+                if (lane == 0) tk[r] = lazy ? -1 : (int)atomicAdd(ticket, 1);          // not looked at before the unit that uses it
                 if (lane == 0) YKT(7);
                 int slot = slot0, rem = item;
                 if (nSlots > 1) { const int q = item / unitsPerSlot; slot += q; rem -= q * unitsPerSlot; }

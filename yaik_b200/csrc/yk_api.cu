@@ -530,6 +530,9 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     YkRun krun = run;
     krun.doR2 = r2Domain ? 1 : 0;
     krun.fresh = fresh ? 1 : 0;
+    // a launch that has the GPU to itself balances its tail by taking its last units on demand; a partial launch runs
+    // beside others (pipelined contexts) which fill its tail anyway
+    krun.endgameUnits = c->analysisCtas >= c->numSMs ? 6 : 0;
     if ((phases & 1) && (krun.nPasses > 0 || krun.doAlpha || krun.doR2)) {
         YkTimed t(c, 0);
         yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, c->analysisCtas, a.d.isU8 != 0, krun, c->stream); c->launches++;

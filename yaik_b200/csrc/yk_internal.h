@@ -93,6 +93,7 @@ struct YkRun {
     int rejectFactor;
     int doAlpha;
     int doR2;                   // code the DynamicTileCompressor tiles of every region after its cascade
+    int endgameUnits;           // units per CTA at the end of a launch that are taken on demand instead of ahead (load balance of the tail)
     int fresh;                  // no cell is claimed yet (first gradient launch after yk_reset_state): cellMask need not be read
 };
 
