@@ -160,6 +160,18 @@ def test_alternative_data_paths(lib):
         c.close()
 
 
+@pytest.mark.parametrize("i", range(64))
+def test_random_shapes_match_oracle(ctx, i):
+    """Randomised sizes (any multiple of 4 up to 192 x 160) and contents, both upload formats, fused and stage by stage."""
+    from test_random_shapes_emulated import _case
+    planes, stages = _case(i)
+    ctx.set_upload_format(i % 2 == 0)
+    try:
+        check_image(ctx, planes, stages, fused=(i % 3 != 0))
+    finally:
+        ctx.set_upload_format(True)
+
+
 def test_repeatability_under_concurrency(lib):
     """The persistent kernel's queue / barrier protocol under load: four contexts on four host threads analyse the same
     1024x1024 textures over and over, with full and half-size analysis launches; every run must give the same streams."""
