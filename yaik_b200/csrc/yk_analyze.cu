@@ -224,6 +224,22 @@ static __device__ void yka_slot_refresh(const YkSlotDev& S, YkaSlotC& C, int slo
     __syncwarp();
 }
 
+// all(alpha == 0) of the 16x16 tile of macro tile mx, from the staged alpha rows (samples outside the image arrive as zeros)
+template <bool U8>
+static __device__ __forceinline__ bool yka_alpha_any(const void* __restrict__ rawv, int mx) {
+    const int lane = threadIdx.x & 31;
+    bool nz;
+    if (U8) {
+        const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(rawv) + 3 * YKA_RAWB_PLANE + (lane >> 1) * YK_UNIT_W + 16 * mx + 8 * (lane & 1));
+        nz = (v.x | v.y) != 0u;
+    } else {
+        const int4* __restrict__ a = reinterpret_cast<const int4*>(reinterpret_cast<const int32_t*>(rawv) + 3 * YKA_RAW_PLANE_INTS) + 4 * mx;
+        const int4 v0 = a[(lane >> 2) * (YK_UNIT_W / 4) + (lane & 3)], v1 = a[((lane >> 2) + 8) * (YK_UNIT_W / 4) + (lane & 3)];
+        nz = (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0;
+    }
+    return __any_sync(YK_FULL, nz);
+}
+
 // Consumer warp: the 17x17 samples of macro tile mx (0..7) of the unit whose left edge is X0, three colour planes, from the raw rows
 // staged by TMA (int32 samples, or bytes when the image was uploaded packed) into the warp-private byte tile, clamped
 // the way Plane::GetPixelValue clamps (framework.h:116-121); then the alpha-zero test of the 16x16 tile (EC.cpp:357-430
@@ -282,19 +298,7 @@ static __device__ __forceinline__ bool yka_pack_macro_tile(const void* __restric
     }
     if (bad & ~255u) atomicOr(&C.hdr[YK_HD_ERR], 1);
     bool kept = false;
-    if (doAlpha) {
-        // samples outside the image arrive as zeros
-        bool nz;
-        if (U8) {
-            const uint2 v = *reinterpret_cast<const uint2*>(rawb + 3 * YKA_RAWB_PLANE + (lane >> 1) * YK_UNIT_W + 16 * mx + 8 * (lane & 1));
-            nz = (v.x | v.y) != 0u;
-        } else {
-            const int4* __restrict__ a = reinterpret_cast<const int4*>(raw + 3 * YKA_RAW_PLANE_INTS) + 4 * mx;
-            const int4 v0 = a[(lane >> 2) * (YK_UNIT_W / 4) + (lane & 3)], v1 = a[((lane >> 2) + 8) * (YK_UNIT_W / 4) + (lane & 3)];
-            nz = (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0;
-        }
-        kept = __any_sync(YK_FULL, nz);
-    }
+    if (doAlpha) kept = yka_alpha_any<U8>(rawv, mx);
     return kept;
 }
 
@@ -549,10 +553,73 @@ static __device__ __forceinline__ void yka_range_tile(const uint8_t* __restrict_
     __syncwarp();       // the histogram entries are clean again before the next tile fills them
 }
 
+// The 16x16 pass of an interior macro tile straight from the raw rows, before anything is packed: about half of all macro
+// tiles of illustration-like content are accepted here by the raw-corner family, and for those the byte tile is never
+// built (compile-time tile size, no per-pass set-up).  Returns 1 = accepted (all side effects done, the macro tile is
+// finished), 2 = proven hopeless for every variant (the cascade can skip the 16x16 pass), 0 = undecided (the cascade
+// repeats the pass with all three families).  Only used on a fresh state with the 16x16 pass first.
+template <bool U8>
+static __device__ __forceinline__ int yka_pass16_raw(const void* __restrict__ rawv, YkaShared& sh, const YkaSlotC& C, int gmx, int gmy, int mx, int R) {
+    const int lane = threadIdx.x & 31, row = lane >> 1, half = lane & 1;
+    constexpr int N = 256;
+    const int hiT = (2 * R + 1) * N, loR = -(N / 2 - 1), loWide = -(4 * N + N / 2 - 1), hiWide = hiT + 3 * N;
+    int umin = INT_MAX, umax = INT_MIN;
+    unsigned bad = 0;
+    int corner[3];                                       // TL of each channel (what the macro tile's own lattice point emits)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        int tl, tr, bl, br, v[8];
+        if (U8) {
+            const uint8_t* p = reinterpret_cast<const uint8_t*>(rawv) + c * YKA_RAWB_PLANE + 16 * mx;
+            tl = p[0]; tr = p[16]; bl = p[16 * YK_U8_BOX]; br = p[16 * YK_U8_BOX + 16];
+            const uint2 w = *reinterpret_cast<const uint2*>(p + row * YK_U8_BOX + 8 * half);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { v[k] = yka_byte(w.x, k); v[4 + k] = yka_byte(w.y, k); }
+        } else {
+            const int32_t* p = reinterpret_cast<const int32_t*>(rawv) + c * YKA_RAW_PLANE_INTS + 16 * mx;
+            tl = p[0]; tr = p[16]; bl = p[16 * YK_RAW_PITCH]; br = p[16 * YK_RAW_PITCH + 16];
+            const int4 a = *reinterpret_cast<const int4*>(p + row * YK_RAW_PITCH + 8 * half), b = *reinterpret_cast<const int4*>(p + row * YK_RAW_PITCH + 8 * half + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            bad |= (unsigned)(a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w | tr | bl | br);
+        }
+        corner[c] = tl;
+        const int B = (tr - tl) * 16, Cc = (bl - tl) * 16, D = tl - tr - bl + br;
+        const int step = B + D * row;
+        int sk = (tl + R) * N + B * (8 * half) + row * (Cc + D * (8 * half));
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const int u0 = sk - v[k] * N, u1 = sk + step - v[k + 1] * N;
+            umin = __vimin3_s32(umin, u0, u1); umax = __vimax3_s32(umax, u0, u1);
+            sk += 2 * step;
+        }
+        if (c == 0 && __any_sync(YK_FULL, (umin < loWide) || (umax >= hiWide))) return 2;     // warp-uniform
+    }
+    if (bad & ~255u) atomicOr(&C.hdr[YK_HD_ERR], 1);
+    const bool dT = __any_sync(YK_FULL, (umin < 0) || (umax >= hiT));
+    const bool dR = __any_sync(YK_FULL, (umin < loR) || (umax >= hiT + loR));
+    if (dT && dR) return __any_sync(YK_FULL, (umin < loWide) || (umax >= hiWide)) ? 2 : 0;
+    // ---- accepted (EC.cpp:3998-4132): bitmap bit, counters, claimed cells, the four touched lattice points, corner colours
+    const YkGeomS g = yk_geom_s(0);
+    if (lane == 0) {
+        const int nSwzX = (C.w + 63) >> 6;
+        const int pos = yk_pos_s(g, nSwzX, gmx >> 4, gmy >> 4);
+        atomicOr(&C.bitmap32[0][pos >> 5], 1u << (pos & 31));
+        yka_stat5(sh, C, YK_HD_PASS0, 1, C.w - gmx, INT_MAX / 2 - (C.yOrg + gmy), gmx + 16, C.yOrg + gmy + 16);
+    }
+    const int cx0 = gmx >> 2, cy0 = gmy >> 2;
+    if (lane < 4) {
+        const int e = (cy0 + lane) * C.nbx + (cx0 >> 4);
+        atomicOr(&C.cellMask32[e >> 1], 15u << (16 * (e & 1) + (cx0 & 15)));
+        // pass position 0: corner role k of the tile at its lattice point k (TL, TR, BL, BR)
+        atomicOr(&C.touchMap[(size_t)(cy0 + 4 * (lane >> 1)) * C.latW + cx0 + 4 * (lane & 1)], 1u << lane);
+    }
+    return 1;
+}
+
 // One macro tile after its pixels have been packed: the cascade of Convert()'s passes (EC.cpp:9057-9093), its results,
 // the corner colours of its lattice points, then the range stage.  (gmx, gmy) = origin of the macro tile in the image.
 static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch, uint8_t* hist,
-                                      const uint32_t* magicTab, int gmx, int gmy) {
+                                      const uint32_t* magicTab, int gmx, int gmy, bool pass16Hopeless) {
     const int lane = threadIdx.x & 31;
     const YkRun& run = sh.run;
     const int wIn = C.w - gmx, hIn = C.h - gmy;              // image extent seen from the macro tile's origin
@@ -581,12 +648,15 @@ static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShare
         if (claimed != 0xFFFFu) {
             // the 16x16 pass usually runs first and straight away (most macro tiles of illustration-like content end there);
             // the other shapes are pre-tested together, once, the first time one of them comes up
-            unsigned long long P = (wIn >= 16 && hIn >= 16) ? 1ull : 0ull;
+            unsigned long long P = (wIn >= 16 && hIn >= 16 && !pass16Hopeless) ? 1ull : 0ull;
             bool pretested = false;
             const int rej = run.rejectFactor;
             for (int rp = 0; rp < nPasses && claimed != 0xFFFFu; rp++) {
                 const int pid = run.passId[rp];
-                if (pid != 0 && !pretested) { P = yka_pretest(priv, sh.pretestTab, wIn, hIn, claimed, rej); pretested = true; }
+                if (pid != 0 && !pretested) {
+                    P = yka_pretest(priv, sh.pretestTab, wIn, hIn, claimed, rej); pretested = true;
+                    if (pass16Hopeless) P &= ~1ull;
+                }
                 const YkGeomS g = yk_geom_s(pid);
                 // tiles of this shape that are possible and whose top-left cell is still unclaimed (EC.cpp:3871-3875): lane = tile
                 bool freeTile = false;
@@ -784,11 +854,33 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         __syncwarp();                                       // every lane has read the cached id before lane 0 may rewrite it
         if (cachedSlot != U.slot) yka_slot_refresh(slots[U.slot], C, U.slot);
         const int X0 = U.bx * 64, Yk = U.by * 64 + 16 * U.k;
-        const bool kept = yka_pack_macro_tile<U8>(raw + i * STAGE_BYTES, priv, C, X0, Yk, mx, U.alpha != 0);
+        const int gmx = X0 + 16 * mx;
+        const unsigned char* rawU = raw + i * STAGE_BYTES;
+        // fresh state, 16x16 pass first, interior macro tile: try that pass straight from the raw rows
+        int fast = 0;
+        if (run.fresh && run.nPasses > 0 && run.passId[0] == 0 && gmx + 20 <= C.w && Yk + YK_RAW_ROWS <= C.h)
+            fast = yka_pass16_raw<U8>(rawU, sh, C, gmx, Yk, mx, run.rejectFactor);
+        bool kept;
+        if (fast == 1) {
+            // accepted: the macro tile is finished without a byte tile; alpha test and the corner colours of its 4x4
+            // lattice points (EC.cpp:4115-4132) come from the raw rows
+            kept = U.alpha ? yka_alpha_any<U8>(rawU, mx) : false;
+            if (lane < 16) {
+                const int li = lane & 3, lj = lane >> 2;
+                uint8_t* d = C.latRGB + ((size_t)((Yk >> 2) + lj) * C.latW + (gmx >> 2) + li) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const int v = U8 ? (int)rawU[c * YKA_RAWB_PLANE + 4 * lj * YK_U8_BOX + 16 * mx + 4 * li]
+                                     : reinterpret_cast<const int32_t*>(rawU)[c * YKA_RAW_PLANE_INTS + 4 * lj * YK_RAW_PITCH + 16 * mx + 4 * li];
+                    d[c] = (uint8_t)yk_compress250(yk_round6(v & 255));
+                }
+            }
+        } else {
+            kept = yka_pack_macro_tile<U8>(rawU, priv, C, X0, Yk, mx, U.alpha != 0);
+        }
         __syncwarp();
         if (lane == 0) yka_mbar_arrive(&sh.rawFree[i]);      // this warp is done with the raw rows
         if (tid == 32) YKT(9);
-        const int gmx = X0 + 16 * mx;
         if (gmx >= C.w) continue;                            // the unit's second region does not exist (odd number of region columns)
         if (U.alpha && Yk < C.h && lane == 0) {
             C.alphaKept[(size_t)(Yk >> 4) * ((C.w + 15) >> 4) + (gmx >> 4)] = kept ? 1 : 0;
@@ -797,7 +889,8 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
                 yka_stat5(sh, C, YK_HD_ALPHA_KEPT0, 1, C.w - gmx, INT_MAX / 2 - (C.yOrg + Yk), min(gmx + 16, C.w), C.yOrg + min(Yk + 16, C.h));
             }
         }
-        yka_macro_tile(priv, sh, C, touch, hist, sMagic, gmx, Yk);
+        if (fast == 1) continue;
+        yka_macro_tile(priv, sh, C, touch, hist, sMagic, gmx, Yk, fast == 2);
         __syncwarp();
         if (tid == 32) YKT(10);
     }
