@@ -497,22 +497,18 @@ static __device__ __forceinline__ void yka_range_tile(const uint8_t* __restrict_
     const int lengthX = (qb == 3u) ? 8 : 4, x2 = (qb == 2u) ? 4 : 0;
     const int pos = (band ? 16 * __popc(q & 3u) : 0) + (r & 3) * lengthX + (c0 - x2);
     int vx[3], vy[3];
-    unsigned mxA[3], mxB[3];
+    // FindAndRemoveMostUsedColor (EC.cpp:8335-8356): per-value counts in a byte histogram (four 8-bit counters per word,
+    // a tile has at most 64 pixels), filled with shared-memory atomics
+    uint32_t* hist32 = reinterpret_cast<uint32_t*>(hist);
 #pragma unroll
     for (int p = 0; p < 3; p++) {
         const unsigned short two = *reinterpret_cast<const unsigned short*>(priv + p * YKP_CH + (ly8 + r) * YKP_RS + lx8 + c0);
         vx[p] = two & 255; vy[p] = two >> 8;                 // CompressF(v,255) == v (EC.cpp:8442)
-        // FindAndRemoveMostUsedColor (EC.cpp:8335-8356): counts per present value from two match rounds
-        mxA[p] = __match_any_sync(YK_FULL, valid ? vx[p] : 256 + lane);
-        mxB[p] = __match_any_sync(YK_FULL, valid ? vy[p] : 512 + lane);
+        if (valid) {
+            atomicAdd(&hist32[p * 64 + (vx[p] >> 2)], 1u << (8 * (vx[p] & 3)));
+            atomicAdd(&hist32[p * 64 + (vy[p] >> 2)], 1u << (8 * (vy[p] & 3)));
+        }
     }
-#pragma unroll
-    for (int p = 0; p < 3; p++)
-        if (valid && lane == __ffs((int)mxA[p]) - 1) hist[p * 256 + vx[p]] = (uint8_t)__popc(mxA[p]);
-    __syncwarp();
-#pragma unroll
-    for (int p = 0; p < 3; p++)
-        if (valid && lane == __ffs((int)mxB[p]) - 1) hist[p * 256 + vy[p]] = (uint8_t)(hist[p * 256 + vy[p]] + __popc(mxB[p]));
     __syncwarp();
     unsigned key[3];
 #pragma unroll
