@@ -82,6 +82,7 @@ int  yk_set_image_device(yk_ctx* ctx, int slot, const int32_t* const* devPlanes,
 /* Device pointer of plane `p` of `slot` (so a caller can fill it in place); NULL on error. */
 int32_t* yk_device_plane(yk_ctx* ctx, int slot, int p);
 int  yk_reset_state(yk_ctx* ctx, int slot);
+int  yk_reset_states(yk_ctx* ctx, int slot0, int nSlots);     /* the same for a batch of slots, one clear */
 
 /* ---- the fused hot path -------------------------------------------------------------------------------
  * Runs, for slots [slot0, slot0+nSlots) (all the same size), on the device, leaving results in HBM:

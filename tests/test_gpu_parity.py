@@ -67,6 +67,14 @@ def test_batch_equals_single(lib):
         for i, im in enumerate(imgs):
             cb.set_image(im, i)
         cb.analyze(capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D, slot0=0, n_slots=4)
+        first = [cb.gradient_pass(4, 4, slot=i) for i in range(4)]
+        cb.reset_states(0, 4)                                    # a second batch on the same slots after one batched reset
+        cb.analyze(capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D, slot0=0, n_slots=4)
+        for i in range(4):
+            again = cb.gradient_pass(4, 4, slot=i)
+            assert np.array_equal(again["bitmap"], first[i]["bitmap"]) and np.array_equal(again["rgb"], first[i]["rgb"])
+        cb.reset_states(0, 4)
+        cb.analyze(capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D, slot0=0, n_slots=4)
         for i, im in enumerate(imgs):
             cs.set_image(im, 0)
             cs.analyze(capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D)

@@ -22,7 +22,7 @@ STAGE_ALPHA, STAGE_GRADIENT, STAGE_RANGE1D, STAGE_RANGEDYN, STAGE_RANGEDYN3 = 1,
 EXPORTS = [
     "yk_abi_version", "yk_error_string", "yk_last_cuda_error", "yk_device_count", "yk_create", "yk_destroy",
     "yk_set_stream", "yk_sync", "yk_set_analysis_ctas", "yk_sm_count", "yk_host_alloc", "yk_host_free", "yk_set_image", "yk_set_image_device", "yk_set_upload_format",
-    "yk_device_plane", "yk_reset_state", "yk_analyze", "yk_alpha_reject", "yk_prepare_quad_smooth",
+    "yk_device_plane", "yk_reset_state", "yk_reset_states", "yk_analyze", "yk_alpha_reject", "yk_prepare_quad_smooth",
     "yk_gradient_pass", "yk_range1d", "yk_range_dyn", "yk_download_state", "yk_fetch_all", "yk_result_bytes", "yk_launch_count",
     "yk_profile", "yk_profile_read",
     "yk_strip_config", "yk_strip_halo_ptrs", "yk_strip_phase",
@@ -85,6 +85,7 @@ def load_library(path: str | None = None):
     L.yk_set_image_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
     L.yk_reset_state.argtypes = [C.c_void_p, C.c_int]
     L.yk_set_upload_format.argtypes = [C.c_void_p, C.c_int]
+    L.yk_reset_states.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.yk_analyze.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.yk_prepare_quad_smooth.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.yk_alpha_reject.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -177,6 +178,9 @@ class Context:
 
     def reset_state(self, slot=0):
         self._ck(self.L.yk_reset_state(self.ctx, slot), "yk_reset_state")
+
+    def reset_states(self, slot0, n_slots):
+        self._ck(self.L.yk_reset_states(self.ctx, slot0, n_slots), "yk_reset_states")
 
     def analyze(self, stages, slot0=0, n_slots=1, reject=3):
         self._ck(self.L.yk_analyze(self.ctx, slot0, n_slots, stages, reject), "yk_analyze")

@@ -350,18 +350,32 @@ static int configure_slot(yk_ctx* c, int slot, int nPlanes, int w, int h) {
     return YK_OK;
 }
 
-extern "C" int yk_reset_state(yk_ctx* c, int slot) {
-    if (!slot_ok(c, slot)) return YK_ERR_ARG;
-    YkSlotHost& s = c->slots[slot];
-    if (!s.haveImage) return YK_ERR_STATE;
-    CK(cudaSetDevice(c->device));
-    CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * slot, 0, c->zeroStride, c->stream));
+static void mark_reset(YkSlotHost& s) {
     s.zeroAClean = true; s.touchDirty = false; s.cellsClean = true; s.harvested = false;
     if (s.d.alphaReset || s.d.alphaValid) s.dirty = true;
     s.d.alphaReset = 0; s.d.alphaValid = 0;
     s.k1Ran = s.alphaRan = s.alphaFetched = s.prepared = s.r2Valid = s.pendingHarvest = false;
     s.nextPass = 0; s.rangeErr = 0; s.lastRunPasses = 0;
     memset(s.hdr, 0, sizeof s.hdr);
+}
+
+extern "C" int yk_reset_state(yk_ctx* c, int slot) {
+    if (!slot_ok(c, slot)) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * slot, 0, c->zeroStride, c->stream));
+    mark_reset(s);
+    return YK_OK;
+}
+
+// the same for slots [slot0, slot0 + nSlots) with one clear (their state areas are contiguous)
+extern "C" int yk_reset_states(yk_ctx* c, int slot0, int nSlots) {
+    if (!c || nSlots < 1 || slot0 < 0 || slot0 + nSlots > c->maxSlots) return YK_ERR_ARG;
+    for (int i = slot0; i < slot0 + nSlots; i++) if (!c->slots[i].haveImage) return YK_ERR_STATE;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->zeroArea + c->zeroStride * slot0, 0, c->zeroStride * nSlots, c->stream));
+    for (int i = slot0; i < slot0 + nSlots; i++) mark_reset(c->slots[i]);
     return YK_OK;
 }
 
