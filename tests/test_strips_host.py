@@ -51,6 +51,26 @@ def test_strips_local_transport_matches_whole_image(emu_lib, name, w, h, n):
             c.close()
 
 
+@pytest.mark.parametrize("i", range(6))
+def test_strips_random_shapes(emu_lib, i):
+    """Random widths (any multiple of 8, odd region counts included), heights and strip counts, both upload formats."""
+    from yaik_b200.synth import _rand
+    r = _rand(4242, i, np.arange(6, dtype=np.uint64))
+    w = 8 * (2 + int(r[0] % np.uint64(22)))              # 16 .. 184
+    h = 8 * (9 + int(r[1] % np.uint64(24)))              # 72 .. 256 (at least two 64-row blocks)
+    n = 2 + int(r[2] % np.uint64(3))
+    planes = cases._patchy(w, h, 500 + i, 4, 1 + int(r[3] % np.uint64(4)))
+    ctxs = [capi.Context(w, h, planes=3, slots=1, lib=emu_lib) for _ in range(n)]
+    try:
+        for c in ctxs:
+            c.set_upload_format(i % 2 == 0)
+        merged = strips.LocalTransport(ctxs).run(planes, n_strips=n)
+        check_against_oracle(merged, planes)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_strips_two_gloo_ranks_host_transport(emu_lib, tmp_path):
     """world_size 2, one strip per rank, exchanges staged through host memory and sent point to point over gloo."""
     script = os.path.join(ROOT, "tests", "strips_rank.py")
