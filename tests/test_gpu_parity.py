@@ -180,6 +180,25 @@ def test_random_shapes_match_oracle(ctx, i):
         ctx.set_upload_format(True)
 
 
+@pytest.mark.parametrize("w,h,ch,seed", [(2048, 2048, 4, SEED_BASE + 1), (4096, 4096, 3, SEED_BASE + 3)])
+def test_streams_decode_with_the_reference_decoders_corner_rule(lib, w, h, ch, seed):
+    """Size-independent property at BASELINE sizes (configs[1]; a 4096x4096 crop-equivalent of configs[3]): replaying the
+    reference decoder's corner consumption (decoder/YAIK_Gradient.cpp) over the emitted bitmaps reads every rgbStream to
+    its last byte, gives every touched lattice point the source pixel's colour, and touches exactly the points the encoder
+    marked in mappedRGB."""
+    import decoder_walk
+    planes = make_image(w, h, ch, seed)
+    c = capi.Context(w, h, planes=ch, slots=1, lib=lib)
+    try:
+        c.set_image(planes)
+        c.analyze((capi.STAGE_ALPHA if ch == 4 else 0) | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D)
+        passes = [c.gradient_pass(sx, sy) for sx, sy in capi.PASS_ORDER]
+        n = decoder_walk.check(planes, passes, c.download_state(recon=False)["mappedRGB"][0])
+        assert n > 1000
+    finally:
+        c.close()
+
+
 def test_repeatability_under_concurrency(lib):
     """The persistent kernel's queue / barrier protocol under load: four contexts on four host threads analyse the same
     1024x1024 textures over and over, with full and half-size analysis launches; every run must give the same streams."""
