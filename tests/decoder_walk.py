@@ -62,3 +62,57 @@ def check(planes, passes, mapped_rgb=None):
         m = np.asarray(mapped_rgb).reshape(h + 1, w + 1)[::4, ::4] != 0
         assert np.array_equal(m, has), "decoder's coloured lattice points differ from the encoder's mappedRGB"
     return int(has.sum())
+
+
+# ---- range stage: Decompress1D (decoder/YAIK_3DTile.cpp:24-240) ---------------------------------------------------
+def walk_range1d(w, h, cell_claimed, idx, typ, range_compression=15):
+    """Replays the decoder's consumption of one plane's DynamicTileCompressor streams.  cell_claimed: bool [h/4][w/4]
+    (== smoothMap != 0 sampled per 4x4 cell).  Tiles in row-major order; a tile with an unclaimed quadrant reads
+    {color0, base, delta} and then, band by band, row by row, the index bytes of its unclaimed quadrants (the decoder's
+    switch on patternQuad & 3).  Returns the decoded plane (-1 where nothing is decoded), the per-pixel delta of the tile
+    and the number of coded tiles."""
+    idx = np.asarray(idx, np.uint8); typ = np.asarray(typ, np.uint8)
+    out = np.full((h, w), -1, np.int32)
+    dmap = np.zeros((h, w), np.int32)
+    inv = (1 << 24) // range_compression
+    ri = rt = 0
+    tiles = 0
+    for ty in range(h // 8):
+        for tx in range(w // 8):
+            q = cell_claimed[2 * ty:2 * ty + 2, 2 * tx:2 * tx + 2]
+            if q.all():
+                continue
+            assert rt + 3 <= typ.size, "type stream too short"
+            color0, base, delta = (int(v) for v in typ[rt:rt + 3]); rt += 3
+            delta2 = ((delta * inv) >> 8) + 1
+            tiles += 1
+            dmap[8 * ty:8 * ty + 8, 8 * tx:8 * tx + 8] = delta
+            for band in range(2):
+                left, right = not q[band, 0], not q[band, 1]
+                if not (left or right):
+                    continue
+                x0, x1 = (0 if left else 4), (8 if right else 4)
+                for r in range(4):
+                    n = x1 - x0
+                    L = idx[ri:ri + n].astype(np.int32); ri += n
+                    assert L.size == n, "index stream too short"
+                    out[8 * ty + 4 * band + r, 8 * tx + x0:8 * tx + x1] = np.where(L != 0, base + (((L - 1) * delta2) >> 16), color0)
+    assert ri == idx.size, f"{idx.size - ri} index bytes are never read by the decoder"
+    assert rt == typ.size, f"{typ.size - rt} type bytes are never read by the decoder"
+    return out, dmap, tiles
+
+
+def check_range1d(plane, cell_claimed, idx, typ):
+    """Consumption (every index and type byte is read, exactly the unclaimed cells are decoded) plus a closeness bound of
+    the decoded samples: within one quantisation step (delta / 15) plus the rounding of Model1 / the decoder's fixed point.
+    Tiles with delta <= 1 are left out of the bound (the reference's index -1 quirk, SURVEY.md hazard 9)."""
+    h, w = plane.shape
+    dec, dmap, tiles = walk_range1d(w, h, cell_claimed, idx, typ)
+    coded = dec >= 0
+    unclaimed_px = ~np.repeat(np.repeat(np.asarray(cell_claimed, bool), 4, 0), 4, 1)[:h, :w]
+    assert np.array_equal(coded, unclaimed_px), "decoded pixels are not exactly the unclaimed cells"
+    sel = coded & (dmap >= 2)
+    err = np.abs(dec - plane.astype(np.int32))
+    bound = (dmap + 14) // 15 + 2
+    assert (err[sel] <= bound[sel]).all(), ("range-stage round trip too far off", int(err[sel].max()))
+    return tiles

@@ -44,3 +44,18 @@ def test_emulated_kernel_streams_decode(emu_lib, name):
         decoder_walk.check(planes, passes, ctx.download_state(recon=False)["mappedRGB"][0])
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("name", ["synth128_rgb", "patchy_192x136", "noise_lowamp96", "noise_delta1", "noise_hi"])
+def test_oracle_range_streams_decode(name):
+    """DynamicTileCompressor's streams through the reference decoder's consumption rule (Decompress1D)."""
+    planes, _ = cases.SMALL_CASES[name]()
+    c, h, w = planes.shape
+    o = Oracle(planes)
+    for sx, sy in PASS_ORDER:
+        o.gradient_pass(sx, sy)
+    claimed = o.state(0).reshape(h, w)[::4, ::4] != 0
+    for n in range(3):
+        r = o.range1d(n)
+        decoder_walk.check_range1d(planes[n], claimed, r["idx"], r["type"])
+    o.close()

@@ -193,8 +193,14 @@ def test_streams_decode_with_the_reference_decoders_corner_rule(lib, w, h, ch, s
         c.set_image(planes)
         c.analyze((capi.STAGE_ALPHA if ch == 4 else 0) | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D)
         passes = [c.gradient_pass(sx, sy) for sx, sy in capi.PASS_ORDER]
-        n = decoder_walk.check(planes, passes, c.download_state(recon=False)["mappedRGB"][0])
+        st = c.download_state(recon=False)
+        n = decoder_walk.check(planes, passes, st["mappedRGB"][0])
         assert n > 1000
+        # the range stage's streams through Decompress1D's consumption rule (decoder/YAIK_3DTile.cpp:24-240)
+        claimed = st["smoothMap"][::4, ::4] != 0
+        for pl in range(3):
+            r = c.range1d(pl)
+            assert decoder_walk.check_range1d(planes[pl], claimed, r["idx"], r["type"]) > 100
     finally:
         c.close()
 
