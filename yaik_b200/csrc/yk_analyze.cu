@@ -612,12 +612,26 @@ static __device__ __forceinline__ int yka_pass16_raw(const void* __restrict__ ra
     return 1;
 }
 
+#ifdef YK_TIMING
+__device__ unsigned long long yk_timing[16];
+#define YKT_DECL long long t__ = clock64(), t2__
+#define YKT(i) (t2__ = clock64(), atomicAdd(&yk_timing[i], (unsigned long long)(t2__ - t__)), t__ = t2__)
+extern "C" void yk_debug_timing(unsigned long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, yk_timing, sizeof(yk_timing));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(yk_timing, z, sizeof(z)); }
+}
+#else
+#define YKT_DECL
+#define YKT(i)
+#endif
+
 // One macro tile after its pixels have been packed: the cascade of Convert()'s passes (EC.cpp:9057-9093), its results,
 // the corner colours of its lattice points, then the range stage.  (gmx, gmy) = origin of the macro tile in the image.
 static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch, uint8_t* hist,
                                       const uint32_t* magicTab, int gmx, int gmy, bool pass16Hopeless) {
     const int lane = threadIdx.x & 31;
     const YkRun& run = sh.run;
+    YKT_DECL;
     const int wIn = C.w - gmx, hIn = C.h - gmy;              // image extent seen from the macro tile's origin
     if (wIn <= 0 || hIn <= 0) return;
     // claimed 4x4 cells of the macro tile (bit = 4*cellY + cellX); cells outside the image count as claimed
@@ -660,6 +674,7 @@ static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShare
                 const unsigned poss = (unsigned)(P >> g.start) & __ballot_sync(YK_FULL, freeTile);
                 if (poss) claimed = yka_macro_pass(priv, sh, C, touch, pid, rp, gmx, gmy, claimed, poss, rej);
             }
+            if (threadIdx.x == 32) YKT(11);
             // EC.cpp:4029-4037: newly claimed cells
             const unsigned fresh4 = ((claimed & ~claimed0) >> (4 * (lane & 3))) & 15u;
             if (lane < 4 && fresh4) {
@@ -684,6 +699,7 @@ static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShare
             }
         }
     }
+    if (threadIdx.x == 32) YKT(12);
     if (run.doR2 && claimed != 0xFFFFu) {
         const int tilesW = C.w >> 3;
 #pragma unroll 1
@@ -697,20 +713,9 @@ static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShare
             }
         }
     }
+    if (threadIdx.x == 32) YKT(13);
 }
 
-#ifdef YK_TIMING
-__device__ unsigned long long yk_timing[16];
-#define YKT_DECL long long t__ = clock64(), t2__
-#define YKT(i) (t2__ = clock64(), atomicAdd(&yk_timing[i], (unsigned long long)(t2__ - t__)), t__ = t2__)
-extern "C" void yk_debug_timing(unsigned long long* out, int reset) {
-    cudaMemcpyFromSymbol(out, yk_timing, sizeof(yk_timing));
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(yk_timing, z, sizeof(z)); }
-}
-#else
-#define YKT_DECL
-#define YKT(i)
-#endif
 
 template <bool U8>
 static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restrict__ slots, int slot0, int nSlots, int nRegions, const YkRun& runArg) {
