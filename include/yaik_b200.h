@@ -74,8 +74,9 @@ void  yk_host_free(void* p);
  * the slot's analysis state (the reference allocates its state planes lazily per image, EC.cpp:3739-3749). */
 int  yk_set_image(yk_ctx* ctx, int slot, const int32_t* const* planes, int nPlanes, int w, int h);
 /* How yk_set_image moves the samples: packedU8 != 0 (default) packs the int32 Plane samples to bytes on the host
- * (threads; a sample outside 0..255 makes the call's analysis return YK_ERR_RANGE) and uploads a quarter of the bytes;
- * 0 uploads the int32 planes as they are.  Results are identical. */
+ * (threads) and uploads a quarter of the bytes; 0 uploads the int32 planes as they are.  Results are identical.  An
+ * image with a sample outside 0..255 (signed chroma planes) goes up as int32 in either mode: yk_range_dyn takes it, the
+ * alpha / gradient / 1-D range stages return YK_ERR_RANGE for it. */
 int  yk_set_upload_format(yk_ctx* ctx, int packedU8);
 /* Same, planes already resident in device memory (borrowed, not copied; row pitch == w). */
 int  yk_set_image_device(yk_ctx* ctx, int slot, const int32_t* const* devPlanes, int nPlanes, int w, int h);

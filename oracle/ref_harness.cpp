@@ -18,7 +18,8 @@
 // (stale code-book bug).
 //
 // usage: yaik_ref <in.ykin> <out.ykout> [alpha] [grad] [r2] [r1] [r1_3bit] [reps=N]
-//   in : "YKIN" int32 w,h,nplanes, then nplanes*h*w bytes (u8 samples, plane-major)
+//   in : "YKIN" int32 w,h,nplanes, then nplanes*h*w bytes (u8 samples, plane-major);
+//        "YKI4" the same with int32 samples
 //   out: records { char name[32]; char dtype; u64 count; payload }, dtype in {i,B,H,d}
 
 #include "EncoderContext.h"
@@ -220,10 +221,17 @@ int main(int argc, char** argv) {
     FILE* fi = fopen(argv[1], "rb");
     if (!fi) { perror(argv[1]); return 1; }
     char magic[4]; int hdr[3];
-    if (fread(magic, 1, 4, fi) != 4 || memcmp(magic, "YKIN", 4) || fread(hdr, 4, 3, fi) != 3) { fprintf(stderr, "bad input\n"); return 1; }
+    if (fread(magic, 1, 4, fi) != 4 || (memcmp(magic, "YKIN", 4) && memcmp(magic, "YKI4", 4)) || fread(hdr, 4, 3, fi) != 3) { fprintf(stderr, "bad input\n"); return 1; }
+    const bool wide = !memcmp(magic, "YKI4", 4);          // int32 samples (planes outside the byte range, R1 only)
     int W = hdr[0], H = hdr[1], NP = hdr[2];
-    std::vector<u8> px((size_t)W * H * NP);
-    if (fread(px.data(), 1, px.size(), fi) != px.size()) { fprintf(stderr, "short input\n"); return 1; }
+    std::vector<int> px((size_t)W * H * NP);
+    if (wide) {
+        if (fread(px.data(), 4, px.size(), fi) != px.size()) { fprintf(stderr, "short input\n"); return 1; }
+    } else {
+        std::vector<u8> b(px.size());
+        if (fread(b.data(), 1, b.size(), fi) != b.size()) { fprintf(stderr, "short input\n"); return 1; }
+        for (size_t i = 0; i < b.size(); i++) px[i] = b[i];
+    }
     fclose(fi);
     // absolute output path before chdir
     std::string outPath = argv[2];
@@ -245,7 +253,7 @@ int main(int argc, char** argv) {
         Probe* ctx = new Probe();
         Image* img = Image::CreateImage(W, H, NP, false);
         for (int c = 0; c < NP; c++) {
-            int* d = img->GetPlane(c)->GetPixels(); const u8* s = px.data() + (size_t)c * W * H;
+            int* d = img->GetPlane(c)->GetPixels(); const int* s = px.data() + (size_t)c * W * H;
             for (size_t i = 0; i < (size_t)W * H; i++) d[i] = s[i];
         }
         ctx->SetImageToEncode(img);

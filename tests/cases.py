@@ -74,6 +74,11 @@ SMALL_CASES = {
     "noise_lowamp96": lambda: (_noise(96, 96, 3, 32, 100, 108), ("grad", "r2", "r1")),
     "noise_delta1": lambda: (_noise(64, 64, 3, 33, 0, 3), ("grad", "r2", "r1")),      # R2 delta==1 -> index -1 quirk
     "noise_hi": lambda: (_noise(64, 64, 3, 34, 250, 255), ("grad", "r2", "r1")),      # R2 clamp 254, R1 base clamp 224
+    # R1 alone on signed planes (int32 upload): the +128 shift of blocks with a negative minimum (EC.cpp:764-768).  The
+    # reference indexes fullTables[min][max] with the shifted values, so a block needs min >= -128 and max + 128 <= 255
+    # when negative, max <= 255 otherwise; anything wider reads outside that array in the reference (undefined there).
+    "r1_signed96": lambda: (_noise(96, 96, 3, 36, -120, 100), ("r1",)),
+    "r1_signed_edge64": lambda: (_noise(64, 64, 3, 37, -128, 127), ("r1",)),
     # mip tail (SURVEY.md hazard 11)
     "mip32_rgba": lambda: (make_image(32, 32, 4, SEED_BASE + 14), ALL),
     "mip16_rgba": lambda: (make_image(16, 16, 4, SEED_BASE + 15, holes=0), ("alpha", "grad", "r2")),

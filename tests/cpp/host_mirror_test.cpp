@@ -30,17 +30,24 @@ int main(int argc, char** argv) {
     }
     FILE* fi = fopen(argv[1], "rb");
     char magic[4]; int hdr[3];
-    if (!fi || fread(magic, 1, 4, fi) != 4 || memcmp(magic, "YKIN", 4) || fread(hdr, 4, 3, fi) != 3) { fprintf(stderr, "bad input\n"); return 1; }
+    if (!fi || fread(magic, 1, 4, fi) != 4 || (memcmp(magic, "YKIN", 4) && memcmp(magic, "YKI4", 4)) || fread(hdr, 4, 3, fi) != 3) { fprintf(stderr, "bad input\n"); return 1; }
+    const bool wide = !memcmp(magic, "YKI4", 4);       // int32 samples (yaik_b200/synth.py to_ykin)
     const int W = hdr[0], H = hdr[1], NP = hdr[2];
-    std::vector<u8> px((size_t)W * H * NP);
-    if (fread(px.data(), 1, px.size(), fi) != px.size()) return 1;
+    std::vector<int> px((size_t)W * H * NP);
+    if (wide) {
+        if (fread(px.data(), 4, px.size(), fi) != px.size()) return 1;
+    } else {
+        std::vector<u8> b(px.size());
+        if (fread(b.data(), 1, b.size(), fi) != b.size()) return 1;
+        for (size_t i = 0; i < b.size(); i++) px[i] = b[i];
+    }
     fclose(fi);
     g_out = fopen(argv[2], "wb");
 
     EncoderContext ctx(0);
     Image* img = Image::CreateImage(W, H, NP, false);
     for (int c = 0; c < NP; c++) {
-        int* d = img->GetPlane(c)->GetPixels(); const u8* s = px.data() + (size_t)c * W * H;
+        int* d = img->GetPlane(c)->GetPixels(); const int* s = px.data() + (size_t)c * W * H;
         for (size_t i = 0; i < (size_t)W * H; i++) d[i] = s[i];
     }
     ctx.SetImageToEncode(img);

@@ -4,7 +4,7 @@ built by oracle/Makefile).  Run in the build container only (the GPU box has no 
 
     make -C oracle ref && python tests/golden/make_golden.py
 
-Each fixture holds the seeded input (uint8 planes) and every observable result of the reference's stage functions
+Each fixture holds the seeded input (uint8 planes; int16 for the signed R1 case) and every observable result of the reference's stage functions
 for it: MipPrefilter (bound, bitmap), the seven FittingQuadSmooth passes (TileDone, bitmap, bbox header,
 rgbStream captured at PaletteCompressor), DynamicTileCompressor (idx/type per plane), DynamicTileEncode (tile defs,
 nibbles, constraint) and SHA-256 digests of the int32 state planes.  tests/test_golden.py pins the C oracle to them
@@ -22,7 +22,7 @@ import cases  # noqa: E402
 from refrun import have_ref, run_ref  # noqa: E402
 
 GOLDEN_CASES = ["ramp64_a2", "patchy128", "patchy_72x40", "noise_delta1", "noise_hi", "mip32_rgba", "mip16_rgba",
-                "mip8_rgb", "mip4_rgb", "alpha_island128", "alpha_corner_only", "synth256_rgba", "synth256_rgb_3bit"]
+                "mip8_rgb", "mip4_rgb", "alpha_island128", "alpha_corner_only", "synth256_rgba", "synth256_rgb_3bit", "r1_signed96"]
 
 
 def digest(a):
@@ -34,7 +34,8 @@ def main():
     for name in GOLDEN_CASES:
         planes, stages = cases.SMALL_CASES[name]()
         ref = run_ref(planes, stages)
-        out = {"input": planes.astype(np.uint8), "stages": np.array(list(stages))}
+        in_bytes = int(planes.min()) >= 0 and int(planes.max()) <= 255
+        out = {"input": planes.astype(np.uint8 if in_bytes else np.int16), "stages": np.array(list(stages))}
         for k, v in ref.items():
             if k.startswith("time."):
                 continue

@@ -54,7 +54,7 @@ def emu_bin():
     return EMU_BIN
 
 
-@pytest.mark.parametrize("name", ["patchy_72x40", "mip32_rgba", "alpha_island128"])
+@pytest.mark.parametrize("name", ["patchy_72x40", "mip32_rgba", "alpha_island128", "r1_signed96"])
 def test_mirror_logic_on_emulated_library(emu_bin, name):
     compare(name, emu_bin)
 

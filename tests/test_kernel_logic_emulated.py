@@ -21,7 +21,7 @@ def emu_lib():
     return capi.load_library(EMU)
 
 
-EMU_CASES = ["synth256_rgb_3bit", "alpha_island256", "ramp64_a2", "patchy_72x40", "patchy128", "mip32_rgba", "mip16_rgba", "mip8_rgb", "mip4_rgb",
+EMU_CASES = ["r1_signed96", "r1_signed_edge64", "synth256_rgb_3bit", "alpha_island256", "ramp64_a2", "patchy_72x40", "patchy128", "mip32_rgba", "mip16_rgba", "mip8_rgb", "mip4_rgb",
              "alpha_island128", "alpha_corner_only", "noise_delta1", "noise_hi", "flat64"]
 
 

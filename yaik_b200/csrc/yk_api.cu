@@ -137,6 +137,9 @@ extern "C" void* yk_host_alloc(size_t bytes) {
 }
 extern "C" void yk_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+// look-back words of yk_k_r1_encode: one per unit of 32 blocks (YK_R1_UNIT, yk_kernels.cu; sized for units down to 8) of the (8-aligned, possibly one block larger) bound box, + ticket
+static size_t r1_status_words(int W, int H) { return ((size_t)(W / 8 + 1) * (H / 8 + 1) + 7) / 8 + 2; }
+
 template <class T> static int dev_alloc(YkSlotHost& s, T** out, size_t count) {
     void* p = nullptr;
     CK(cudaMalloc(&p, (count ? count : 1) * sizeof(T) + 64));
@@ -259,9 +262,7 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
             if ((rc = dev_alloc(s, &s.d.r2Idx[p], W * H))) return rc;
             if ((rc = dev_alloc(s, &s.d.r2Type[p], 3 * (W / 8 + 1) * (H / 8 + 1)))) return rc;
         }
-        size_t nblk = (W / 8) * (H / 8 + 1) + 1;
-        if ((rc = dev_alloc(s, &s.d.r1Cnt, nblk))) return rc;
-        if ((rc = dev_alloc(s, &s.d.r1Def, nblk))) return rc;
+        if ((rc = dev_alloc(s, &s.d.r1Status, r1_status_words(W, H)))) return rc;
         for (int p = 0; p < 3; p++) {
             if ((rc = dev_alloc(s, &s.d.r1Nib[p], (W / 8) * (H / 8) * 8 + 4))) return rc;
             if ((rc = dev_alloc(s, &s.d.r1Defs[p], (W / 8) * (H / 8) + 4))) return rc;
@@ -393,7 +394,8 @@ extern "C" int yk_set_image(yk_ctx* c, int slot, const int32_t* const* planes, i
     CK(cudaSetDevice(c->device));
     for (int p = 0; p < nPlanes; p++) if (!planes[p]) return YK_ERR_ARG;
     unsigned bad = 0;
-    if (c->packedUpload) {
+    bool packed = c->packedUpload != 0;
+    if (packed) {
         // Plane samples are 0..255 on this path: pack them to bytes on the host (threads, range check included) and move a
         // quarter of the bytes over PCIe; yk_k_analyze_u8 stages the packed planes with byte TMA boxes
         const size_t pitch = ((size_t)w + 15) / 16 * 16, planeBytes = pitch * h, need = planeBytes * nPlanes;
@@ -416,7 +418,11 @@ extern "C" int yk_set_image(yk_ctx* c, int slot, const int32_t* const* planes, i
         s.stageBusy = true;
         s.d.isU8 = 1; s.d.pitchU8 = (int)pitch;
         s.int32Valid = false;
-    } else {
+        // samples outside 0..255 (signed chroma planes): this image goes up as int32 instead.  yk_range_dyn takes such
+        // planes; the alpha / gradient / 1-D range stages report YK_ERR_RANGE for them either way.
+        if (bad & ~255u) packed = false;
+    }
+    if (!packed) {
         for (int p = 0; p < nPlanes; p++) {
             CK(cudaMemcpyAsync(s.owned[p], planes[p], (size_t)w * h * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
             s.d.plane[p] = s.owned[p];
@@ -782,16 +788,20 @@ extern "C" int yk_range1d(yk_ctx* c, int slot, int plane, uint8_t* idx, int idxC
 // Six LUTs per (base6, range7) pair, built on the host with the reference's own float expression and glibc powf
 // (DynamicTile::buildTable, EC.cpp:625-699; SURVEY.md hazard 12).  range7 can exceed 7 bits for bases close to 224
 // (a reference quirk: EncodeTileType then spills into the type bits) — the table simply covers it.
+// Behind the 72 entries sit the 72 decision thresholds yk_k_r1_encode searches with (see there): the LUTs are
+// non-decreasing (checked here: the kernel's search depends on it), so "first strict minimum of |entry - value|"
+// is "number of thresholds below the value".
 #define YK_R1_R7MAX 176
+#define YK_R1_LUT_INTS 144
 static int ensure_r1_lut(yk_ctx* c) {
     if (c->lutDev) return YK_OK;
-    std::vector<int> lut((size_t)64 * YK_R1_R7MAX * 72, 0);
+    std::vector<int> lut((size_t)64 * YK_R1_R7MAX * YK_R1_LUT_INTS, 0);
     for (int b6 = 0; b6 < 64; b6++) {
         const int BN = (b6 * 224) / 63, scale = 223 - BN;
         for (int r7 = 0; r7 < YK_R1_R7MAX; r7++) {
             const int D = (r7 * scale) / 127 + 32;                 // DiffRangeDecode, EC.cpp:620-623
             const float DistNormF = (float)D;
-            int* T = &lut[((size_t)b6 * YK_R1_R7MAX + r7) * 72];
+            int* T = &lut[((size_t)b6 * YK_R1_R7MAX + r7) * YK_R1_LUT_INTS];
             for (int input = 0; input < 16; input++) {              // EC.cpp:662-677
                 float pos = input / 15.0f;
                 float ExpNormV = powf(pos, 1.4f), LogNormV = 1.0f - powf((1.0f - pos), 1.4f);
@@ -803,6 +813,18 @@ static int ensure_r1_lut(yk_ctx* c) {
                 float ExpNormV = powf(pos, 1.4f), LogNormV = 1.0f - powf((1.0f - pos), 1.4f);
                 float outLinear = pos * DistNormF, outExp = ExpNormV * DistNormF, outLog = LogNormV * DistNormF;
                 T[48 + input] = (int)(BN + outLinear); T[56 + input] = (int)(BN + outExp); T[64 + input] = (int)(BN + outLog);
+            }
+            for (int m = 0; m < 6; m++) {
+                const int off = m < 3 ? 16 * m : 48 + 8 * (m - 3), count = m < 3 ? 16 : 8;
+                const int* L = T + off;
+                int* TH = T + 72 + off;
+                TH[0] = INT_MIN;
+                int next = INT_MAX;                                  // threshold of the next distinct entry
+                for (int n = count - 1; n >= 1; n--) {
+                    if (L[n] < L[n - 1]) return YK_ERR_STATE;        // never: every curve is monotone
+                    if (L[n] > L[n - 1]) next = (L[n - 1] + L[n]) >> 1;
+                    TH[n] = next;
+                }
             }
         }
     }
@@ -836,13 +858,10 @@ extern "C" int yk_range_dyn(yk_ctx* c, int slot, int plane, int mode3BitOnly, ui
     }
     s.d.r1Dst = dDst; s.dirty = true;
     if ((rc = upload_slots(c, slot, 1))) return rc;
-    const size_t nibWords = (size_t)(w / 8) * (h / 8) * 8 + 4;
-    CK(cudaMemsetAsync(s.d.r1Nib[plane], 0, nibWords * 4, c->stream));
     if (nBlocks > 0) {
-        yk_launch_range_dyn_count(c->slotsDev, slot, cx, cy, cw, ch, nBlocks, c->stream);
-        yk_launch_range_dyn_scan(c->slotsDev, slot, nBlocks, plane, c->stream);
+        CK(cudaMemsetAsync(s.d.r1Status, 0, r1_status_words(w, h) * sizeof(unsigned long long), c->stream));
         yk_launch_range_dyn_encode(c->slotsDev, slot, plane, mode3BitOnly ? 1 : 0, cx, cy, cw, ch, nBlocks, c->lutDev, c->stream);
-        c->launches += 3;
+        c->launches += 1;
     }
     CK(cudaGetLastError());
     int tot[2] = { 0, 0 };

@@ -78,9 +78,8 @@ struct alignas(128) YkSlotDev {
     uint8_t*  r2Idx[3];         // the streams in the reference's order (gathered by yk_k_emit)
     uint8_t*  r2Type[3];
     // ---- range stage R1 (DynamicTileEncode)
-    int*      r1Cnt;            // [ (h/8+1) * (w/8) ] valid pixels per block in LeftRightOrder, then exclusive offsets
-    int*      r1Def;            // exclusive offsets of emitted tile defs
-    uint32_t* r1Nib[3];         // nibble stream as zeroed u32 words
+    unsigned long long* r1Status;   // look-back words of yk_k_r1_encode's units (256 blocks of the walk each) + the unit ticket; zeroed per call
+    uint32_t* r1Nib[3];         // nibble stream (two nibbles per byte, written pairwise)
     uint16_t* r1Defs[3];
     int32_t*  r1Dst;            // optional w*h int32 (one plane at a time)
     int       alphaReset;       // set by the host after the alpha stage: bbox == full image -> mask all 255 (EC.cpp:1400-1403)
@@ -109,8 +108,6 @@ void yk_launch_owner(const YkSlotDev* slotsDev, int slot0, int nSlots, int nPoin
 void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int gradGroups, int r2Groups, const YkRun& run, cudaStream_t st);
 void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t* smoothMap, int32_t* mipmapMask,
                      int32_t* mappedRGB, int32_t* recon0, int32_t* recon1, int32_t* recon2, cudaStream_t st);
-void yk_launch_range_dyn_count(const YkSlotDev* slotsDev, int slot, int cx, int cy, int cw, int ch, int nBlocks, cudaStream_t st);
-void yk_launch_range_dyn_scan(const YkSlotDev* slotsDev, int slot, int nBlocks, int plane, cudaStream_t st);
 void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, int plane, int mode3, int cx, int cy, int cw, int ch,
                                 int nBlocks, const int* lutDev, cudaStream_t st);
 #ifdef __cplusplus

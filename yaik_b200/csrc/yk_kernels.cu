@@ -185,114 +185,149 @@ static __device__ int yk_block_exclusive(int v, int* sWarp, int& total) {
     return r;
 }
 
-__global__ void __launch_bounds__(256)
-yk_k_r1_count(const YkSlotDev* __restrict__ slots, int slot, int cx, int cy, int cw, int ch, int nBlocks) {
-    const YkSlotDev& S = slots[slot];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nBlocks) return;
-    const int nbw = cw >> 3;
-    const int x = cx + 8 * (i % nbw), y = cy + 8 * (i / nbw);
-    int n = 0;
-    if (x + 8 <= cw && y + 8 <= ch && x + 8 <= S.w && y + 8 <= S.h) n = 16 * __popc(yk_r1_cells(S, x, y));
-    S.r1Cnt[i] = n;
-}
+// One launch per plane.  A CTA takes a unit of YK_R1_UNIT consecutive blocks of the walk (global ticket): one thread
+// per block counts its valid pixels, a block scan + one decoupled look-back turn the counts into nibble / tile-def
+// offsets, the blocks that hold valid pixels are compacted into a list in shared memory and the warps encode them one
+// block per warp.  Small units: the per-block work is a long dependent chain (min/max -> table -> search -> ordered
+// float sum), so the kernel wants as many warps in flight as the SM holds.
+//
+// lut: [64 base6][176 range7][144] ints.  [0,72) = the six LUTs (16,16,16,8,8,8 entries) of DynamicTile::buildTable
+// (EC.cpp:625-699); [72,144) = their decision thresholds, same layout.  Every LUT is non-decreasing, so the reference's
+// "first strict minimum of |entry - value|" scan (EC.cpp:873-881) picks entry n over all earlier ones exactly when
+// value > floor((L[n-1] + L[n]) / 2) with L[n] > L[n-1]; a repeated entry is never picked and inherits the threshold of
+// the next distinct one (INT_MAX if none), which keeps the thresholds non-decreasing: code = #{n >= 1 : value > thr[n]}.
+#ifndef YK_R1_UNIT
+#define YK_R1_UNIT 32
+#endif
+#ifndef YK_R1_THREADS
+#define YK_R1_THREADS 128
+#endif
+#define YK_R1_LUT_INTS 144
 
-__global__ void __launch_bounds__(1024)
-yk_k_r1_scan(const YkSlotDev* __restrict__ slots, int slot, int nBlocks, int plane) {
-    __shared__ int sWarp[33];
-    const YkSlotDev& S = slots[slot];
-    const int tid = threadIdx.x;
-    const int per = (nBlocks + (int)blockDim.x - 1) / (int)blockDim.x;
-    const int b = min(nBlocks, tid * per), e = min(nBlocks, b + per);
-    int sn = 0, sd = 0;
-    for (int i = b; i < e; i++) { int v = S.r1Cnt[i]; sn += v; sd += (v > 0); }
-    int totN, totD;
-    int rn = yk_block_exclusive(sn, sWarp, totN);
-    int rd = yk_block_exclusive(sd, sWarp, totD);
-    for (int i = b; i < e; i++) { int v = S.r1Cnt[i]; S.r1Cnt[i] = rn | (v ? (1 << 31) : 0); S.r1Def[i] = rd; rn += v; rd += (v > 0); }
-    if (tid == 0) { S.hdr[YK_HD_R1_NIB0 + plane] = totN; S.hdr[YK_HD_R1_DEF0 + plane] = totD; }
-}
-
-// lut: [64 base6][176 range7][72] ints = six LUTs (16,16,16,8,8,8 entries) of DynamicTile::buildTable (EC.cpp:625-699)
-__global__ void __launch_bounds__(YK_THREADS)
+__global__ void __launch_bounds__(YK_R1_THREADS)
 yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, int plane, int mode3, int cx, int cy, int cw, int ch,
                int nBlocks, const int* __restrict__ lut) {
-    __shared__ float sTerm[YK_THREADS / 32][6][64];
+    __shared__ __align__(16) float sTerm[YK_R1_THREADS / 32][6][64];
+    __shared__ int sBlock[YK_R1_UNIT], sNibOff[YK_R1_UNIT];      // sBlock: x / 8 | (y / 8) << 12 | cells << 28 (x, y < 32768)
+    __shared__ int sWarp[33];
+    __shared__ int sUnit;
+    __shared__ unsigned sBase[2];
     const YkSlotDev& S = slots[slot];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * (YK_THREADS / 32) + warp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nUnits = (nBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT;
+    unsigned long long* status = S.r1Status;
+    if (tid == 0) sUnit = (int)atomicAdd(reinterpret_cast<unsigned*>(&status[nUnits]), 1u);
+    __syncthreads();
+    const int u = sUnit;
     const int nbw = cw >> 3;
-    const bool inRange = i < nBlocks;
-    const int x = cx + 8 * ((inRange ? i : 0) % nbw), y = cy + 8 * ((inRange ? i : 0) / nbw);
+    // ---- count
+    const int i = u * YK_R1_UNIT + tid;
     unsigned cells = 0;
-    int offWord = inRange ? S.r1Cnt[i] : 0;
-    if (inRange && (offWord < 0) ) cells = yk_r1_cells(S, x, y);          // sign bit = block has valid pixels
-    if (cells == 0) return;                                               // warp-uniform
-    const int nibOff = offWord & 0x7FFFFFFF, defOff = S.r1Def[i];
+    int bx = 0, by = 0;
+    if (tid < YK_R1_UNIT && i < nBlocks) {
+        const int x = cx + 8 * (i % nbw), y = cy + 8 * (i / nbw);
+        bx = x; by = y;
+        if (x + 8 <= cw && y + 8 <= ch && x + 8 <= S.w && y + 8 <= S.h) cells = yk_r1_cells(S, x, y);
+    }
+    const int n = 16 * __popc(cells);
+    // ---- offsets: pixels in the low 16 bits (<= 64 * YK_R1_UNIT per unit), blocks with pixels above
+    int tot;
+    const int ex = yk_block_exclusive(n | ((n > 0) << 16), sWarp, tot);
+    if (warp == 0) {
+        const unsigned long long base = yk_lookback64(status, u, (unsigned)(tot & 0xFFFF), (unsigned)(tot >> 16));
+        if (lane == 0) {
+            sBase[0] = (unsigned)(base >> 32); sBase[1] = (unsigned)base;
+            if (u == nUnits - 1) {
+                S.hdr[YK_HD_R1_NIB0 + plane] = (int)(base >> 32) + (tot & 0xFFFF);
+                S.hdr[YK_HD_R1_DEF0 + plane] = (int)(unsigned)base + (tot >> 16);
+            }
+        }
+    }
+    if (n > 0) { sBlock[ex >> 16] = (bx >> 3) | ((by >> 3) << 12) | ((int)cells << 28); sNibOff[ex >> 16] = ex & 0xFFFF; }
+    __syncthreads();
+    const int nList = tot >> 16;
+    const int nibBase = (int)sBase[0], defBase = (int)sBase[1];
     const int r = lane >> 2, c0 = (lane & 3) * 2;
-    const bool valid = (cells >> ((r >> 2) * 2 + (c0 >> 2))) & 1u;
-    int v0 = 0, v1 = 0;
-    if (valid) {
-        int2 p = __ldg(reinterpret_cast<const int2*>(S.plane[plane] + (size_t)(y + r) * S.w + x + c0));
-        v0 = p.x; v1 = p.y;
-    }
-    int mn = __reduce_min_sync(YK_FULL, valid ? min(v0, v1) : INT_MAX);
-    int mx = __reduce_max_sync(YK_FULL, valid ? max(v0, v1) : INT_MIN);
-    int sgn = 0;
-    if (mn < 0) { mn += 128; mx += 128; sgn = 128; }                       // EC.cpp:764-768
-    mn = min(max(mn, 0), 255); mx = min(max(mx, mn), 255);
-    // DynamicTile::buildTable index (EC.cpp:635-650)
-    const int m = min(mn, 224);
-    const int diff = max(mx - m, 16);
-    const int b6 = (m * 63 + 112) / 224, BN = (b6 * 224) / 63;
-    const int scale = 223 - BN;
-    const int r7 = ((max(diff, 32) - 32) * 127 + scale - 1) / scale;
-    const int* T = lut + ((size_t)b6 * 176 + min(r7, 175)) * 72;
-    const int o0 = v0 + sgn, o1 = v1 + sgn;
-    unsigned codes0 = 0, codes1 = 0;                                       // 4 bits per mode
     const int startMode = mode3 ? 3 : 0;
-    for (int mode = startMode; mode < 6; mode++) {
-        const int count = mode < 3 ? 16 : 8;
-        const int* L = T + (mode < 3 ? 16 * mode : 48 + 8 * (mode - 3));
-        int d0 = 99999, d1 = 99999, f0 = 0, f1 = 0;
-        for (int n = 0; n < count; n++) {                                  // first strict minimum, EC.cpp:873-881
-            const int e = __ldg(L + n);
-            const int a0 = abs(e - o0), a1 = abs(e - o1);
-            if (a0 < d0) { d0 = a0; f0 = n; }
-            if (a1 < d1) { d1 = a1; f1 = n; }
+    for (int k = warp; k < nList; k += YK_R1_THREADS / 32) {
+        const int word = sBlock[k];
+        const unsigned bc = (unsigned)word >> 28;
+        const int x = (word & 0xFFF) << 3, y = ((word >> 12) & 0xFFF) << 3;
+        const bool valid = (bc >> ((r >> 2) * 2 + (c0 >> 2))) & 1u;
+        int v0 = 0, v1 = 0;
+        if (valid) {
+            int2 p = __ldg(reinterpret_cast<const int2*>(S.plane[plane] + (size_t)(y + r) * S.w + x + c0));
+            v0 = p.x; v1 = p.y;
         }
-        codes0 |= (unsigned)f0 << (4 * mode); codes1 |= (unsigned)f1 << (4 * mode);
-        // cumulated relative error term, float32 (EC.cpp:884-886); invalid pixels add +0.0f which leaves the sum unchanged
-        sTerm[warp][mode][2 * lane] = (valid && o0 != 0) ? ((float)d0 / (float)o0) : 0.0f;
-        sTerm[warp][mode][2 * lane + 1] = (valid && o1 != 0) ? ((float)d1 / (float)o1) : 0.0f;
-    }
-    __syncwarp();
-    float err = 0.0f;
-    if (lane >= startMode && lane < 6) {
-        // the reference sums in row-major valid-pixel order; float addition is not associative, so one lane per mode
-        for (int k = 0; k < 64; k++) err = __fadd_rn(err, sTerm[warp][lane][k]);
-    }
-    int bestMode = -1;
-    float bestErr = 99999999.0f;
-    for (int mode = startMode; mode < 6; mode++) {                          // `<=`: later modes win ties, EC.cpp:897-905
-        const float e = __shfl_sync(YK_FULL, err, mode);
-        if (e <= bestErr) { bestErr = e; bestMode = mode; }
-    }
-    const unsigned bv0 = __ballot_sync(YK_FULL, valid);
-    if (valid) {
-        const int before = 2 * __popc(bv0 & ((1u << lane) - 1u));           // both pixels of a lane share validity
-        const int c0v = (codes0 >> (4 * bestMode)) & 15, c1v = (codes1 >> (4 * bestMode)) & 15;
-        const int n0 = nibOff + before;                                     // nibble index of pixel 0; pixel 1 follows
-        uint32_t* W = S.r1Nib[plane];
-        atomicOr(&W[n0 >> 3], (uint32_t)c0v << (4 * (n0 & 7)));             // low nibble first, EC.cpp:1180-1184
-        atomicOr(&W[(n0 + 1) >> 3], (uint32_t)c1v << (4 * ((n0 + 1) & 7)));
-        if (S.r1Dst) {
-            const int* L = T + (bestMode < 3 ? 16 * bestMode : 48 + 8 * (bestMode - 3));
-            int* d = S.r1Dst + (size_t)(y + r) * S.w + x + c0;
-            d[0] = __ldg(L + c0v); d[1] = __ldg(L + c1v);                    // EC.cpp:4448-4457 (offset 0 for full-resolution planes)
+        int mn = __reduce_min_sync(YK_FULL, valid ? min(v0, v1) : INT_MAX);
+        int mx = __reduce_max_sync(YK_FULL, valid ? max(v0, v1) : INT_MIN);
+        int sgn = 0;
+        if (mn < 0) { mn += 128; mx += 128; sgn = 128; }                       // EC.cpp:764-768
+        mn = min(max(mn, 0), 255); mx = min(max(mx, mn), 255);
+        // DynamicTile::buildTable index (EC.cpp:635-650)
+        const int m = min(mn, 224);
+        const int diff = max(mx - m, 16);
+        const int b6 = (m * 63 + 112) / 224, BN = (b6 * 224) / 63;
+        const int scale = 223 - BN;
+        const int r7 = ((max(diff, 32) - 32) * 127 + scale - 1) / scale;
+        const int* T = lut + ((size_t)b6 * 176 + min(r7, 175)) * YK_R1_LUT_INTS;
+        const int o0 = v0 + sgn, o1 = v1 + sgn;
+        unsigned codes0 = 0, codes1 = 0;                                       // 4 bits per mode
+#pragma unroll
+        for (int mode = 0; mode < 6; mode++) {
+            if (mode < startMode) continue;
+            const int off = mode < 3 ? 16 * mode : 48 + 8 * (mode - 3);
+            const int4* H = reinterpret_cast<const int4*>(T + 72 + off);
+            int f0 = 0, f1 = 0;
+#pragma unroll
+            for (int q = 0; q < (mode < 3 ? 4 : 2); q++) {
+                const int4 t = __ldg(H + q);
+                if (q) { f0 += (o0 > t.x); f1 += (o1 > t.x); }                  // threshold 0 of a LUT is unused
+                f0 += (o0 > t.y); f1 += (o1 > t.y);
+                f0 += (o0 > t.z); f1 += (o1 > t.z);
+                f0 += (o0 > t.w); f1 += (o1 > t.w);
+            }
+            const int d0 = abs(__ldg(T + off + f0) - o0), d1 = abs(__ldg(T + off + f1) - o1);
+            codes0 |= (unsigned)f0 << (4 * mode); codes1 |= (unsigned)f1 << (4 * mode);
+            // cumulated relative error term, float32 (EC.cpp:884-886); invalid pixels add +0.0f which leaves the sum unchanged.
+            // The quotient is taken on operands that are never zero (a zero on either side sends the whole warp down the
+            // slow path of the IEEE division) and dropped afterwards: 0 / o is +-0 and adds nothing either.
+            const float q0 = (float)(d0 ? d0 : 1) / (float)(o0 ? o0 : 1), q1 = (float)(d1 ? d1 : 1) / (float)(o1 ? o1 : 1);
+            sTerm[warp][mode][2 * lane] = (valid && o0 != 0 && d0 != 0) ? q0 : 0.0f;
+            sTerm[warp][mode][2 * lane + 1] = (valid && o1 != 0 && d1 != 0) ? q1 : 0.0f;
         }
+        __syncwarp();
+        float err = 0.0f;
+        if (lane >= startMode && lane < 6) {
+            // the reference sums in row-major valid-pixel order; float addition is not associative, so one lane per mode
+            const float4* P = reinterpret_cast<const float4*>(sTerm[warp][lane]);
+#pragma unroll 4
+            for (int q = 0; q < 16; q++) {
+                const float4 t = P[q];
+                err = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(err, t.x), t.y), t.z), t.w);
+            }
+        }
+        int bestMode = -1;
+        float bestErr = 99999999.0f;
+        for (int mode = startMode; mode < 6; mode++) {                          // `<=`: later modes win ties, EC.cpp:897-905
+            const float e = __shfl_sync(YK_FULL, err, mode);
+            if (e <= bestErr) { bestErr = e; bestMode = mode; }
+        }
+        __syncwarp();                                                           // sTerm is rewritten by the next block
+        const unsigned bv0 = __ballot_sync(YK_FULL, valid);
+        if (valid) {
+            const int before = 2 * __popc(bv0 & ((1u << lane) - 1u));           // both pixels of a lane share validity
+            const int c0v = (codes0 >> (4 * bestMode)) & 15, c1v = (codes1 >> (4 * bestMode)) & 15;
+            const int n0 = nibBase + sNibOff[k] + before;                       // even: the two nibbles share a byte
+            reinterpret_cast<uint8_t*>(S.r1Nib[plane])[n0 >> 1] = (uint8_t)(c0v | (c1v << 4));   // low nibble first, EC.cpp:1180-1184
+            if (S.r1Dst) {
+                const int* L = T + (bestMode < 3 ? 16 * bestMode : 48 + 8 * (bestMode - 3));
+                int* d = S.r1Dst + (size_t)(y + r) * S.w + x + c0;
+                d[0] = __ldg(L + c0v); d[1] = __ldg(L + c1v);                    // EC.cpp:4448-4457 (offset 0 for full-resolution planes)
+            }
+        }
+        if (lane == 0) S.r1Defs[plane][defBase + k] = (uint16_t)((bestMode << 13) | (r7 << 7) | b6);    // EncodeTileType, YAIK_private.h:358
     }
-    if (lane == 0) S.r1Defs[plane][defOff] = (uint16_t)((bestMode << 13) | (r7 << 7) | b6);    // EncodeTileType, YAIK_private.h:358
 }
 
 // ------------------------------------------------------------------------------------------------------------------// launch wrappers
@@ -300,14 +335,7 @@ void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t*
                      int32_t* mappedRGB, int32_t* recon0, int32_t* recon1, int32_t* recon2, cudaStream_t st) {
     YK_LAUNCH(yk_k_state, dim3(nRegions), dim3(YK_THREADS), 0, st, slotsDev, slot, smoothMap, mipmapMask, mappedRGB, recon0, recon1, recon2);
 }
-void yk_launch_range_dyn_count(const YkSlotDev* slotsDev, int slot, int cx, int cy, int cw, int ch, int nBlocks, cudaStream_t st) {
-    YK_LAUNCH(yk_k_r1_count, dim3((nBlocks + 255) / 256), dim3(256), 0, st, slotsDev, slot, cx, cy, cw, ch, nBlocks);
-}
-void yk_launch_range_dyn_scan(const YkSlotDev* slotsDev, int slot, int nBlocks, int plane, cudaStream_t st) {
-    YK_LAUNCH(yk_k_r1_scan, dim3(1), dim3(1024), 0, st, slotsDev, slot, nBlocks, plane);
-}
 void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, int plane, int mode3, int cx, int cy, int cw, int ch,
                                 int nBlocks, const int* lutDev, cudaStream_t st) {
-    const int per = YK_THREADS / 32;
-    YK_LAUNCH(yk_k_r1_encode, dim3((nBlocks + per - 1) / per), dim3(YK_THREADS), 0, st, slotsDev, slot, plane, mode3, cx, cy, cw, ch, nBlocks, lutDev);
+    YK_LAUNCH(yk_k_r1_encode, dim3((nBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT), dim3(YK_R1_THREADS), 0, st, slotsDev, slot, plane, mode3, cx, cy, cw, ch, nBlocks, lutDev);
 }

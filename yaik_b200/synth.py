@@ -144,6 +144,9 @@ def mip_chain(top: int = 4096, seed: int = SEED_BASE + 4, channels: int = 4):
 
 
 def to_ykin(planes: np.ndarray) -> bytes:
-    """Serialise for oracle/_ref/yaik_ref: 'YKIN', int32 w,h,nplanes, then u8 samples plane-major."""
+    """Serialise for oracle/_ref/yaik_ref: 'YKIN', int32 w,h,nplanes, then u8 samples plane-major
+    ('YKI4' + int32 samples when the planes leave the byte range)."""
     c, h, w = planes.shape
+    if int(planes.min()) < 0 or int(planes.max()) > 255:
+        return b"YKI4" + np.asarray([w, h, c], dtype="<i4").tobytes() + planes.astype("<i4").tobytes()
     return b"YKIN" + np.asarray([w, h, c], dtype="<i4").tobytes() + planes.astype(np.uint8).tobytes()
