@@ -204,17 +204,60 @@ struct Probe : EncoderContext {
             snprintf(nm, sizeof nm, "r1.dst%d", c);     recPlane(nm, dst);
         }
     }
+
+    // The chroma pipeline of Convert() (EC.cpp:9539-9545, compiled out there): convRGB2YCoCg, chromaReduction, then
+    // DynamicTileEncode on Y (full), Co and Cg (reduced as configured).  cfg = halfCoW halfCoH halfCgW halfCgH, modes = EDownSample
+    void runChroma(const int cfg[4], const int modes[2], double* secs) {
+        int W = original->GetWidth(), H = original->GetHeight();
+        DynamicTileEncoderTable();
+        halfCoW = cfg[0]; halfCoH = cfg[1]; halfCgW = cfg[2]; halfCgH = cfg[3];
+        downSampleCo = (EDownSample)modes[0]; downSampleCg = (EDownSample)modes[1];
+        convRGB2YCoCg(true);
+        chromaReduction();
+        recPlane("yc.Y", YCoCgImg->GetPlane(0)); recPlane("yc.Co", YCoCgImg->GetPlane(1)); recPlane("yc.Cg", YCoCgImg->GetPlane(2));
+        recPlane("yc.workCo", workCo); recPlane("yc.workCg", workCg);
+        Plane* src[3] = { YCoCgImg->GetPlane(0), workCo, workCg };
+        const bool m3[3] = { false, false, true }, isCo[3] = { false, true, false }, isCg[3] = { false, false, true };
+        const bool hx[3] = { false, halfCoW, halfCgW }, hy[3] = { false, halfCoH, halfCgH };
+        for (int c = 0; c < 3; c++) {
+            Plane* dst = new Plane(W, H);
+            BoundingBox all = dst->GetRect(); dst->Fill(all, -1000);
+            size_t p0 = tell();
+            double t0 = now();
+            int ret = DynamicTileEncode(m3[c], src[c], dst, isCo[c], isCg[c], hx[c], hy[c]);
+            *secs += now() - t0;
+            size_t p1 = tell();
+            const u8* ch = (const u8*)memBuf + p0;
+            if (p1 <= p0) { fprintf(stderr, "yaik_ref: no PLNT chunk\n"); abort(); }
+            PlaneTile pt; memcpy(&pt, ch + sizeof(HeaderBase), sizeof pt);
+            const u8* z0 = ch + sizeof(HeaderBase) + sizeof(PlaneTile);
+            int pw = src[c]->GetWidth(), ph = src[c]->GetHeight();
+            std::vector<u8> defs = unzstd(z0, pt.streamSizeTileMap, (size_t)(pw / 8) * (ph / 8) * 2 + 16);
+            std::vector<u8> nib  = unzstd(z0 + pt.streamSizeTileMap, pt.streamSizeTileStream, (size_t)(pw / 8) * (ph / 8) * 32 + 16);
+            char nm[32];
+            snprintf(nm, sizeof nm, "yc.defs%d", c);    rec(nm, 'H', defs.data(), defs.size() / 2);
+            snprintf(nm, sizeof nm, "yc.nibbles%d", c); rec(nm, 'B', nib.data(), nib.size());
+            snprintf(nm, sizeof nm, "yc.hdr%d", c);
+            recInts(nm, { pt.bbox.x, pt.bbox.y, pt.bbox.w, pt.bbox.h, (int)pt.expectedSizeTileStream, pt.version, pt.format, ret });
+            snprintf(nm, sizeof nm, "yc.dst%d", c);     recPlane(nm, dst);
+        }
+    }
 };
 
 int main(int argc, char** argv) {
-    if (argc < 3) { fprintf(stderr, "usage: %s in out [alpha] [grad] [r2] [r1] [r1_3bit] [reps=N] [perpass]\n", argv[0]); return 2; }
-    bool doAlpha = false, doGrad = false, doR2 = false, doR1 = false, r1_3bit = false, perPass = false;
-    int reps = 1;
+    if (argc < 3) { fprintf(stderr, "usage: %s in out [alpha] [grad] [r2] [r1] [r1_3bit] [chroma=XYXY:MM] [reps=N] [perpass]\n", argv[0]); return 2; }
+    bool doAlpha = false, doGrad = false, doR2 = false, doR1 = false, r1_3bit = false, perPass = false, doChroma = false;
+    int reps = 1, chromaCfg[4] = { 1, 0, 1, 0 }, chromaModes[2] = { 2, 2 };       // CLI defaults, ImageEncoder.cpp:175-181
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         if (a == "alpha") doAlpha = true; else if (a == "grad") doGrad = true; else if (a == "r2") doR2 = true;
         else if (a == "r1") doR1 = true; else if (a == "r1_3bit") { doR1 = true; r1_3bit = true; }
         else if (a == "perpass") perPass = true;
+        else if (a.rfind("chroma=", 0) == 0 && a.size() == 14) {                  // chroma=XYXY:MM  e.g. chroma=1010:22
+            doChroma = true;
+            for (int k = 0; k < 4; k++) chromaCfg[k] = a[7 + k] == '1';
+            chromaModes[0] = a[12] - '0'; chromaModes[1] = a[13] - '0';
+        }
         else if (a.rfind("reps=", 0) == 0) reps = atoi(a.c_str() + 5);
         else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
     }
@@ -261,9 +304,10 @@ int main(int argc, char** argv) {
         Image* output = Image::CreateImage(W, H, 3, true);
         if (doAlpha && NP == 4) ctx->runAlpha(&tAlpha);
         if (doGrad) ctx->runGradient(output, &tGrad, perPass);
-        if (doR2 || doR1) ctx->ensureGradState(output);
+        if (doR2 || doR1 || doChroma) ctx->ensureGradState(output);
         if (doR2) ctx->runR2(output, &tR2);
         if (doR1) ctx->runR1(r1_3bit, &tR1);
+        if (doChroma) ctx->runChroma(chromaCfg, chromaModes, &tR1);
         if (!last) { fclose(g_out); g_out = keep; }
         // leak everything like the reference does (README.md:48-50); process exits soon
     }

@@ -337,16 +337,66 @@ int yko_dyn_table(int minV, int maxV, int mode, int lut[16], int* base6, int* ra
     return count;
 }
 
-/* DynamicTileEncode (EC.cpp:4365-4602) full-resolution case, with LeftRightOrder (framework.h:228-256),
- * GetTileEncode_Y (EC.cpp:1214-1221), Plane::GetMinMax_Y (Plane.cpp:489-587), GetTileDynamic_Y (EC.cpp:747-1212). */
-int yko_range_dyn(yko_ctx* c, int plane, int mode3BitOnly, uint8_t* nibbles, int* nNibbles,
-                  uint16_t* defs, int* nDefs, int32_t* dst, int constraint[4]) {
-    int w = c->w, h = c->h;
-    const int32_t* src = c->src[plane];
+/* Chroma front-end of the range stage. */
+
+/* RGBtoYCoCg (EC.cpp:53-67) over the image: Image::ConvertToRGB2YCoCg(true), Image.cpp:285-321.  C `/`: truncation. */
+void yko_rgb_to_ycocg(yko_ctx* c, int32_t* oY, int32_t* oCo, int32_t* oCg) {
+    size_t n = (size_t)c->w * c->h;
+    for (size_t i = 0; i < n; i++) {
+        int R = c->src[0][i], G = c->src[1][i], B = c->src[2][i];
+        int Co = R - B;
+        int tmp = B + Co / 2;
+        int Cg = G - tmp;
+        oY[i] = tmp + Cg / 2; oCo[i] = Co / 2; oCg[i] = Cg / 2;
+    }
+}
+
+/* Plane::SampleDown (Plane.cpp:278-369).  mode = EDownSample (framework.h:60-66): 0 NEAREST_TL, 1 NEAREST_BR,
+ * 2 AVERAGE_BOX, 3 MAX_BOX, 4 MIN_BOX.  dst is (halfX ? w/2 : w) x (halfY ? h/2 : h).  The reference loads the four
+ * source samples of every output whatever the mode; the combinations whose RESULT depends on a sample outside the
+ * plane (NEAREST_BR / MAX_BOX / MIN_BOX with one axis only) are outside the parity domain: returns -1. */
+int yko_sample_down(const int32_t* src, int w, int h, int halfX, int halfY, int mode, int32_t* dst) {
+    if (mode < 0 || mode > 4 || (w & 1) || (h & 1)) return -1;
+    if ((mode == 1 || mode == 3 || mode == 4) && !(halfX && halfY)) return -1;
+    int stepX = halfX ? 2 : 1, stepY = halfY ? 2 : 1;
+    int strideDst = halfX ? w / 2 : w;
+    for (int y = 0; y < h; y += stepY)
+        for (int x = 0; x < w; x += stepX) {
+            size_t idx = x + (size_t)y * w;
+            int A = src[idx];
+            int v = A;
+            if (mode == 2) {
+                if (halfX && halfY) v = (A + src[idx + 1] + src[idx + w] + src[idx + 1 + w]) / 4;
+                else if (halfX) v = (A + src[idx + 1]) / 2;
+                else if (halfY) v = (A + src[idx + w]) / 2;
+            } else if (mode != 0) {                                  /* both axes halved here */
+                int B = src[idx + 1], C = src[idx + w], D = src[idx + 1 + w];
+                if (mode == 1) v = D;
+                else if (mode == 3) { int a = A > B ? A : B, b = C > D ? C : D; v = a > b ? a : b; }
+                else { int a = A < B ? A : B, b = C < D ? C : D; v = a < b ? a : b; }
+            }
+            dst[(size_t)(y >> (halfY ? 1 : 0)) * strideDst + (x >> (halfX ? 1 : 0))] = v;
+        }
+    return 0;
+}
+
+/* DynamicTileEncode (EC.cpp:4365-4602) with LeftRightOrder (framework.h:228-256), GetTileEncode_Y (EC.cpp:1214-1221),
+ * Plane::GetMinMax_Y (Plane.cpp:489-587), GetTileDynamic_Y (EC.cpp:747-1212), on any plane `src` of pw x ph samples:
+ * the full-resolution planes (pw == w) or a SampleDown'ed chroma plane (halfX / halfY).  Two validity rules coexist for
+ * the reduced planes, as in the reference: the min/max of a block runs over "any of the covered mask pixels"
+ * (Plane.cpp:528-555, whose row stride is the REDUCED plane's width - kept as is), the coding over "all of them"
+ * (EC.cpp:831-861).  isChroma = isCo | isCg: blocks with a negative minimum are written back minus 128 (EC.cpp:4441). */
+int yko_range_dyn_plane(yko_ctx* c, const int32_t* src, int pw, int ph, int mode3BitOnly, int isChroma, int halfX, int halfY,
+                        uint8_t* nibbles, int* nNibbles, uint16_t* defs, int* nDefs, int32_t* dst, int constraint[4]) {
+    int W = c->w;                                                                   /* validPixel->GetWidth() */
+    int shX = halfX ? 1 : 0, shY = halfY ? 1 : 0;
+    const int32_t* mask = c->mipmapMask; const int32_t* smooth = c->smoothMap;
     int cx = (c->boundX0 >> 3) << 3, cy = (c->boundY0 >> 3) << 3;                   /* EC.cpp:4386-4391 */
     int cw = (((c->boundX1 + 7) >> 3) << 3) - cx, chh = (((c->boundY1 + 7) >> 3) << 3) - cy;
+    if (halfX) { cx >>= 1; cw >>= 1; }                                              /* EC.cpp:4393-4401 */
+    if (halfY) { cy >>= 1; chh >>= 1; }
     constraint[0] = cx; constraint[1] = cy; constraint[2] = cw; constraint[3] = chh;
-    size_t maxNib = (size_t)(w / 8) * (h / 8) * 32;
+    size_t maxNib = (size_t)(pw / 8) * (ph / 8) * 32;
     memset(nibbles, 0, maxNib);                                                     /* EC.cpp:4422 */
     int indexGlobal = 0, nd = 0;
     int x = cx - 8, y = cy;                                                         /* LeftRightOrder::Start */
@@ -354,19 +404,27 @@ int yko_range_dyn(yko_ctx* c, int plane, int mode3BitOnly, uint8_t* nibbles, int
         int valid = y < cy + chh;                                                   /* framework.h:239-255 */
         if (valid) {
             x += 8;
-            if (x >= cx + cw) { x = cx; y += 8; valid = y < h; }
+            if (x >= cx + cw) { x = cx; y += 8; valid = y < ph; }
         }
         if (!valid) break;
         int rw = (x + 8 > cw) ? (x % 8) : 8;
         int rh = (y + 8 > chh) ? (y % 8) : 8;
         /* GetMinMax_Y, Plane.cpp:489-587 (rect clipped to the plane) */
         int mn = 99999999, mx = -99999999, any = 0;
-        int maxY = y + rh > h ? h : y + rh, maxX = x + rw > w ? w : x + rw;
+        int maxY = y + rh > ph ? ph : y + rh, maxX = x + rw > pw ? pw : x + rw;
         for (int yy = y; yy < maxY; yy++)
             for (int xx = x; xx < maxX; xx++) {
-                size_t i = xx + (size_t)yy * w;
-                if (c->mipmapMask[i] && !c->smoothMap[i]) {
-                    int V = src[i];
+                size_t vi = ((size_t)xx << shX) + (size_t)(yy << shY) * pw;        /* `w` of the sampled plane, Plane.cpp:516 */
+                int ok;
+                if (!halfX && !halfY) ok = mask[vi] && !smooth[vi];
+                else {
+                    int hasGrad = smooth[vi] != 0, a = mask[vi] != 0, b, cc, d;
+                    if (halfX && halfY) { b = mask[vi + 1] != 0; cc = mask[vi + pw] != 0; d = mask[vi + pw + 1] != 0; ok = !hasGrad && (a | b | cc | d); }
+                    else if (halfX) { b = mask[vi + 1] != 0; ok = !hasGrad && (a | b); }
+                    else { b = mask[vi + pw] != 0; ok = !hasGrad && (a | b); }
+                }
+                if (ok) {
+                    int V = src[xx + (size_t)yy * pw];
                     if (V < mn) mn = V;
                     if (V > mx) mx = V;
                     any = 1;
@@ -380,7 +438,7 @@ int yko_range_dyn(yko_ctx* c, int plane, int mode3BitOnly, uint8_t* nibbles, int
         float bestErr = 99999999.0f;
         int b6 = 0, r7 = 0;
         int bT[64], bC[64];
-        for (int k = 0; k < 64; k++) bC[k] = 0;
+        for (int k = 0; k < 64; k++) { bC[k] = 0; best[k] = -999; bestCode[k] = 0; }
         for (int mode = mode3BitOnly ? 3 : 0; mode < 6; mode++) {
             int lut[16];
             int count = yko_dyn_table(mn, mx, mode, lut, &b6, &r7);
@@ -388,9 +446,17 @@ int yko_range_dyn(yko_ctx* c, int plane, int mode3BitOnly, uint8_t* nibbles, int
             for (int k = 0; k < 64; k++) bT[k] = -999;
             for (int yy = 0; yy < rh; yy++)
                 for (int xx = 0; xx < rw; xx++) {
-                    size_t i = (xx + x) + (size_t)(yy + y) * w;
-                    if (!(c->mipmapMask[i] && !c->smoothMap[i])) continue;          /* EC.cpp:830 */
-                    int vo = src[i] + (useSigned ? 128 : 0);
+                    size_t i = ((size_t)(xx + x) << shX) + (size_t)((yy + y) << shY) * W;
+                    int ok;                                                         /* EC.cpp:826-861 */
+                    if (!halfX && !halfY) ok = mask[i] && !smooth[i];
+                    else {
+                        int hasGrad = smooth[i] != 0, a = mask[i] != 0, b, cc, d;
+                        if (halfX && halfY) { b = mask[i + 1] != 0; cc = mask[i + W] != 0; d = mask[i + W + 1] != 0; ok = !hasGrad && (a & b & cc & d); }
+                        else if (halfX) { b = mask[i + 1] != 0; ok = !hasGrad && (a & b); }
+                        else { b = mask[i + W] != 0; ok = !hasGrad && (a & b); }
+                    }
+                    if (!ok) continue;
+                    int vo = src[(xx + x) + (size_t)(yy + y) * pw] + (useSigned ? 128 : 0);
                     int minDiff = 99999, found = 0, vfound = 0;
                     for (int n = 0; n < count; n++) {                               /* EC.cpp:873-881 */
                         int d = abs(lut[n] - vo);
@@ -405,6 +471,7 @@ int yko_range_dyn(yko_ctx* c, int plane, int mode3BitOnly, uint8_t* nibbles, int
             }
         }
         int valueCount = 0;
+        int offset = isChroma ? (useSigned ? -128 : 0) : 0;                         /* EC.cpp:4441-4442 */
         for (int yy = 0; yy < rh; yy++)
             for (int xx = 0; xx < rw; xx++) {                                       /* EC.cpp:1174-1190 */
                 int v = best[xx + (yy << 3)];
@@ -412,11 +479,16 @@ int yko_range_dyn(yko_ctx* c, int plane, int mode3BitOnly, uint8_t* nibbles, int
                     if (indexGlobal & 1) nibbles[indexGlobal >> 1] |= (uint8_t)(bestCode[xx + (yy << 3)] << 4);
                     else nibbles[indexGlobal >> 1] |= (uint8_t)bestCode[xx + (yy << 3)];
                     indexGlobal++; valueCount++;
-                    if (dst) dst[(xx + x) + (size_t)(yy + y) * w] = v;              /* EC.cpp:4448-4457 (offset 0 for Y/RGB) */
+                    if (dst) dst[((size_t)(xx + x) << shX) + ((size_t)(yy + y) << shY) * W] = v + offset;   /* EC.cpp:4444-4502 */
                 }
             }
         if (valueCount) defs[nd++] = (uint16_t)((bestMode << 13) | (r7 << 7) | b6); /* EC.cpp:4437; YAIK_private.h:358 */
     }
     *nNibbles = indexGlobal; *nDefs = nd;
     return 0;
+}
+
+int yko_range_dyn(yko_ctx* c, int plane, int mode3BitOnly, uint8_t* nibbles, int* nNibbles,
+                  uint16_t* defs, int* nDefs, int32_t* dst, int constraint[4]) {
+    return yko_range_dyn_plane(c, c->src[plane], c->w, c->h, mode3BitOnly, 0, 0, 0, nibbles, nNibbles, defs, nDefs, dst, constraint);
 }

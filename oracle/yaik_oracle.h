@@ -45,6 +45,15 @@ int yko_range1d(yko_ctx* c, int plane, uint8_t* idx, int* idxBytes, uint8_t* typ
 int yko_range_dyn(yko_ctx* c, int plane, int mode3BitOnly, uint8_t* nibbles, int* nNibbles,
                   uint16_t* defs, int* nDefs, int32_t* dst, int constraint[4]);
 
+/* Chroma front-end: Image::ConvertToRGB2YCoCg(true) (Image.cpp:285-321, RGBtoYCoCg EC.cpp:53-67),
+ * Plane::SampleDown (Plane.cpp:278-369; mode = EDownSample 0 NEAREST_TL, 1 NEAREST_BR, 2 AVERAGE_BOX, 3 MAX_BOX,
+ * 4 MIN_BOX; -1 for the combinations whose result reads outside the plane in the reference), and DynamicTileEncode on
+ * any plane: the Y plane, or a chroma plane reduced by SampleDown (isChroma = isCo | isCg, halfX, halfY). */
+void yko_rgb_to_ycocg(yko_ctx* c, int32_t* oY, int32_t* oCo, int32_t* oCg);
+int  yko_sample_down(const int32_t* src, int w, int h, int halfX, int halfY, int mode, int32_t* dst);
+int  yko_range_dyn_plane(yko_ctx* c, const int32_t* src, int pw, int ph, int mode3BitOnly, int isChroma, int halfX, int halfY,
+                         uint8_t* nibbles, int* nNibbles, uint16_t* defs, int* nDefs, int32_t* dst, int constraint[4]);
+
 /* State planes for comparison with the reference's: 0 smoothMap, 1 mipmapMask, 2..4 mapSmoothTile[c]
  * (w*h), 5..7 mappedRGB[c] ((w+1)*(h+1)), 8..10 recon/testOutput[c] (w*h). */
 const int32_t* yko_state_plane(yko_ctx* c, int which);

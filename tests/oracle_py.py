@@ -40,7 +40,7 @@ def lib():
         L.yko_destroy.argtypes = [C.c_void_p]
         L.yko_state_plane.restype = C.POINTER(C.c_int32)
         L.yko_state_plane.argtypes = [C.c_void_p, C.c_int]
-        for f in ("yko_alpha_reject", "yko_gradient_pass", "yko_range1d", "yko_range_dyn", "yko_dyn_table"):
+        for f in ("yko_alpha_reject", "yko_gradient_pass", "yko_range1d", "yko_range_dyn", "yko_dyn_table", "yko_sample_down", "yko_range_dyn_plane"):
             getattr(L, f).restype = C.c_int
         _lib = L
     return _lib
@@ -109,6 +109,35 @@ class Oracle:
         assert rc == 0
         return dict(nibbles=nib[:(nn.value + 1) // 2].copy(), n_nibbles=nn.value, defs=defs[:nd.value].copy(), dst=dst,
                     constraint=list(cons))
+
+    def chroma(self, cfg=(1, 0, 1, 0), modes=(2, 2), dst_fill=-1000):
+        """The chroma pipeline of Convert() (EC.cpp:9539-9545): RGB -> YCoCg, SampleDown of Co / Cg as configured
+        (cfg = halfCoW, halfCoH, halfCgW, halfCgH; modes = EDownSample of Co, Cg), DynamicTileEncode of Y (4 bit allowed),
+        Co (4 bit allowed) and Cg (3 bit only).  Returns the planes and the three coded streams."""
+        h, w = self.h, self.w
+        Y = np.zeros((h, w), np.int32); Co = np.zeros((h, w), np.int32); Cg = np.zeros((h, w), np.int32)
+        lib().yko_rgb_to_ycocg(C.c_void_p(self.ctx), _p(Y), _p(Co), _p(Cg))
+        work = []
+        for src, hx, hy, mode in ((Co, cfg[0], cfg[1], modes[0]), (Cg, cfg[2], cfg[3], modes[1])):
+            if hx or hy:
+                d = np.zeros((h // 2 if hy else h, w // 2 if hx else w), np.int32)
+                assert lib().yko_sample_down(_p(src), w, h, int(hx), int(hy), int(mode), _p(d)) == 0
+            else:
+                d = src.copy()
+            work.append(d)
+        out = dict(Y=Y, Co=Co, Cg=Cg, workCo=work[0], workCg=work[1], coded=[])
+        for src, m3, chroma, hx, hy in ((Y, 0, 0, 0, 0), (work[0], 0, 1, cfg[0], cfg[1]), (work[1], 1, 1, cfg[2], cfg[3])):
+            ph, pw = src.shape
+            nt = (pw // 8) * (ph // 8)
+            nib = np.zeros(nt * 32 + 8, np.uint8); defs = np.zeros(nt + 8, np.uint16)
+            dst = np.full((h, w), dst_fill, np.int32)
+            nn, nd = C.c_int(), C.c_int(); cons = (C.c_int * 4)()
+            rc = lib().yko_range_dyn_plane(C.c_void_p(self.ctx), _p(src), pw, ph, m3, chroma, int(hx), int(hy), _p(nib), C.byref(nn),
+                                           _p(defs), C.byref(nd), _p(dst), cons)
+            assert rc == 0
+            out["coded"].append(dict(nibbles=nib[:(nn.value + 1) // 2].copy(), n_nibbles=nn.value, defs=defs[:nd.value].copy(), dst=dst,
+                                     constraint=list(cons)))
+        return out
 
     def state(self, which):
         n = (self.w + 1) * (self.h + 1) if 5 <= which <= 7 else self.w * self.h

@@ -86,3 +86,41 @@ def test_dyn_tables_match_reference_for_all_min_max():
                 assert len(lut) == (16 if mode < 3 else 8)
                 assert 0 <= b < 64 and 0 <= r < 128
                 assert all(lut[i] <= lut[i + 1] for i in range(len(lut) - 1))
+
+
+CHROMA_CASES = [
+    # image, preceding stages, (halfCoW, halfCoH, halfCgW, halfCgH), (EDownSample Co, Cg)
+    ("synth128_rgb", ("grad",), (1, 0, 1, 0), (2, 2)),            # the CLI's configuration (ImageEncoder.cpp:175-181)
+    ("synth256_rgba", ("alpha", "grad"), (1, 1, 1, 1), (2, 2)),    # quarter-size chroma, alpha holes
+    ("alpha_island128", ("alpha", "grad"), (1, 0, 0, 1), (2, 2)),  # one axis each, bound box smaller than the image
+    ("patchy128", ("grad",), (0, 0, 1, 1), (2, 0)),                # full-size Co, nearest Cg
+    ("alpha_island256", ("alpha", "grad"), (1, 1, 1, 1), (3, 4)),  # max / min box
+    ("noise64", (), (1, 0, 1, 0), (2, 2)),                         # no gradient stage before (all pixels coded)
+    ("alpha_corner_only", ("alpha", "grad"), (1, 1, 1, 0), (1, 2)),
+]
+
+
+def check_chroma(got, ref):
+    """got: Oracle.chroma()-shaped dict; ref: records of the reference harness."""
+    for k in ("Y", "Co", "Cg", "workCo", "workCg"):
+        assert np.array_equal(np.asarray(got[k]).ravel(), ref["yc." + k]), k
+    for n in range(3):
+        r = got["coded"][n]
+        assert r["constraint"] == list(ref[f"yc.hdr{n}"][:4]), n
+        assert np.array_equal(r["defs"], ref[f"yc.defs{n}"]), n
+        assert np.array_equal(r["nibbles"], ref[f"yc.nibbles{n}"]), n
+        assert np.array_equal(np.asarray(r["dst"]).ravel(), ref[f"yc.dst{n}"]), n
+
+
+@pytest.mark.parametrize("name,pre,cfg,modes", CHROMA_CASES)
+def test_oracle_chroma_pipeline_matches_reference(name, pre, cfg, modes):
+    planes, _ = cases.SMALL_CASES[name]()
+    arg = "chroma=%d%d%d%d:%d%d" % (*cfg, *modes)
+    ref = run_ref(planes, (*pre, arg))
+    o = Oracle(planes)
+    if "alpha" in pre:
+        o.alpha()
+    if "grad" in pre:
+        o.gradient_cascade()
+    check_chroma(o.chroma(cfg, modes), ref)
+    o.close()
