@@ -143,6 +143,26 @@ int  yk_range1d(yk_ctx* ctx, int slot, int plane, uint8_t* idx, int idxCap, int*
 int  yk_range_dyn(yk_ctx* ctx, int slot, int plane, int mode3BitOnly, uint8_t* nibbles, int nibCap, int* nNibbles,
                   uint16_t* defs, int defsCap, int* nDefs, int constraint[4], int32_t* dst);
 
+/* Chroma front-end of the range stage (the pipeline Convert() holds at EC.cpp:9539-9545):
+ *
+ * yk_chroma_prepare = EncoderContext::convRGB2YCoCg(true) + chromaReduction() (EC.cpp:2766-2782), i.e.
+ *   Image::ConvertToRGB2YCoCg (Image.cpp:285-321, RGBtoYCoCg EC.cpp:53-67) and Plane::SampleDown (Plane.cpp:278-369)
+ *   of Co and of Cg, in one kernel over the slot's colour planes.  half = {halfCoW, halfCoH, halfCgW, halfCgH}
+ *   (EncoderContext.h:265-271; the CLI sets {1,0,1,0}, ImageEncoder.cpp:175-181); downMode = EDownSample of Co, Cg
+ *   (framework.h:60-66: 0 NEAREST_TL, 1 NEAREST_BR, 2 AVERAGE_BOX, 3 MAX_BOX, 4 MIN_BOX).  NEAREST_BR / MAX_BOX /
+ *   MIN_BOX with ONE axis halved read past the plane in the reference: YK_ERR_UNSUPPORTED.  The planes stay on the device.
+ * yk_chroma_plane: which = 0 Y (YCoCgImg plane 0), 1 workCo, 2 workCg; out may be NULL to ask for the size only.
+ * yk_range_dyn_chroma = DynamicTileEncode(mode3BitOnly, Y | workCo | workCg, dst, isCo, isCg, isHalfX, isHalfY)
+ *   (EC.cpp:4365-4503) with the flags that belong to `which`: the constraint box is halved on the reduced axes
+ *   (EC.cpp:4393-4401), both validity rules of the reduced planes are the reference's (min/max: Plane.cpp:528-555 with
+ *   its row stride, coding: EC.cpp:831-861), chroma blocks with a negative minimum are written to dst minus 128 and
+ *   reduced planes land on dst (full size, w*h int32) at their top-left full-size position only (EC.cpp:4441-4502).
+ *   Convert() calls it with mode3BitOnly = 0, 0, 1 for Y, Co, Cg.  Needs w, h (and the reduced sizes) to be multiples of 8. */
+int  yk_chroma_prepare(yk_ctx* ctx, int slot, const int half[4], const int downMode[2]);
+int  yk_chroma_plane(yk_ctx* ctx, int slot, int which, int32_t* out, int* outW, int* outH);
+int  yk_range_dyn_chroma(yk_ctx* ctx, int slot, int which, int mode3BitOnly, uint8_t* nibbles, int nibCap, int* nNibbles,
+                         uint16_t* defs, int defsCap, int* nDefs, int constraint[4], int32_t* dst);
+
 /* Expands the compact device state into the reference's int32 state planes so later reference stages
  * (3D LUT search, debug PNGs) keep working: smoothMap, mapSmoothTile[3] (w*h each), mappedRGB[3]
  * ((w+1)*(h+1) each), mipmapMask, recon = testOutput planes (w*h each) — EncoderContext.h:300-323.

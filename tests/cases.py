@@ -93,3 +93,15 @@ SMALL_CASES = {
                                                _alpha_island(64, 64, 0, 0, 64, 64, [(16, 16, 48, 32)])), ALL),
     "alpha_corner_only": lambda: (_with_alpha(_patchy(64, 64, 29, 4, 3), _alpha_island(64, 64, 40, 40, 64, 64)), ALL),
 }
+
+
+# Chroma front-end: image, stages run before, (halfCoW, halfCoH, halfCgW, halfCgH), (EDownSample Co, Cg)
+CHROMA_CASES = [
+    ("synth128_rgb", ("grad",), (1, 0, 1, 0), (2, 2)),            # the CLI's configuration (ImageEncoder.cpp:175-181)
+    ("synth256_rgba", ("alpha", "grad"), (1, 1, 1, 1), (2, 2)),    # quarter-size chroma, alpha holes
+    ("alpha_island128", ("alpha", "grad"), (1, 0, 0, 1), (2, 2)),  # one axis each, bound box smaller than the image
+    ("patchy128", ("grad",), (0, 0, 1, 1), (2, 0)),                # full-size Co, nearest Cg
+    ("alpha_island256", ("alpha", "grad"), (1, 1, 1, 1), (3, 4)),  # max / min box
+    ("noise64", (), (1, 0, 1, 0), (2, 2)),                         # no gradient stage before (all pixels coded)
+    ("alpha_corner_only", ("alpha", "grad"), (1, 1, 1, 0), (1, 2)),
+]

@@ -21,12 +21,18 @@ static void recInts(const char* name, std::vector<int> v) { rec(name, 'i', v.dat
 
 int main(int argc, char** argv) {
     if (argc < 3) return 2;
-    bool doAlpha = false, doGrad = false, doR2 = false, doR1 = false, r1_3bit = false, prepare = true;
+    bool doAlpha = false, doGrad = false, doR2 = false, doR1 = false, r1_3bit = false, prepare = true, doChroma = false;
+    int chromaCfg[4] = { 1, 0, 1, 0 }, chromaModes[2] = { 2, 2 };
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         if (a == "alpha") doAlpha = true; else if (a == "grad") doGrad = true; else if (a == "r2") doR2 = true;
         else if (a == "r1") doR1 = true; else if (a == "r1_3bit") { doR1 = true; r1_3bit = true; }
         else if (a == "noprepare") prepare = false;
+        else if (a.rfind("chroma=", 0) == 0 && a.size() == 14) {                  // chroma=XYXY:MM, as oracle/ref_harness.cpp
+            doChroma = true;
+            for (int k = 0; k < 4; k++) chromaCfg[k] = a[7 + k] == '1';
+            chromaModes[0] = a[12] - '0'; chromaModes[1] = a[13] - '0';
+        }
     }
     FILE* fi = fopen(argv[1], "rb");
     char magic[4]; int hdr[3];
@@ -109,6 +115,30 @@ int main(int argc, char** argv) {
             snprintf(nm, sizeof nm, "r1.hdr%d", c);     recInts(nm, { d.constraint.x, d.constraint.y, d.constraint.w, d.constraint.h, (int)d.nibbles.size(), 1, 0, ret });
             snprintf(nm, sizeof nm, "r1.dst%d", c);     recPlane(nm, dst);
             delete dst;
+        }
+    }
+    if (doChroma) {                                                                 // EC.cpp:9539-9545
+        ctx.halfCoW = chromaCfg[0]; ctx.halfCoH = chromaCfg[1]; ctx.halfCgW = chromaCfg[2]; ctx.halfCgH = chromaCfg[3];
+        ctx.downSampleCo = (EDownSample)chromaModes[0]; ctx.downSampleCg = (EDownSample)chromaModes[1];
+        ctx.convRGB2YCoCg(true);
+        ctx.chromaReduction();
+        if (!ctx.lastError) {
+            recPlane("yc.Y", ctx.YCoCgImg->GetPlane(0)); recPlane("yc.workCo", ctx.workCo); recPlane("yc.workCg", ctx.workCg);
+            Plane* src[3] = { ctx.YCoCgImg->GetPlane(0), ctx.workCo, ctx.workCg };
+            const bool m3[3] = { false, false, true }, isCo[3] = { false, true, false }, isCg[3] = { false, false, true };
+            const bool hx[3] = { false, ctx.halfCoW, ctx.halfCgW }, hy[3] = { false, ctx.halfCoH, ctx.halfCgH };
+            for (int c = 0; c < 3; c++) {
+                Plane* dst = new Plane(W, H);
+                BoundingBox all = dst->GetRect(); dst->Fill(all, -1000);
+                int ret = ctx.DynamicTileEncode(m3[c], src[c], dst, isCo[c], isCg[c], hx[c], hy[c]);
+                auto& d = ctx.lastDynamic;
+                char nm[32];
+                snprintf(nm, sizeof nm, "yc.defs%d", c);    rec(nm, 'H', d.tileDefs.data(), d.tileDefs.size());
+                snprintf(nm, sizeof nm, "yc.nibbles%d", c); rec(nm, 'B', d.nibbles.data(), d.nibbles.size());
+                snprintf(nm, sizeof nm, "yc.hdr%d", c);     recInts(nm, { d.constraint.x, d.constraint.y, d.constraint.w, d.constraint.h, (int)d.nibbles.size(), 1, 0, ret });
+                snprintf(nm, sizeof nm, "yc.dst%d", c);     recPlane(nm, dst);
+                delete dst;
+            }
         }
     }
     recInts("meta", { W, H, NP, ctx.lastError });

@@ -25,6 +25,10 @@ GOLDEN_CASES = ["ramp64_a2", "patchy128", "patchy_72x40", "noise_delta1", "noise
                 "mip8_rgb", "mip4_rgb", "alpha_island128", "alpha_corner_only", "synth256_rgba", "synth256_rgb_3bit", "r1_signed96"]
 
 
+# chroma front-end fixtures: indices into cases.CHROMA_CASES (the CLI configuration, quarter size with alpha, one axis each)
+CHROMA_GOLDEN = [0, 1, 2]
+
+
 def digest(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -45,6 +49,21 @@ def main():
                 out[k] = v
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, planes.shape, sorted(k for k in out if not k.startswith("sha256"))[:6], "...")
+    for k in CHROMA_GOLDEN:
+        name, pre, cfg, modes = cases.CHROMA_CASES[k]
+        planes, _ = cases.SMALL_CASES[name]()
+        stages = (*pre, "chroma=%d%d%d%d:%d%d" % (*cfg, *modes))
+        ref = run_ref(planes, stages)
+        out = {"input": planes.astype(np.uint8), "stages": np.array(list(stages))}
+        for key, v in ref.items():
+            if key.startswith("time."):
+                continue
+            if key.startswith("state.") or key == "alpha.mask" or key.startswith("yc.dst") or key in ("yc.Y", "yc.Co", "yc.Cg", "yc.workCo", "yc.workCg"):
+                out["sha256:" + key] = np.array(digest(v.astype(np.int32)))
+            else:
+                out[key] = v
+        np.savez_compressed(os.path.join(HERE, "chroma_" + name + ".npz"), **out)
+        print("chroma_" + name, planes.shape, stages)
 
 
 if __name__ == "__main__":

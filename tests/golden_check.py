@@ -23,7 +23,15 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(np.asarray(a, dtype=np.int32)).tobytes()).hexdigest()
 
 
-def check(g, stages, *, alpha, gradient_pass, range1d, range_dyn, state=None):
+def chroma_args(stages):
+    """(cfg, modes) of a "chroma=XYXY:MM" stage, or None."""
+    for s in stages:
+        if s.startswith("chroma="):
+            return tuple(int(ch) for ch in s[7:11]), tuple(int(ch) for ch in s[12:14])
+    return None
+
+
+def check(g, stages, *, alpha, gradient_pass, range1d, range_dyn, state=None, chroma=None):
     """The callables return dicts shaped like oracle_py.Oracle's methods."""
     if "alpha" in stages:
         a = alpha()
@@ -60,3 +68,15 @@ def check(g, stages, *, alpha, gradient_pass, range1d, range_dyn, state=None):
             assert np.array_equal(r["nibbles"], g[f"r1.nibbles{n}"]), n
             assert r["constraint"] == list(g[f"r1.hdr{n}"][:4])
             assert sha(r["dst"]) == str(g[f"sha256:r1.dst{n}"])
+    ca = chroma_args(stages)
+    if ca is not None:
+        assert chroma is not None, "fixture holds a chroma stage"
+        r = chroma(*ca)
+        for k in ("Y", "workCo", "workCg"):
+            assert sha(r[k]) == str(g["sha256:yc." + k]), k
+        for n in range(3):
+            d = r["coded"][n]
+            assert d["constraint"] == list(g[f"yc.hdr{n}"][:4]), n
+            assert np.array_equal(d["defs"], g[f"yc.defs{n}"]), n
+            assert np.array_equal(d["nibbles"], g[f"yc.nibbles{n}"]), n
+            assert sha(d["dst"]) == str(g[f"sha256:yc.dst{n}"]), n

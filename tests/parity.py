@@ -68,3 +68,29 @@ def check_image(ctx: "capi.Context", planes: np.ndarray, stages, *, fused=True, 
             _eq(got["nibbles"], want["nibbles"], f"R1 nibbles plane {n}")
             _eq(got["dst"], want["dst"], f"R1 dst plane {n}")
     o.close()
+
+
+def check_chroma(ctx: "capi.Context", planes: np.ndarray, pre, cfg, modes, slot=0):
+    """The chroma front-end (yk_chroma_prepare + yk_range_dyn_chroma x3) after the stages in `pre`, against the oracle."""
+    c, h, w = planes.shape
+    o = Oracle(planes)
+    ctx.set_image(planes, slot)
+    st = (capi.STAGE_ALPHA if ("alpha" in pre and c == 4) else 0) | (capi.STAGE_GRADIENT if "grad" in pre else 0)
+    if st:
+        ctx.analyze(st, slot0=slot)
+    if "alpha" in pre and c == 4:
+        o.alpha()
+    if "grad" in pre:
+        o.gradient_cascade()
+    want = o.chroma(cfg, modes)
+    got = ctx.chroma(cfg, modes, slot=slot)
+    for k in ("Y", "workCo", "workCg"):
+        _eq(got[k], want[k], "chroma plane " + k)
+    for n in range(3):
+        g, wnt = got["coded"][n], want["coded"][n]
+        assert g["constraint"] == wnt["constraint"], (n, g["constraint"], wnt["constraint"])
+        _eq(g["defs"], wnt["defs"], f"chroma R1 defs {n}")
+        assert g["n_nibbles"] == wnt["n_nibbles"]
+        _eq(g["nibbles"], wnt["nibbles"], f"chroma R1 nibbles {n}")
+        _eq(g["dst"], wnt["dst"], f"chroma R1 dst {n}")
+    o.close()

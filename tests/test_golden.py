@@ -16,6 +16,7 @@ def test_oracle_matches_golden(name):
         gradient_pass=o.gradient_pass,
         range1d=o.range1d,
         range_dyn=lambda n, m3: o.range_dyn(n, mode3=m3, want_dst=True),
+        chroma=lambda cfg, modes: o.chroma(cfg, modes),
         state=lambda: dict(smoothMap=o.state(0), mipmapMask=o.state(1), mapSmoothTile=[o.state(2 + i) for i in range(3)],
                            mappedRGB=[o.state(5 + i) for i in range(3)], recon=[o.state(8 + i) for i in range(3)]))
     o.close()

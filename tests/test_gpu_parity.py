@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import cases
-from parity import check_image
+from parity import check_chroma, check_image
 from yaik_b200 import capi
 from yaik_b200.synth import make_image, mip_chain, SEED_BASE
 
@@ -46,7 +46,24 @@ def test_cuda_matches_golden_vectors_of_the_reference(ctx, name):
         st = (capi.STAGE_ALPHA if ("alpha" in stages and planes.shape[0] == 4) else 0) | capi.STAGE_GRADIENT | (capi.STAGE_RANGE1D if "r2" in stages else 0)
         ctx.analyze(st)
     golden_check.check(g, stages, alpha=ctx.alpha_reject, gradient_pass=ctx.gradient_pass, range1d=ctx.range1d,
-                       range_dyn=lambda n, m3: ctx.range_dyn(n, mode3=m3, want_dst=True), state=ctx.download_state)
+                       range_dyn=lambda n, m3: ctx.range_dyn(n, mode3=m3, want_dst=True), state=ctx.download_state,
+                       chroma=lambda cfg, modes: ctx.chroma(cfg, modes))
+
+
+@pytest.mark.parametrize("name,pre,cfg,modes", cases.CHROMA_CASES)
+def test_chroma_front_end(ctx, name, pre, cfg, modes):
+    """RGB -> YCoCg, SampleDown, DynamicTileEncode of Y / reduced Co / Cg against the oracle."""
+    planes, _ = cases.SMALL_CASES[name]()
+    check_chroma(ctx, planes, pre, cfg, modes)
+
+
+def test_chroma_front_end_2048_rgba(lib):
+    """The bench texture through the CLI's chroma configuration (half-width Co and Cg, box average)."""
+    c = capi.Context(2048, 2048, planes=4, slots=1, lib=lib)
+    try:
+        check_chroma(c, make_image(2048, 2048, 4, SEED_BASE + 1), ("alpha", "grad"), (1, 0, 1, 0), (2, 2))
+    finally:
+        c.close()
 
 
 def test_config0_512_rgb(ctx):

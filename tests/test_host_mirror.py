@@ -42,6 +42,9 @@ def compare(name, binary, extra=()):
         gradient_pass=grad,
         range1d=lambda n: dict(idx=r[f"r2.idx{n}"], type=r[f"r2.type{n}"]),
         range_dyn=lambda n, m3: dict(defs=r[f"r1.defs{n}"], nibbles=r[f"r1.nibbles{n}"], constraint=list(r[f"r1.hdr{n}"][:4]), dst=r[f"r1.dst{n}"]),
+        chroma=lambda cfg, modes: dict(Y=r["yc.Y"], workCo=r["yc.workCo"], workCg=r["yc.workCg"],
+                                       coded=[dict(defs=r[f"yc.defs{n}"], nibbles=r[f"yc.nibbles{n}"], constraint=list(r[f"yc.hdr{n}"][:4]),
+                                                   dst=r[f"yc.dst{n}"]) for n in range(3)]),
         state=lambda: dict(smoothMap=r["state.smoothMap"], mipmapMask=r["state.mipmapMask"],
                            mapSmoothTile=[r[f"state.mapSmoothTile{i}"] for i in range(3)],
                            mappedRGB=[r[f"state.mappedRGB{i}"] for i in range(3)], recon=[r[f"state.recon{i}"] for i in range(3)]))
@@ -54,7 +57,7 @@ def emu_bin():
     return EMU_BIN
 
 
-@pytest.mark.parametrize("name", ["patchy_72x40", "mip32_rgba", "alpha_island128", "r1_signed96"])
+@pytest.mark.parametrize("name", ["patchy_72x40", "mip32_rgba", "alpha_island128", "r1_signed96", "chroma_synth128_rgb", "chroma_alpha_island128"])
 def test_mirror_logic_on_emulated_library(emu_bin, name):
     compare(name, emu_bin)
 

@@ -8,7 +8,7 @@ import subprocess
 import pytest
 
 import cases
-from parity import check_image
+from parity import check_chroma, check_image
 from yaik_b200 import capi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -59,5 +59,15 @@ def test_emulated_alternative_data_paths(emu_lib):
             keep.append(np.ascontiguousarray(planes, dtype=np.int32))
             return [keep[-1][i].ctypes.data for i in range(planes.shape[0])]
         paths_check.check_device_resident_planes(ctx, to_device)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("name,pre,cfg,modes", cases.CHROMA_CASES)
+def test_emulated_chroma_front_end(emu_lib, name, pre, cfg, modes):
+    planes, _ = cases.SMALL_CASES[name]()
+    ctx = capi.Context(256, 256, planes=4, slots=1, lib=emu_lib)
+    try:
+        check_chroma(ctx, planes, pre, cfg, modes)
     finally:
         ctx.close()

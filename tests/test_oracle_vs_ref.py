@@ -88,16 +88,7 @@ def test_dyn_tables_match_reference_for_all_min_max():
                 assert all(lut[i] <= lut[i + 1] for i in range(len(lut) - 1))
 
 
-CHROMA_CASES = [
-    # image, preceding stages, (halfCoW, halfCoH, halfCgW, halfCgH), (EDownSample Co, Cg)
-    ("synth128_rgb", ("grad",), (1, 0, 1, 0), (2, 2)),            # the CLI's configuration (ImageEncoder.cpp:175-181)
-    ("synth256_rgba", ("alpha", "grad"), (1, 1, 1, 1), (2, 2)),    # quarter-size chroma, alpha holes
-    ("alpha_island128", ("alpha", "grad"), (1, 0, 0, 1), (2, 2)),  # one axis each, bound box smaller than the image
-    ("patchy128", ("grad",), (0, 0, 1, 1), (2, 0)),                # full-size Co, nearest Cg
-    ("alpha_island256", ("alpha", "grad"), (1, 1, 1, 1), (3, 4)),  # max / min box
-    ("noise64", (), (1, 0, 1, 0), (2, 2)),                         # no gradient stage before (all pixels coded)
-    ("alpha_corner_only", ("alpha", "grad"), (1, 1, 1, 0), (1, 2)),
-]
+CHROMA_CASES = cases.CHROMA_CASES
 
 
 def check_chroma(got, ref):

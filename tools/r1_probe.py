@@ -20,3 +20,10 @@ for mode3 in (False, True):
             r = ctx.range_dyn(p, mode3=mode3)
     dt = (time.perf_counter() - t0) / N
     print(f"mode3BitOnly={mode3}: 3 planes {dt * 1e3:.3f} ms wall (kernels + D2H of {r['nibbles'].size} nibble bytes and {r['defs'].size} defs per plane)")
+# chroma front-end: yk_chroma_prepare + DynamicTileEncode of Y / half-width Co / half-width Cg (the CLI's configuration)
+for _ in range(2):
+    ctx.chroma((1, 0, 1, 0), (2, 2), planes=False)
+t0 = time.perf_counter()
+for _ in range(5):
+    ctx.chroma((1, 0, 1, 0), (2, 2), planes=False)
+print(f"chroma pipeline (prepare + 3 encodes, streams and dst planes downloaded): {(time.perf_counter() - t0) / 5 * 1e3:.3f} ms wall")

@@ -23,7 +23,7 @@ EXPORTS = [
     "yk_abi_version", "yk_error_string", "yk_last_cuda_error", "yk_device_count", "yk_create", "yk_destroy",
     "yk_set_stream", "yk_sync", "yk_set_analysis_ctas", "yk_sm_count", "yk_host_alloc", "yk_host_free", "yk_set_image", "yk_set_image_device", "yk_set_upload_format",
     "yk_device_plane", "yk_reset_state", "yk_reset_states", "yk_analyze", "yk_alpha_reject", "yk_prepare_quad_smooth",
-    "yk_gradient_pass", "yk_range1d", "yk_range_dyn", "yk_download_state", "yk_fetch_all", "yk_result_bytes", "yk_launch_count",
+    "yk_gradient_pass", "yk_range1d", "yk_range_dyn", "yk_chroma_prepare", "yk_chroma_plane", "yk_range_dyn_chroma", "yk_download_state", "yk_fetch_all", "yk_result_bytes", "yk_launch_count",
     "yk_profile", "yk_profile_read",
     "yk_strip_config", "yk_strip_halo_ptrs", "yk_strip_phase",
     "yk_ipc_export", "yk_ipc_open", "yk_ipc_close", "yk_copy_async", "yk_copy_to_host", "yk_copy_from_host",
@@ -95,6 +95,9 @@ def load_library(path: str | None = None):
     L.yk_range1d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.yk_range_dyn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+    L.yk_chroma_prepare.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.yk_chroma_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.yk_range_dyn_chroma.argtypes = L.yk_range_dyn.argtypes
     L.yk_download_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)]
     L.yk_result_bytes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
     L.yk_fetch_all.argtypes = [C.c_void_p, C.c_int, C.POINTER(Results)]
@@ -226,6 +229,32 @@ class Context:
         cons = (C.c_int * 4)()
         self._ck(self.L.yk_range_dyn(self.ctx, slot, plane, int(mode3), _p(nib), capn, C.byref(nn), _p(defs), nt + 8, C.byref(nd), cons, _p(dst)), "yk_range_dyn")
         return dict(nibbles=nib[:(nn.value + 1) // 2].copy(), n_nibbles=nn.value, defs=defs[:nd.value].copy(), dst=dst, constraint=list(cons))
+
+    def chroma(self, cfg=(1, 0, 1, 0), modes=(2, 2), slot=0, dst_fill=-1000, planes=True):
+        """The chroma pipeline of Convert() (EC.cpp:9539-9545): yk_chroma_prepare, then DynamicTileEncode of Y, workCo and
+        workCg with the reference's mode3BitOnly = 0, 0, 1.  cfg = halfCoW, halfCoH, halfCgW, halfCgH; modes = EDownSample."""
+        c, h, w = self.dims[slot]
+        half = (C.c_int * 4)(*[int(v) for v in cfg]); dm = (C.c_int * 2)(*[int(v) for v in modes])
+        self._ck(self.L.yk_chroma_prepare(self.ctx, slot, half, dm), "yk_chroma_prepare")
+        out = dict(coded=[])
+        for which, key in enumerate(("Y", "workCo", "workCg")):
+            pw, ph = C.c_int(), C.c_int()
+            self._ck(self.L.yk_chroma_plane(self.ctx, slot, which, None, C.byref(pw), C.byref(ph)), "yk_chroma_plane")
+            if planes:
+                a = np.zeros((ph.value, pw.value), np.int32)
+                self._ck(self.L.yk_chroma_plane(self.ctx, slot, which, _p(a), None, None), "yk_chroma_plane")
+                out[key] = a
+            nt = (pw.value // 8) * (ph.value // 8)
+            capn = nt * 32 + 8
+            nib = np.zeros(capn, np.uint8); defs = np.zeros(nt + 8, np.uint16)
+            dst = np.full((h, w), dst_fill, np.int32)
+            nn, nd = C.c_int(), C.c_int()
+            cons = (C.c_int * 4)()
+            self._ck(self.L.yk_range_dyn_chroma(self.ctx, slot, which, int(which == 2), _p(nib), capn, C.byref(nn), _p(defs), nt + 8, C.byref(nd),
+                                                cons, _p(dst)), "yk_range_dyn_chroma")
+            out["coded"].append(dict(nibbles=nib[:(nn.value + 1) // 2].copy(), n_nibbles=nn.value, defs=defs[:nd.value].copy(), dst=dst,
+                                     constraint=list(cons)))
+        return out
 
     def download_state(self, slot=0, recon=True):
         c, h, w = self.dims[slot]

@@ -64,6 +64,9 @@ struct YkSlotHost {
     bool pendingHarvest = false; // a run's header has not been copied back yet
     int  lastRunPasses = 0;      // bit p: pass p was in the last run; bit 8: alpha
     int  rangeErr = 0;
+    int32_t* chroma[3] = { nullptr, nullptr, nullptr };   // Y, workCo, workCg of the chroma front-end (allocated on first use)
+    int  chromaHalf[4] = { 0, 0, 0, 0 };
+    bool chromaReady = false;
     int  hdr[YK_HD_INTS];        // harvested copy: per-pass stats of the run that produced them, alpha box, R2 totals
     long long resultBytes[6] = { 0, 0, 0, 0, 0, 0 };
     // alpha results (host)
@@ -347,7 +350,7 @@ static int configure_slot(yk_ctx* c, int slot, int nPlanes, int w, int h) {
     s.d.imgH = h; s.d.y0 = 0; s.d.hasAbove = 0; s.d.hasBelow = 0; s.d.touchInTop = nullptr; s.d.touchInBottom = nullptr;
     s.d.latW = w / 4 + 1; s.d.latH = h / 4 + 1;
     for (int p = 0; p < 3; p++) s.d.rowBelow[p] = nullptr;
-    s.haveImage = true; s.dirty = true;
+    s.haveImage = true; s.dirty = true; s.chromaReady = false;
     return YK_OK;
 }
 
@@ -833,23 +836,29 @@ static int ensure_r1_lut(yk_ctx* c) {
     return YK_OK;
 }
 
-extern "C" int yk_range_dyn(yk_ctx* c, int slot, int plane, int mode3BitOnly, uint8_t* nibbles, int nibCap, int* nNibbles,
-                            uint16_t* defs, int defsCap, int* nDefs, int constraint[4], int32_t* dst) {
-    if (!slot_ok(c, slot) || plane < 0 || plane > 2) return YK_ERR_ARG;
+// DynamicTileEncode on one device plane (the slot's colour planes, or Y / reduced Co / Cg of the chroma front-end)
+static int range_dyn_impl(yk_ctx* c, int slot, const int32_t* src, int pw, int ph, int out, int mode3BitOnly, int chroma, int halfX, int halfY,
+                          uint8_t* nibbles, int nibCap, int* nNibbles, uint16_t* defs, int defsCap, int* nDefs, int constraint[4], int32_t* dst) {
     YkSlotHost& s = c->slots[slot];
-    if (!s.haveImage) return YK_ERR_STATE;
     const int w = s.d.w, h = s.d.h;
-    if ((w & 7) || (h & 7)) return YK_ERR_ARG;
-    CK(cudaSetDevice(c->device));
+    if ((pw & 7) || (ph & 7)) return YK_ERR_ARG;
     int rc;
     if ((rc = ensure_r1_lut(c))) return rc;
-    if ((rc = ensure_int32(c, slot))) return rc;
     int bound[4] = { 0, 0, w, h };                               // CheckMipmapMask: full image (EC.cpp:2784-2794)
     if (s.alphaRan) { if ((rc = alpha_finish(c, s))) return rc; memcpy(bound, s.bound, sizeof bound); }
-    const int cx = (bound[0] >> 3) << 3, cy = (bound[1] >> 3) << 3;              // EC.cpp:4386-4391
-    const int cw = (((bound[2] + 7) >> 3) << 3) - cx, ch = (((bound[3] + 7) >> 3) << 3) - cy;
-    if (constraint) { constraint[0] = cx; constraint[1] = cy; constraint[2] = cw; constraint[3] = ch; }
-    const int nBlocks = (cw >> 3) * (ch >> 3);
+    YkR1Args a;
+    memset(&a, 0, sizeof a);
+    a.src = src; a.pw = pw; a.ph = ph; a.shX = halfX ? 1 : 0; a.shY = halfY ? 1 : 0; a.chroma = chroma; a.mode3 = mode3BitOnly ? 1 : 0; a.out = out;
+    a.cx = (bound[0] >> 3) << 3; a.cy = (bound[1] >> 3) << 3;                      // EC.cpp:4386-4391
+    a.cw = (((bound[2] + 7) >> 3) << 3) - a.cx; a.ch = (((bound[3] + 7) >> 3) << 3) - a.cy;
+    if (halfX) { a.cx >>= 1; a.cw >>= 1; }                                          // EC.cpp:4393-4401
+    if (halfY) { a.cy >>= 1; a.ch >>= 1; }
+    if (constraint) { constraint[0] = a.cx; constraint[1] = a.cy; constraint[2] = a.cw; constraint[3] = a.ch; }
+    // LeftRightOrder (framework.h:228-256): full rows of the box, then the first block of the row below it if the plane has one
+    a.nbw = (a.cw + 7) >> 3;
+    const int rows = (a.ch + 7) >> 3;
+    a.nBlocks = a.nbw * rows;
+    if (a.nBlocks > 0 && a.cy + 8 * rows < ph) a.nBlocks += 1;
     if (s.pendingHarvest) { rc = fetch_hdr(c, s); if (rc && rc != YK_ERR_RANGE) return rc; }
     int32_t* dDst = nullptr;
     if (dst) {
@@ -858,24 +867,24 @@ extern "C" int yk_range_dyn(yk_ctx* c, int slot, int plane, int mode3BitOnly, ui
     }
     s.d.r1Dst = dDst; s.dirty = true;
     if ((rc = upload_slots(c, slot, 1))) return rc;
-    if (nBlocks > 0) {
+    if (a.nBlocks > 0) {
         CK(cudaMemsetAsync(s.d.r1Status, 0, r1_status_words(w, h) * sizeof(unsigned long long), c->stream));
-        yk_launch_range_dyn_encode(c->slotsDev, slot, plane, mode3BitOnly ? 1 : 0, cx, cy, cw, ch, nBlocks, c->lutDev, c->stream);
+        yk_launch_range_dyn_encode(c->slotsDev, slot, a, c->lutDev, c->stream);
         c->launches += 1;
     }
     CK(cudaGetLastError());
     int tot[2] = { 0, 0 };
-    if (nBlocks > 0) {
-        CK(cudaMemcpyAsync(&tot[0], s.d.hdr + YK_HD_R1_NIB0 + plane, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(&tot[1], s.d.hdr + YK_HD_R1_DEF0 + plane, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (a.nBlocks > 0) {
+        CK(cudaMemcpyAsync(&tot[0], s.d.hdr + YK_HD_R1_NIB0 + out, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&tot[1], s.d.hdr + YK_HD_R1_DEF0 + out, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
     const int nb = (tot[0] + 1) / 2;
     rc = YK_OK;
     if (nb > nibCap || tot[1] > defsCap) rc = YK_ERR_CAPACITY;
     if (!rc) {
-        if (nibbles && nb) CK(cudaMemcpyAsync(nibbles, s.d.r1Nib[plane], nb, cudaMemcpyDeviceToHost, c->stream));
-        if (defs && tot[1]) CK(cudaMemcpyAsync(defs, s.d.r1Defs[plane], (size_t)tot[1] * 2, cudaMemcpyDeviceToHost, c->stream));
+        if (nibbles && nb) CK(cudaMemcpyAsync(nibbles, s.d.r1Nib[out], nb, cudaMemcpyDeviceToHost, c->stream));
+        if (defs && tot[1]) CK(cudaMemcpyAsync(defs, s.d.r1Defs[out], (size_t)tot[1] * 2, cudaMemcpyDeviceToHost, c->stream));
         if (dst) CK(cudaMemcpyAsync(dst, dDst, (size_t)w * h * 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
@@ -884,6 +893,80 @@ extern "C" int yk_range_dyn(yk_ctx* c, int slot, int plane, int mode3BitOnly, ui
     if (nNibbles) *nNibbles = tot[0];
     if (nDefs) *nDefs = tot[1];
     return rc;
+}
+
+extern "C" int yk_range_dyn(yk_ctx* c, int slot, int plane, int mode3BitOnly, uint8_t* nibbles, int nibCap, int* nNibbles,
+                            uint16_t* defs, int defsCap, int* nDefs, int constraint[4], int32_t* dst) {
+    if (!slot_ok(c, slot) || plane < 0 || plane > 2) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_int32(c, slot))) return rc;
+    return range_dyn_impl(c, slot, s.d.plane[plane], s.d.w, s.d.h, plane, mode3BitOnly, 0, 0, 0, nibbles, nibCap, nNibbles, defs, defsCap, nDefs, constraint, dst);
+}
+
+// ---- chroma front-end ----------------------------------------------------------------
+extern "C" int yk_chroma_prepare(yk_ctx* c, int slot, const int half[4], const int downMode[2]) {
+    if (!slot_ok(c, slot) || !half || !downMode) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage) return YK_ERR_STATE;
+    const int w = s.d.w, h = s.d.h;
+    if ((w & 1) || (h & 1)) return YK_ERR_ARG;
+    for (int k = 0; k < 2; k++) {
+        const int hx = half[2 * k] != 0, hy = half[2 * k + 1] != 0, m = downMode[k];
+        if (m < 0 || m > 4) return YK_ERR_ARG;
+        // NEAREST_BR / MAX_BOX / MIN_BOX on one axis read the sample past the plane in the reference (Plane.cpp:297-356)
+        if ((hx != hy) && (m == 1 || m == 3 || m == 4)) return YK_ERR_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_int32(c, slot))) return rc;
+    for (int k = 0; k < 3; k++)
+        if (!s.chroma[k]) { if ((rc = dev_alloc(s, &s.chroma[k], (size_t)c->maxW * c->maxH))) return rc; }
+    YkChromaArgs a;
+    a.y = s.chroma[0]; a.co = s.chroma[1]; a.cg = s.chroma[2];
+    for (int k = 0; k < 4; k++) { a.half[k] = half[k] != 0; s.chromaHalf[k] = a.half[k]; }
+    a.mode[0] = downMode[0]; a.mode[1] = downMode[1];
+    if ((rc = upload_slots(c, slot, 1))) return rc;
+    yk_launch_chroma(c->slotsDev, slot, w, h, a, c->stream);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    s.chromaReady = true;
+    return YK_OK;
+}
+
+static void chroma_dims(const YkSlotHost& s, int which, int* pw, int* ph) {
+    const int hx = which ? s.chromaHalf[2 * (which - 1)] : 0, hy = which ? s.chromaHalf[2 * (which - 1) + 1] : 0;
+    *pw = hx ? s.d.w / 2 : s.d.w; *ph = hy ? s.d.h / 2 : s.d.h;
+}
+
+extern "C" int yk_chroma_plane(yk_ctx* c, int slot, int which, int32_t* out, int* outW, int* outH) {
+    if (!slot_ok(c, slot) || which < 0 || which > 2) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage || !s.chromaReady) return YK_ERR_STATE;
+    int pw, ph;
+    chroma_dims(s, which, &pw, &ph);
+    if (outW) *outW = pw;
+    if (outH) *outH = ph;
+    if (out) {
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemcpyAsync(out, s.chroma[which], (size_t)pw * ph * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return YK_OK;
+}
+
+extern "C" int yk_range_dyn_chroma(yk_ctx* c, int slot, int which, int mode3BitOnly, uint8_t* nibbles, int nibCap, int* nNibbles,
+                                   uint16_t* defs, int defsCap, int* nDefs, int constraint[4], int32_t* dst) {
+    if (!slot_ok(c, slot) || which < 0 || which > 2) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage || !s.chromaReady) return YK_ERR_STATE;
+    CK(cudaSetDevice(c->device));
+    int pw, ph;
+    chroma_dims(s, which, &pw, &ph);
+    const int hx = pw != s.d.w, hy = ph != s.d.h;
+    return range_dyn_impl(c, slot, s.chroma[which], pw, ph, which, mode3BitOnly, which != 0, hx, hy, nibbles, nibCap, nNibbles, defs, defsCap, nDefs, constraint, dst);
 }
 
 // ---- compat state download --------------------------------------------------------------------------------

@@ -108,8 +108,18 @@ void yk_launch_owner(const YkSlotDev* slotsDev, int slot0, int nSlots, int nPoin
 void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int gradGroups, int r2Groups, const YkRun& run, cudaStream_t st);
 void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t* smoothMap, int32_t* mipmapMask,
                      int32_t* mappedRGB, int32_t* recon0, int32_t* recon1, int32_t* recon2, cudaStream_t st);
-void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, int plane, int mode3, int cx, int cy, int cw, int ch,
-                                int nBlocks, const int* lutDev, cudaStream_t st);
+// DynamicTileEncode on one plane: the source samples, the (possibly halved) constraint box and the walk over it
+struct YkR1Args {
+    const int32_t* src; int pw, ph;      // plane coded: pw x ph int32 samples on the device
+    int shX, shY;                        // 1 = the plane is SampleDown'ed on that axis (isHalfX / isHalfY)
+    int chroma, mode3;                   // isCo | isCg; mode3BitOnly
+    int cx, cy, cw, ch;                  // constraint box in the plane's own coordinates (EC.cpp:4386-4401)
+    int nbw, nBlocks;                    // blocks per row of the walk; all blocks (rows * nbw + the extra one, see yk_r1_block)
+    int out;                             // index of r1Nib / r1Defs / header counters written
+};
+struct YkChromaArgs { int32_t *y, *co, *cg; int half[4]; int mode[2]; };
+void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, const YkR1Args& args, const int* lutDev, cudaStream_t st);
+void yk_launch_chroma(const YkSlotDev* slotsDev, int slot, int w, int h, const YkChromaArgs& args, cudaStream_t st);
 #ifdef __cplusplus
 }
 #endif

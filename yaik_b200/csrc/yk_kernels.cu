@@ -1,7 +1,9 @@
 // yaik_b200 — auxiliary sm_100a kernels of the YAIK encoder-analysis stage (the hot path is yk_analyze.cu + yk_emit.cu):
 //
 //   yk_k_state        expands the compact masks into the reference's int32 state planes (compat download).
-//   yk_k_r1_*         DynamicTileEncode (EC.cpp:4365-4503, 747-1212), LUT search at 3/4 bits per pixel.
+//   yk_k_r1_encode    DynamicTileEncode (EC.cpp:4365-4503, 747-1212), LUT search at 3/4 bits per pixel, on the colour planes
+//                     or on the Y / reduced Co / Cg planes of the chroma front-end.
+//   yk_k_chroma       RGB -> YCoCg + SampleDown of the chroma planes (Image.cpp:285-321, Plane.cpp:278-369).
 //
 // Reference line numbers are KLab/YAIK's encoder/EncoderContext.cpp ("EC.cpp") unless another file is named.
 #include "yk_device.h"
@@ -204,32 +206,66 @@ static __device__ int yk_block_exclusive(int v, int* sWarp, int& total) {
 #endif
 #define YK_R1_LUT_INTS 144
 
+// Validity of one full-resolution pixel as DynamicTileEncode sees it: mipmapMask != 0 (kept by the alpha stage) and
+// smoothMap == 0 (its 4x4 cell not claimed by a gradient tile).
+static __device__ __forceinline__ bool yk_r1_mask_at(const YkSlotDev& S, int fx, int fy) {
+    return !(S.alphaValid && !S.alphaReset && !S.alphaKept[(size_t)(fy >> 4) * ((S.w + 15) >> 4) + (fx >> 4)]);
+}
+static __device__ __forceinline__ bool yk_r1_smooth_at(const YkSlotDev& S, int fx, int fy) {
+    const int cx = fx >> 2;
+    return (S.cellMask[(size_t)(fy >> 2) * S.nbx + (cx >> 4)] >> (cx & 15)) & 1u;
+}
+
+// The walk of LeftRightOrder (framework.h:228-256) over the constraint box of a plane of pw x ph samples: rows of
+// nbw = ceil(cw / 8) blocks while y < cy + ch, then one more block at the start of the next row when that row still
+// lies inside the plane (HasNextBlock tests `y < h` after the wrap).  Block sizes: the reference compares with the
+// constraint's width / height, not its right / bottom edge, and falls back to x % 8 (framework.h:251-252) - 0 for the
+// full-resolution planes, possibly 4 for a reduced chroma plane whose box starts on an odd multiple of 4.
+struct YkR1Block { int x, y, rw, rh; };
+static __device__ __forceinline__ YkR1Block yk_r1_block(const YkR1Args& A, int i) {
+    YkR1Block b;
+    b.x = A.cx + 8 * (i % A.nbw); b.y = A.cy + 8 * (i / A.nbw);
+    b.rw = (b.x + 8 > A.cw) ? (b.x & 7) : 8;
+    b.rh = (b.y + 8 > A.ch) ? (b.y & 7) : 8;
+    return b;
+}
+
 __global__ void __launch_bounds__(YK_R1_THREADS)
-yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, int plane, int mode3, int cx, int cy, int cw, int ch,
-               int nBlocks, const int* __restrict__ lut) {
+yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, const YkR1Args A, const int* __restrict__ lut) {
     __shared__ __align__(16) float sTerm[YK_R1_THREADS / 32][6][64];
-    __shared__ int sBlock[YK_R1_UNIT], sNibOff[YK_R1_UNIT];      // sBlock: x / 8 | (y / 8) << 12 | cells << 28 (x, y < 32768)
+    __shared__ int sBlock[YK_R1_UNIT], sNibOff[YK_R1_UNIT];      // sBlock: block index of the walk
+    __shared__ unsigned sMask[YK_R1_UNIT];                       // coded pixel pairs of the block: bit = 4 * row + pair
     __shared__ int sWarp[33];
     __shared__ int sUnit;
     __shared__ unsigned sBase[2];
     const YkSlotDev& S = slots[slot];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nUnits = (nBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT;
+    const int nUnits = (A.nBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT;
+    const bool reduced = (A.shX | A.shY) != 0;
     unsigned long long* status = S.r1Status;
     if (tid == 0) sUnit = (int)atomicAdd(reinterpret_cast<unsigned*>(&status[nUnits]), 1u);
     __syncthreads();
     const int u = sUnit;
-    const int nbw = cw >> 3;
-    // ---- count
+    // ---- count: which pixel pairs of my block are coded (EC.cpp:826-861; the 2x2 / 2x1 / 1x2 mask samples a reduced
+    // pixel covers lie in one 16x16 alpha tile, so "all of them" is the top-left one)
     const int i = u * YK_R1_UNIT + tid;
-    unsigned cells = 0;
-    int bx = 0, by = 0;
-    if (tid < YK_R1_UNIT && i < nBlocks) {
-        const int x = cx + 8 * (i % nbw), y = cy + 8 * (i / nbw);
-        bx = x; by = y;
-        if (x + 8 <= cw && y + 8 <= ch && x + 8 <= S.w && y + 8 <= S.h) cells = yk_r1_cells(S, x, y);
+    unsigned pairs = 0;
+    if (tid < YK_R1_UNIT && i < A.nBlocks) {
+        const YkR1Block b = yk_r1_block(A, i);
+        if (!reduced) {
+            if (b.rw == 8 && b.rh == 8 && b.x + 8 <= S.w && b.y + 8 <= S.h) {
+                const unsigned cells = yk_r1_cells(S, b.x, b.y);
+                pairs = ((cells & 1u) ? 0x00003333u : 0u) | ((cells & 2u) ? 0x0000CCCCu : 0u) | ((cells & 4u) ? 0x33330000u : 0u) | ((cells & 8u) ? 0xCCCC0000u : 0u);
+            }
+        } else {
+            for (int r = 0; r < b.rh; r++)
+                for (int p = 0; 2 * p < b.rw; p++) {
+                    const int fx = (b.x + 2 * p) << A.shX, fy = (b.y + r) << A.shY;
+                    if (yk_r1_mask_at(S, fx, fy) && !yk_r1_smooth_at(S, fx, fy)) pairs |= 1u << (4 * r + p);
+                }
+        }
     }
-    const int n = 16 * __popc(cells);
+    const int n = 2 * __popc(pairs);
     // ---- offsets: pixels in the low 16 bits (<= 64 * YK_R1_UNIT per unit), blocks with pixels above
     int tot;
     const int ex = yk_block_exclusive(n | ((n > 0) << 16), sWarp, tot);
@@ -238,29 +274,50 @@ yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, int plane, int mod
         if (lane == 0) {
             sBase[0] = (unsigned)(base >> 32); sBase[1] = (unsigned)base;
             if (u == nUnits - 1) {
-                S.hdr[YK_HD_R1_NIB0 + plane] = (int)(base >> 32) + (tot & 0xFFFF);
-                S.hdr[YK_HD_R1_DEF0 + plane] = (int)(unsigned)base + (tot >> 16);
+                S.hdr[YK_HD_R1_NIB0 + A.out] = (int)(base >> 32) + (tot & 0xFFFF);
+                S.hdr[YK_HD_R1_DEF0 + A.out] = (int)(unsigned)base + (tot >> 16);
             }
         }
     }
-    if (n > 0) { sBlock[ex >> 16] = (bx >> 3) | ((by >> 3) << 12) | ((int)cells << 28); sNibOff[ex >> 16] = ex & 0xFFFF; }
+    if (n > 0) { sBlock[ex >> 16] = i; sMask[ex >> 16] = pairs; sNibOff[ex >> 16] = ex & 0xFFFF; }
     __syncthreads();
     const int nList = tot >> 16;
     const int nibBase = (int)sBase[0], defBase = (int)sBase[1];
     const int r = lane >> 2, c0 = (lane & 3) * 2;
-    const int startMode = mode3 ? 3 : 0;
+    const int startMode = A.mode3 ? 3 : 0;
     for (int k = warp; k < nList; k += YK_R1_THREADS / 32) {
-        const int word = sBlock[k];
-        const unsigned bc = (unsigned)word >> 28;
-        const int x = (word & 0xFFF) << 3, y = ((word >> 12) & 0xFFF) << 3;
-        const bool valid = (bc >> ((r >> 2) * 2 + (c0 >> 2))) & 1u;
+        const YkR1Block b = yk_r1_block(A, sBlock[k]);
+        const int x = b.x, y = b.y;
+        const bool valid = (sMask[k] >> lane) & 1u;
+        // ---- min / max of the block (Plane::GetMinMax_Y, Plane.cpp:489-587).  Full resolution: over the coded pixels.
+        // Reduced planes: over "not smooth and any covered mask sample set", where the reference addresses the
+        // full-size mask with the REDUCED plane's width as row stride (Plane.cpp:516, 538-553) - restated literally.
+        bool m0 = valid, m1 = valid;
+        const bool inRect = r < b.rh && c0 < b.rw;
+        if (reduced) {
+            m0 = m1 = false;
+            if (inRect) {
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const size_t vi = ((size_t)(x + c0 + q) << A.shX) + (size_t)((y + r) << A.shY) * A.pw;
+                    const int W = S.w;
+                    bool any = yk_r1_mask_at(S, (int)(vi % W), (int)(vi / W));
+                    if (A.shX) any |= yk_r1_mask_at(S, (int)((vi + 1) % W), (int)((vi + 1) / W));
+                    if (A.shY) any |= yk_r1_mask_at(S, (int)((vi + A.pw) % W), (int)((vi + A.pw) / W));
+                    if (A.shX && A.shY) any |= yk_r1_mask_at(S, (int)((vi + A.pw + 1) % W), (int)((vi + A.pw + 1) / W));
+                    const bool ok = any && !yk_r1_smooth_at(S, (int)(vi % W), (int)(vi / W));
+                    if (q) m1 = ok; else m0 = ok;
+                }
+            }
+        }
         int v0 = 0, v1 = 0;
-        if (valid) {
-            int2 p = __ldg(reinterpret_cast<const int2*>(S.plane[plane] + (size_t)(y + r) * S.w + x + c0));
+        if (valid || m0 || m1) {
+            int2 p = __ldg(reinterpret_cast<const int2*>(A.src + (size_t)(y + r) * A.pw + x + c0));
             v0 = p.x; v1 = p.y;
         }
-        int mn = __reduce_min_sync(YK_FULL, valid ? min(v0, v1) : INT_MAX);
-        int mx = __reduce_max_sync(YK_FULL, valid ? max(v0, v1) : INT_MIN);
+        int mn = __reduce_min_sync(YK_FULL, min(m0 ? v0 : INT_MAX, m1 ? v1 : INT_MAX));
+        int mx = __reduce_max_sync(YK_FULL, max(m0 ? v0 : INT_MIN, m1 ? v1 : INT_MIN));
+        if (mn == INT_MAX) { mn = 0; mx = 0; }                                 // Plane.cpp:579-585
         int sgn = 0;
         if (mn < 0) { mn += 128; mx += 128; sgn = 128; }                       // EC.cpp:764-768
         mn = min(max(mn, 0), 255); mx = min(max(mx, mn), 255);
@@ -319,15 +376,71 @@ yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, int plane, int mod
             const int before = 2 * __popc(bv0 & ((1u << lane) - 1u));           // both pixels of a lane share validity
             const int c0v = (codes0 >> (4 * bestMode)) & 15, c1v = (codes1 >> (4 * bestMode)) & 15;
             const int n0 = nibBase + sNibOff[k] + before;                       // even: the two nibbles share a byte
-            reinterpret_cast<uint8_t*>(S.r1Nib[plane])[n0 >> 1] = (uint8_t)(c0v | (c1v << 4));   // low nibble first, EC.cpp:1180-1184
+            reinterpret_cast<uint8_t*>(S.r1Nib[A.out])[n0 >> 1] = (uint8_t)(c0v | (c1v << 4));   // low nibble first, EC.cpp:1180-1184
             if (S.r1Dst) {
+                // EC.cpp:4441-4502: chroma blocks with a negative minimum go back minus 128; reduced planes are
+                // written at their top-left full-size position only ("interpolation comes later")
                 const int* L = T + (bestMode < 3 ? 16 * bestMode : 48 + 8 * (bestMode - 3));
-                int* d = S.r1Dst + (size_t)(y + r) * S.w + x + c0;
-                d[0] = __ldg(L + c0v); d[1] = __ldg(L + c1v);                    // EC.cpp:4448-4457 (offset 0 for full-resolution planes)
+                const int offset = (A.chroma && sgn) ? -128 : 0;
+                int* d = S.r1Dst + (size_t)((y + r) << A.shY) * S.w + ((x + c0) << A.shX);
+                d[0] = __ldg(L + c0v) + offset; d[1 << A.shX] = __ldg(L + c1v) + offset;
             }
         }
-        if (lane == 0) S.r1Defs[plane][defBase + k] = (uint16_t)((bestMode << 13) | (r7 << 7) | b6);    // EncodeTileType, YAIK_private.h:358
+        if (lane == 0) S.r1Defs[A.out][defBase + k] = (uint16_t)((bestMode << 13) | (r7 << 7) | b6);    // EncodeTileType, YAIK_private.h:358
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Chroma front-end: Image::ConvertToRGB2YCoCg (Image.cpp:285-321, RGBtoYCoCg EC.cpp:53-67) fused
+// with EncoderContext::chromaReduction (EC.cpp:2770-2782) = Plane::SampleDown (Plane.cpp:278-369) of Co and of Cg.
+// One thread per 2x2 quad of the image: reads the three colour planes once, writes Y at full size and each chroma
+// plane at its own reduction.  C `/` throughout (truncation towards zero: the chroma samples are signed).
+static __device__ __forceinline__ void yk_reduce_quad(int a, int b, int c, int d, int hx, int hy, int mode,
+                                                      int32_t* __restrict__ out, int ow, int qx, int qy) {
+    // a b / c d = the quad at (2qx, 2qy); EDownSample (framework.h:60-66): 0 NEAREST_TL 1 NEAREST_BR 2 AVERAGE_BOX 3 MAX_BOX 4 MIN_BOX
+    if (hx && hy) {
+        int v = a;
+        if (mode == 2) v = (a + b + c + d) / 4;
+        else if (mode == 1) v = d;
+        else if (mode == 3) v = max(max(a, b), max(c, d));
+        else if (mode == 4) v = min(min(a, b), min(c, d));
+        out[(size_t)qy * ow + qx] = v;
+    } else if (hx) {                          // modes 0 and 2 only (the API refuses the others on one axis)
+        out[(size_t)(2 * qy) * ow + qx] = mode == 2 ? (a + b) / 2 : a;
+        out[(size_t)(2 * qy + 1) * ow + qx] = mode == 2 ? (c + d) / 2 : c;
+    } else if (hy) {
+        *reinterpret_cast<int2*>(out + (size_t)qy * ow + 2 * qx) = mode == 2 ? make_int2((a + c) / 2, (b + d) / 2) : make_int2(a, b);
+    } else {
+        *reinterpret_cast<int2*>(out + (size_t)(2 * qy) * ow + 2 * qx) = make_int2(a, b);
+        *reinterpret_cast<int2*>(out + (size_t)(2 * qy + 1) * ow + 2 * qx) = make_int2(c, d);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+yk_k_chroma(const YkSlotDev* __restrict__ slots, int slot, const YkChromaArgs A) {
+    const YkSlotDev& S = slots[slot];
+    const int qw = S.w >> 1, qh = S.h >> 1;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= qw * qh) return;
+    const int qx = q % qw, qy = q / qw;
+    int Y[4], Co[4], Cg[4];
+#pragma unroll
+    for (int row = 0; row < 2; row++) {
+        const size_t at = (size_t)(2 * qy + row) * S.w + 2 * qx;
+        const int2 R = __ldg(reinterpret_cast<const int2*>(S.plane[0] + at));
+        const int2 G = __ldg(reinterpret_cast<const int2*>(S.plane[1] + at));
+        const int2 B = __ldg(reinterpret_cast<const int2*>(S.plane[2] + at));
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int r = k ? R.y : R.x, g = k ? G.y : G.x, b = k ? B.y : B.x;
+            const int co = r - b, tmp = b + co / 2, cg = g - tmp;             // EC.cpp:55-66
+            Y[2 * row + k] = tmp + cg / 2; Co[2 * row + k] = co / 2; Cg[2 * row + k] = cg / 2;
+        }
+    }
+    *reinterpret_cast<int2*>(A.y + (size_t)(2 * qy) * S.w + 2 * qx) = make_int2(Y[0], Y[1]);
+    *reinterpret_cast<int2*>(A.y + (size_t)(2 * qy + 1) * S.w + 2 * qx) = make_int2(Y[2], Y[3]);
+    yk_reduce_quad(Co[0], Co[1], Co[2], Co[3], A.half[0], A.half[1], A.mode[0], A.co, A.half[0] ? qw : S.w, qx, qy);
+    yk_reduce_quad(Cg[0], Cg[1], Cg[2], Cg[3], A.half[2], A.half[3], A.mode[1], A.cg, A.half[2] ? qw : S.w, qx, qy);
 }
 
 // ------------------------------------------------------------------------------------------------------------------// launch wrappers
@@ -335,7 +448,10 @@ void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t*
                      int32_t* mappedRGB, int32_t* recon0, int32_t* recon1, int32_t* recon2, cudaStream_t st) {
     YK_LAUNCH(yk_k_state, dim3(nRegions), dim3(YK_THREADS), 0, st, slotsDev, slot, smoothMap, mipmapMask, mappedRGB, recon0, recon1, recon2);
 }
-void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, int plane, int mode3, int cx, int cy, int cw, int ch,
-                                int nBlocks, const int* lutDev, cudaStream_t st) {
-    YK_LAUNCH(yk_k_r1_encode, dim3((nBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT), dim3(YK_R1_THREADS), 0, st, slotsDev, slot, plane, mode3, cx, cy, cw, ch, nBlocks, lutDev);
+void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, const YkR1Args& args, const int* lutDev, cudaStream_t st) {
+    YK_LAUNCH(yk_k_r1_encode, dim3((args.nBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT), dim3(YK_R1_THREADS), 0, st, slotsDev, slot, args, lutDev);
+}
+void yk_launch_chroma(const YkSlotDev* slotsDev, int slot, int w, int h, const YkChromaArgs& args, cudaStream_t st) {
+    const int quads = (w >> 1) * (h >> 1);
+    YK_LAUNCH(yk_k_chroma, dim3((quads + 255) / 256), dim3(256), 0, st, slotsDev, slot, args);
 }

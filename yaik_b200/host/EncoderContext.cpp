@@ -8,12 +8,15 @@ u8* pType = streamType;         // beyond 33 333 tile records); Dy
 EncoderContext::EncoderContext(int cudaDevice)
     : original(NULL), mipmapMask(NULL), smoothMap(NULL), mapSmoothTile(NULL), mappedRGB(NULL),
       boundX0(0), boundY0(0), boundX1(0), boundY1(0), remainingPixels(0), mipMapTileSize(16),
-      colorCompressionQuad(250), colorCompression1D(255), rangeCompression1D(15), lastError(YK_OK),
-      ctx(NULL), device(cudaDevice), capW(0), capH(0), lastTestOutput(NULL), prepared(false) {}
+      colorCompressionQuad(250), colorCompression1D(255), rangeCompression1D(15),
+      halfCoW(true), halfCoH(false), halfCgW(true), halfCgH(false), downSampleCo(AVERAGE_BOX), downSampleCg(AVERAGE_BOX),
+      YCoCgImg(NULL), workCo(NULL), workCg(NULL), lastError(YK_OK),
+      ctx(NULL), device(cudaDevice), capW(0), capH(0), lastTestOutput(NULL), prepared(false), useYCoCgPlanes(false) {}
 
 EncoderContext::~EncoderContext() {
     if (ctx) yk_destroy(ctx);
     delete mipmapMask; delete smoothMap; delete mapSmoothTile; delete mappedRGB;
+    delete YCoCgImg; delete workCo; delete workCg;
 }
 
 void EncoderContext::ensureContext(int w, int h, int planes) {
@@ -35,6 +38,8 @@ void EncoderContext::SetImageToEncode(Image* img) {
     lastError = yk_set_image(ctx, 0, planes, n, w, h);
     delete mipmapMask; delete smoothMap; delete mapSmoothTile; delete mappedRGB;
     mipmapMask = NULL; smoothMap = NULL; mapSmoothTile = NULL; mappedRGB = NULL;
+    delete YCoCgImg; delete workCo; delete workCg;
+    YCoCgImg = NULL; workCo = NULL; workCg = NULL;
     boundX0 = 0; boundY0 = 0; boundX1 = w; boundY1 = h; remainingPixels = w * h; mipMapTileSize = 16;
     prepared = false; lastTestOutput = NULL;
 }
@@ -124,17 +129,49 @@ u8* EncoderContext::DynamicTileCompressor(u8* stream, Plane* src, Plane* map, Pl
     return stream + ni;
 }
 
+void EncoderContext::convRGB2YCoCg(bool notUseRGBAsIs) {
+    useYCoCgPlanes = notUseRGBAsIs;                 // the conversion itself runs fused with chromaReduction()
+}
+
+void EncoderContext::chromaReduction() {
+    if (!ctx || !original) { lastError = YK_ERR_STATE; return; }
+    if (!useYCoCgPlanes) { lastError = YK_ERR_UNSUPPORTED; return; }       // "RGB as is" feeds DynamicTileEncode the image planes directly
+    const int half[4] = { halfCoW, halfCoH, halfCgW, halfCgH }, mode[2] = { (int)downSampleCo, (int)downSampleCg };
+    lastError = yk_chroma_prepare(ctx, 0, half, mode);
+    if (lastError) { fprintf(stderr, "yaik_b200: chromaReduction: %s\n", yk_error_string(lastError)); return; }
+    delete YCoCgImg; delete workCo; delete workCg;
+    const int w = original->GetWidth(), h = original->GetHeight();
+    YCoCgImg = Image::CreateImage(w, h, 1, false, false);
+    workCo = new Plane(halfCoW ? w / 2 : w, halfCoH ? h / 2 : h, false);
+    workCg = new Plane(halfCgW ? w / 2 : w, halfCgH ? h / 2 : h, false);
+    Plane* out[3] = { YCoCgImg->GetPlane(0), workCo, workCg };
+    for (int k = 0; k < 3 && !lastError; k++) lastError = yk_chroma_plane(ctx, 0, k, out[k]->GetPixels(), NULL, NULL);
+}
+
 int EncoderContext::DynamicTileEncode(bool mode3BitOnly, Plane* plane, Plane* dst, bool isCo, bool isCg, bool isHalfX, bool isHalfY) {
     CheckMipmapMask();
     if (!ctx || !original) { lastError = YK_ERR_STATE; return 0; }
-    const int n = planeIndexOf(plane, original);
-    if (n < 0 || isCo || isCg || isHalfX || isHalfY) { lastError = YK_ERR_UNSUPPORTED; return 0; }   // full-resolution planes of the image
-    const int w = original->GetWidth(), h = original->GetHeight(), nt = (w / 8) * (h / 8);
+    // which device plane: one of the image's colour planes, or Y / workCo / workCg of the chroma front-end
+    int which = -1;
+    if (YCoCgImg && plane == YCoCgImg->GetPlane(0)) which = 0;
+    else if (plane && plane == workCo) which = 1;
+    else if (plane && plane == workCg) which = 2;
+    const int n = which < 0 ? planeIndexOf(plane, original) : -1;
+    if (which < 0 && (n < 0 || isCo || isCg || isHalfX || isHalfY)) { lastError = YK_ERR_UNSUPPORTED; return 0; }
+    if (which >= 0) {                               // the flags must be the ones the plane was made with
+        const bool hx = which == 1 ? halfCoW : which == 2 ? halfCgW : false, hy = which == 1 ? halfCoH : which == 2 ? halfCgH : false;
+        if (isHalfX != hx || isHalfY != hy || (isCo || isCg) != (which != 0)) { lastError = YK_ERR_ARG; return 0; }
+    }
+    const int pw = plane->GetWidth(), ph = plane->GetHeight(), nt = (pw / 8) * (ph / 8);
     lastDynamic.nibbles.assign((size_t)nt * 32 + 8, 0);
     lastDynamic.tileDefs.assign((size_t)nt + 8, 0);
     int nn = 0, nd = 0, cons[4] = { 0, 0, 0, 0 };
-    lastError = yk_range_dyn(ctx, 0, n, mode3BitOnly ? 1 : 0, lastDynamic.nibbles.data(), (int)lastDynamic.nibbles.size(), &nn,
-                             lastDynamic.tileDefs.data(), (int)lastDynamic.tileDefs.size(), &nd, cons, dst ? dst->GetPixels() : NULL);
+    if (which < 0)
+        lastError = yk_range_dyn(ctx, 0, n, mode3BitOnly ? 1 : 0, lastDynamic.nibbles.data(), (int)lastDynamic.nibbles.size(), &nn,
+                                 lastDynamic.tileDefs.data(), (int)lastDynamic.tileDefs.size(), &nd, cons, dst ? dst->GetPixels() : NULL);
+    else
+        lastError = yk_range_dyn_chroma(ctx, 0, which, mode3BitOnly ? 1 : 0, lastDynamic.nibbles.data(), (int)lastDynamic.nibbles.size(), &nn,
+                                        lastDynamic.tileDefs.data(), (int)lastDynamic.tileDefs.size(), &nd, cons, dst ? dst->GetPixels() : NULL);
     if (lastError) { fprintf(stderr, "yaik_b200: DynamicTileEncode: %s\n", yk_error_string(lastError)); return 0; }
     lastDynamic.nibbles.resize((nn + 1) / 2); lastDynamic.tileDefs.resize(nd); lastDynamic.nNibbles = nn;
     lastDynamic.constraint.x = (s16)cons[0]; lastDynamic.constraint.y = (s16)cons[1];

@@ -25,6 +25,11 @@ struct EncoderContext {
     u8*  DynamicTileCompressor(u8* stream, Plane* src, Plane* map, Plane* debug);     // EncoderContext.h:236, EC.cpp:8398
     int  DynamicTileEncode(bool mode3BitOnly, Plane* plane, Plane* dst, bool isCo, bool isCg, bool isHalfX, bool isHalfY);   // EncoderContext.h:370, EC.cpp:4365
     void CheckMipmapMask();                         // EC.cpp:2784-2794
+    // chroma front-end of the range stage (Convert() holds it at EC.cpp:9539-9545).  convRGB2YCoCg only records the
+    // request; chromaReduction runs RGB -> YCoCg and the SampleDown of Co / Cg in one kernel (yk_chroma_prepare) and
+    // brings Y, workCo and workCg back.  DynamicTileEncode recognises those three planes by pointer.
+    void convRGB2YCoCg(bool notUseRGBAsIs);         // EncoderContext.h:334, EC.cpp:2766
+    void chromaReduction();                         // EncoderContext.h:336, EC.cpp:2770
 
     // expands the compact device state into the int32 state planes below (and into `testOutput` of the last
     // FittingQuadSmooth call) — the reference updates them in place on every call; here it is explicit because it
@@ -40,6 +45,11 @@ struct EncoderContext {
     int boundX0, boundY0, boundX1, boundY1;
     int remainingPixels, mipMapTileSize;
     int colorCompressionQuad, colorCompression1D, rangeCompression1D;   // 250, 255, 15 (EncoderContext.h:221-224)
+    bool halfCoW, halfCoH, halfCgW, halfCgH;        // EncoderContext.h:265-271 (the CLI sets W only, AVERAGE_BOX: ImageEncoder.cpp:175-181)
+    EDownSample downSampleCo, downSampleCg;
+    Image* YCoCgImg;            // plane 0 = Y.  Co / Cg exist at their working size only: workCo / workCg
+    Plane* workCo;
+    Plane* workCg;
     int lastError;              // YK_* code of the last failing call (the reference printf()s and carries on)
 
     // ---- what the reference's host tails consume
@@ -51,7 +61,7 @@ private:
     yk_ctx* ctx;
     int device, capW, capH;
     Image* lastTestOutput;
-    bool prepared;
+    bool prepared, useYCoCgPlanes;
     int planeIndexOf(Plane* p, Image* img);
     void ensureContext(int w, int h, int planes);
 };

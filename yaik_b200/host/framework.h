@@ -13,6 +13,7 @@ typedef uint32_t u32;
 typedef int16_t s16;
 
 struct BoundingBox { s16 x, y, w, h; };             // include/YAIK_private.h:15-20
+enum EDownSample { NEAREST_TL, NEAREST_BR, AVERAGE_BOX, MAX_BOX, MIN_BOX };     // encoder/framework.h:60-66
 
 class Plane {                                       // encoder/framework.h:74-127
 public:
