@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=96)
     ap.add_argument("--e2e-threads", type=int, default=8, help="host threads (one context each) the end-to-end steps are pipelined over")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the informational timing of the stages outside the metric")
     ap.add_argument("--streams", type=int, default=8, help="contexts/streams the steps are pipelined over (1, 2, 4 or 8)")
     ap.add_argument("--analysis-ctas", type=int, default=-1, help="CTAs of the persistent analysis kernel in the pipelined region (-1: a quarter of the SMs with 8 streams, half with 2-4, else one per SM)")
     ap.add_argument("--roofline-steps", type=int, default=100, help="launches of the separate pass that times the dominant kernel alone")
@@ -396,6 +397,35 @@ def main():
         cpu = {"value": round(mp_per_step / sec, 3), "unit": UNIT, "cores": 1, "kind": kind,
                "sample": f"the same 2048x2048 RGBA texture, alpha + 7 gradient passes (incl. the reference's host tail) + R2, {reps} repetitions, 1 thread"}
 
+    # ---- stages of the path that are not part of the metric (informational): DynamicTileEncode (R1) per colour plane and the
+    # chroma front-end in the CLI's configuration, device time of their kernels (event pairs around each launch)
+    other = None
+    if rank == 0 and world == 1 and not args.no_other:
+        c = capi.Context(W, H, planes=CH, slots=1, device=local, lib=lib)
+        c.set_image(imgs[0], 0)
+        c.analyze(capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D)
+        c.sync()
+        for it in range(4):
+            if it == 1:
+                lib.yk_profile(c.ctx, 1)
+            for p in range(3):
+                c.range_dyn(p)
+        a = (C.c_double * 8)(); b = (C.c_longlong * 8)()
+        lib.yk_profile_read(c.ctx, a, b)
+        r1_us = a[3] / b[3] * 1e3 if b[3] else None
+        for it in range(4):
+            if it == 1:
+                lib.yk_profile(c.ctx, 1)
+            c.chroma((1, 0, 1, 0), (2, 2), planes=False)
+        lib.yk_profile_read(c.ctx, a, b)
+        lib.yk_profile(c.ctx, 0)
+        other = {"r1_encode_us_per_plane": round(r1_us, 2) if r1_us else None,
+                 "chroma_convert_us": round(a[4] / b[4] * 1e3, 2) if b[4] else None,
+                 "chroma_encode_us_per_plane": round(a[3] / b[3] * 1e3, 2) if b[3] else None,
+                 "what": "kernel device time on the bench texture after the analysis: yk_k_r1_encode (DynamicTileEncode, all six LUT modes) per "
+                         "colour plane; yk_k_chroma (RGB -> YCoCg + half-width Co / Cg) and yk_k_r1_encode averaged over Y, Co, Cg. Not in `value`."}
+        c.close()
+
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -404,7 +434,8 @@ def main():
                            "pipelining": f"steps are independent textures, issued round-robin on {NCTX} CUDA streams (contexts); analysis launches of {actas or sms} CTAs on {sms} SMs",
                            "l2": "inputs rotate over 8 resident 64 MiB images (512 MiB > 126 MB L2), so every step reads cold planes",
                            "stages": "MipPrefilter + 7x FittingQuadSmooth + 3x DynamicTileCompressor, results left in HBM", "kernels_per_step": "yk_k_analyze (persistent, TMA-staged, range stage fused) + yk_k_owner + yk_k_emit"},
-                "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+                "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "stages_outside_metric": other}
         print(json.dumps(line), flush=True)
     for c in ctxs:
         c.close()

@@ -190,8 +190,8 @@ int  yk_result_bytes(yk_ctx* ctx, int slot, long long out[6]);
 long long yk_launch_count(yk_ctx* ctx);
 
 /* Per-kernel device time: while enabled, every launch is bracketed by a CUDA event pair on the launching stream;
- * yk_profile_read synchronises, sums the elapsed milliseconds per kernel (0 yk_k_analyze, 1 yk_k_emit, 2 yk_k_owner;
- * the other entries are unused) with their launch counts, and clears the record.  Used by bench.py's roofline figure. */
+ * yk_profile_read synchronises, sums the elapsed milliseconds per kernel (0 yk_k_analyze, 1 yk_k_emit, 2 yk_k_owner,
+ * 3 yk_k_r1_encode, 4 yk_k_chroma; the other entries are unused) with their launch counts, and clears the record.  Used by bench.py's roofline figure. */
 int  yk_profile(yk_ctx* ctx, int enable);
 int  yk_profile_read(yk_ctx* ctx, double ms[8], long long count[8]);
 

@@ -94,7 +94,7 @@ struct yk_ctx {
     size_t planeCap = 0;
     // optional per-kernel timing with CUDA events on the launching stream (yk_profile)
     bool profile = false;
-    std::vector<cudaEvent_t> evA[5], evB[5];      // 0 analyze, 1 emit, 2 owner
+    std::vector<cudaEvent_t> evA[5], evB[5];      // 0 analyze, 1 emit, 2 owner, 3 r1_encode, 4 chroma
 };
 
 struct YkTimed {        // records an event pair around one launch when profiling is on
@@ -869,7 +869,7 @@ static int range_dyn_impl(yk_ctx* c, int slot, const int32_t* src, int pw, int p
     if ((rc = upload_slots(c, slot, 1))) return rc;
     if (a.nBlocks > 0) {
         CK(cudaMemsetAsync(s.d.r1Status, 0, r1_status_words(w, h) * sizeof(unsigned long long), c->stream));
-        yk_launch_range_dyn_encode(c->slotsDev, slot, a, c->lutDev, c->stream);
+        { YkTimed t(c, 3); yk_launch_range_dyn_encode(c->slotsDev, slot, a, c->lutDev, c->stream); }
         c->launches += 1;
     }
     CK(cudaGetLastError());
@@ -929,7 +929,7 @@ extern "C" int yk_chroma_prepare(yk_ctx* c, int slot, const int half[4], const i
     for (int k = 0; k < 4; k++) { a.half[k] = half[k] != 0; s.chromaHalf[k] = a.half[k]; }
     a.mode[0] = downMode[0]; a.mode[1] = downMode[1];
     if ((rc = upload_slots(c, slot, 1))) return rc;
-    yk_launch_chroma(c->slotsDev, slot, w, h, a, c->stream);
+    { YkTimed t(c, 4); yk_launch_chroma(c->slotsDev, slot, w, h, a, c->stream); }
     c->launches += 1;
     CK(cudaGetLastError());
     s.chromaReady = true;
