@@ -105,3 +105,26 @@ CHROMA_CASES = [
     ("noise64", (), (1, 0, 1, 0), (2, 2)),                         # no gradient stage before (all pixels coded)
     ("alpha_corner_only", ("alpha", "grad"), (1, 1, 1, 0), (1, 2)),
 ]
+
+
+def random_chroma_case(i):
+    """Random 16-aligned shape, content, reduction and down-sampling mode; RGBA cases get alpha holes (power-of-two square)."""
+    r = _rand(888, i, np.arange(12, dtype=np.uint64))
+    rgba = int(r[0] % np.uint64(3)) == 0
+    if rgba:
+        w = h = 64 << int(r[1] % np.uint64(3))         # 64, 128, 256: the alpha stage's parity domain; reduced planes stay >= 32 (R1's domain)
+        planes = make_image(w, h, 4, SEED_BASE + 700 + i)
+        pre = ("alpha", "grad")
+    else:
+        w = 16 * (4 + int(r[1] % np.uint64(7)))        # 64 .. 160 (a reduced plane below 32 crashes the reference)
+        h = 16 * (4 + int(r[2] % np.uint64(5)))        # 64 .. 128
+        kind = int(r[3] % np.uint64(3))
+        planes = (_patchy(w, h, 4000 + i, 4, 2) if kind == 0 else make_image(w, h, 3, SEED_BASE + 800 + i) if kind == 1
+                  else _noise(w, h, 3, 5000 + i, 60, 200))
+        pre = ("grad",) if int(r[4] % np.uint64(4)) else ()
+    cfg = tuple(int(r[5 + k] % np.uint64(2)) for k in range(4))
+    modes = []
+    for k in range(2):
+        both = cfg[2 * k] and cfg[2 * k + 1]
+        modes.append(int(r[9 + k] % np.uint64(5)) if both else (0, 2)[int(r[9 + k] % np.uint64(2))])   # one axis: nearest / average only
+    return planes, pre, cfg, tuple(modes)

@@ -57,6 +57,13 @@ def test_chroma_front_end(ctx, name, pre, cfg, modes):
     check_chroma(ctx, planes, pre, cfg, modes)
 
 
+@pytest.mark.parametrize("i", range(16))
+def test_chroma_front_end_random_configurations(ctx, i):
+    """The configurations tests/test_oracle_vs_ref.py pins the oracle on against the compiled reference."""
+    planes, pre, cfg, modes = cases.random_chroma_case(i)
+    check_chroma(ctx, planes, pre, cfg, modes)
+
+
 def test_chroma_front_end_2048_rgba(lib):
     """The bench texture through the CLI's chroma configuration (half-width Co and Cg, box average)."""
     c = capi.Context(2048, 2048, planes=4, slots=1, lib=lib)

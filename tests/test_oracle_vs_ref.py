@@ -115,3 +115,16 @@ def test_oracle_chroma_pipeline_matches_reference(name, pre, cfg, modes):
         o.gradient_cascade()
     check_chroma(o.chroma(cfg, modes), ref)
     o.close()
+
+
+@pytest.mark.parametrize("i", range(16))
+def test_oracle_chroma_pipeline_random_configurations(i):
+    planes, pre, cfg, modes = cases.random_chroma_case(i)
+    ref = run_ref(planes, (*pre, "chroma=%d%d%d%d:%d%d" % (*cfg, *modes)))
+    o = Oracle(planes)
+    if "alpha" in pre:
+        o.alpha()
+    if "grad" in pre:
+        o.gradient_cascade()
+    check_chroma(o.chroma(cfg, modes), ref)
+    o.close()

@@ -51,3 +51,15 @@ def test_random_shape_matches_oracle(emu_lib, i):
         check_image(ctx, planes, stages, fused=(i % 3 != 0))
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("i", range(16))
+def test_random_chroma_pipeline_matches_oracle(emu_lib, i):
+    from parity import check_chroma
+    planes, pre, cfg, modes = cases.random_chroma_case(i)
+    c, h, w = planes.shape
+    ctx = capi.Context(w, h, planes=4, slots=1, lib=emu_lib)
+    try:
+        check_chroma(ctx, planes, pre, cfg, modes)
+    finally:
+        ctx.close()
