@@ -496,40 +496,31 @@ static __device__ __forceinline__ void yka_range_tile(const uint8_t* __restrict_
     const unsigned qb = (q >> (band * 2)) & 3u;             // coded quadrants of this band: bit0 left, bit1 right
     const int lengthX = (qb == 3u) ? 8 : 4, x2 = (qb == 2u) ? 4 : 0;
     const int pos = (band ? 16 * __popc(q & 3u) : 0) + (r & 3) * lengthX + (c0 - x2);
-    int vx[3], vy[3];
+    // One plane at a time, the loop NOT unrolled: the side-by-side form (three planes interleaved) was 370 instructions
+    // against 130 and 10 % slower for the whole kernel - the consumers' code has to stay small (instruction cache).
     // FindAndRemoveMostUsedColor (EC.cpp:8335-8356): per-value counts in a byte histogram (four 8-bit counters per word,
     // a tile has at most 64 pixels), filled with shared-memory atomics
     uint32_t* hist32 = reinterpret_cast<uint32_t*>(hist);
-#pragma unroll
+#pragma unroll 1
     for (int p = 0; p < 3; p++) {
         const unsigned short two = *reinterpret_cast<const unsigned short*>(priv + p * YKP_CH + (ly8 + r) * YKP_RS + lx8 + c0);
-        vx[p] = two & 255; vy[p] = two >> 8;                 // CompressF(v,255) == v (EC.cpp:8442)
+        const int vx = two & 255, vy = two >> 8;             // CompressF(v,255) == v (EC.cpp:8442)
+        uint8_t* hp = hist + p * 256;
         if (valid) {
-            atomicAdd(&hist32[p * 64 + (vx[p] >> 2)], 1u << (8 * (vx[p] & 3)));
-            atomicAdd(&hist32[p * 64 + (vy[p] >> 2)], 1u << (8 * (vy[p] & 3)));
+            atomicAdd(&hist32[p * 64 + (vx >> 2)], 1u << (8 * (vx & 3)));
+            atomicAdd(&hist32[p * 64 + (vy >> 2)], 1u << (8 * (vy & 3)));
         }
-    }
-    __syncwarp();
-    unsigned key[3];
-#pragma unroll
-    for (int p = 0; p < 3; p++) {
+        __syncwarp();
         // highest index among the maximal counts (`>=`, EC.cpp:8340); only present values can win
-        key[p] = valid ? max(((unsigned)hist[p * 256 + vx[p]] << 8) | (unsigned)vx[p], ((unsigned)hist[p * 256 + vy[p]] << 8) | (unsigned)vy[p]) : 0u;
-        key[p] = __reduce_max_sync(YK_FULL, key[p]);
-    }
-    __syncwarp();
-    if (valid) {
-#pragma unroll
-        for (int p = 0; p < 3; p++) { hist[p * 256 + vx[p]] = 0; hist[p * 256 + vy[p]] = 0; }
-    }
-#pragma unroll
-    for (int p = 0; p < 3; p++) {
-        const int color0 = min(max((int)(key[p] & 255u), 1), 254);
+        unsigned key = valid ? max(((unsigned)hp[vx] << 8) | (unsigned)vx, ((unsigned)hp[vy] << 8) | (unsigned)vy) : 0u;
+        key = __reduce_max_sync(YK_FULL, key);
+        if (valid) { hp[vx] = 0; hp[vy] = 0; }               // clean again for the next tile (ordered by the reductions below)
+        const int color0 = min(max((int)(key & 255u), 1), 254);
         // Model1 (EC.cpp:8358-8381) over what is left of the histogram
-        const bool remx = valid && (vx[p] < color0 - 1 || vx[p] > color0 + 1);
-        const bool remy = valid && (vy[p] < color0 - 1 || vy[p] > color0 + 1);
-        const int mn = __reduce_min_sync(YK_FULL, min(remx ? vx[p] : 999, remy ? vy[p] : 999));
-        const int mx = __reduce_max_sync(YK_FULL, max(remx ? vx[p] : -1, remy ? vy[p] : -1));
+        const bool remx = valid && (vx < color0 - 1 || vx > color0 + 1);
+        const bool remy = valid && (vy < color0 - 1 || vy > color0 + 1);
+        const int mn = __reduce_min_sync(YK_FULL, min(remx ? vx : 999, remy ? vy : 999));
+        const int mx = __reduce_max_sync(YK_FULL, max(remx ? vx : -1, remy ? vy : -1));
         int minCol = 0, delta = 0;
         if (mn != 999) { minCol = mn; delta = mx - mn; }
         if (valid) {
@@ -539,12 +530,12 @@ static __device__ __forceinline__ void yka_range_tile(const uint8_t* __restrict_
             if (delta) {
                 const unsigned magic = magicTab[delta];
                 const int rnd = (delta >> 1) - 1;
-                if (remx) { const int n = (vx[p] - minCol) * 15 + rnd; bxv = 1 + (n < 0 ? n : (int)(((unsigned)n * magic) >> 20)); }
-                if (remy) { const int n = (vy[p] - minCol) * 15 + rnd; byv = 1 + (n < 0 ? n : (int)(((unsigned)n * magic) >> 20)); }
+                if (remx) { const int n = (vx - minCol) * 15 + rnd; bxv = 1 + (n < 0 ? n : (int)(((unsigned)n * magic) >> 20)); }
+                if (remy) { const int n = (vy - minCol) * 15 + rnd; byv = 1 + (n < 0 ? n : (int)(((unsigned)n * magic) >> 20)); }
             } else { bxv = remx ? 1 : 0; byv = remy ? 1 : 0; }
             *reinterpret_cast<uint16_t*>(Rg.r2Raw[p] + tile * 64 + pos) = (uint16_t)((bxv & 255) | ((byv & 255) << 8));
         }
-        if (lane == p) Rg.r2RawType[p][tile] = (uint32_t)color0 | ((uint32_t)minCol << 8) | ((uint32_t)delta << 16);     // EC.cpp:8503-8505
+        if (lane == 0) Rg.r2RawType[p][tile] = (uint32_t)color0 | ((uint32_t)minCol << 8) | ((uint32_t)delta << 16);     // EC.cpp:8503-8505
     }
     __syncwarp();       // the histogram entries are clean again before the next tile fills them
 }
