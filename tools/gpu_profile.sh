@@ -4,7 +4,7 @@
 # The bench command issues 3 warm-up + 8 pipelined steps (quarter-SM analysis launches) and then 4 steps of its roofline
 # pass (one CTA per SM, the kernel alone); 3 kernels per step.
 TAG=${1:-rXX}; KRE=${2:-yk_k_}
-B="python bench.py --steps 8 --warmup 3 --e2e-steps 0 --no-cpu --no-prewarm --roofline-steps 4"
+B="python bench.py --steps 8 --warmup 3 --e2e-steps 0 --no-cpu --no-other --no-prewarm --roofline-steps 4"
 mkdir -p gpurun_out
 $B > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 40 --csv --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/ncu_list_$TAG.log 2>&1
