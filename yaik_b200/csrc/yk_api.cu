@@ -860,11 +860,14 @@ static int range_dyn_impl(yk_ctx* c, int slot, const int32_t* src, int pw, int p
     a.nBlocks = a.nbw * rows;
     if (a.nBlocks > 0 && a.cy + 8 * rows < ph) a.nBlocks += 1;
     if (s.pendingHarvest) { rc = fetch_hdr(c, s); if (rc && rc != YK_ERR_RANGE) return rc; }
-    int32_t* dDst = nullptr;
+    // the optional full-size write-back plane lives on the device for the duration of the call (freed on every way out)
+    struct DstGuard { int32_t* p = nullptr; YkSlotHost* s; ~DstGuard() { if (p) cudaFree(p); s->d.r1Dst = nullptr; s->dirty = true; } } guard;
+    guard.s = &s;
     if (dst) {
-        CK(cudaMalloc((void**)&dDst, (size_t)w * h * 4));
-        CK(cudaMemcpyAsync(dDst, dst, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMalloc((void**)&guard.p, (size_t)w * h * 4));
+        CK(cudaMemcpyAsync(guard.p, dst, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream));
     }
+    int32_t* const dDst = guard.p;
     s.d.r1Dst = dDst; s.dirty = true;
     if ((rc = upload_slots(c, slot, 1))) return rc;
     if (a.nBlocks > 0) {
@@ -888,8 +891,6 @@ static int range_dyn_impl(yk_ctx* c, int slot, const int32_t* src, int pw, int p
         if (dst) CK(cudaMemcpyAsync(dst, dDst, (size_t)w * h * 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
-    if (dDst) cudaFree(dDst);
-    s.d.r1Dst = nullptr; s.dirty = true;
     if (nNibbles) *nNibbles = tot[0];
     if (nDefs) *nDefs = tot[1];
     return rc;
