@@ -823,6 +823,7 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
     uint32_t* touch = sh.touch[cw];
     YkaSlotC& C = sh.slotc[cw];
     YKT_DECL;
+    const bool fast16 = run.fresh && run.nPasses > 0 && run.passId[0] == 0;      // uniform for the launch
     for (;;) {
         int q = 0;
         if (lane == 0) q = atomicAdd(&sh.queueHead, 1);
@@ -850,7 +851,7 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         const unsigned char* rawU = raw + i * STAGE_BYTES;
         // fresh state, 16x16 pass first, interior macro tile: try that pass straight from the raw rows
         int fast = 0;
-        if (run.fresh && run.nPasses > 0 && run.passId[0] == 0 && gmx + 20 <= C.w && Yk + YK_RAW_ROWS <= C.h)
+        if (fast16 && gmx + 20 <= C.w && Yk + YK_RAW_ROWS <= C.h)
             fast = yka_pass16_raw<U8>(rawU, sh, C, gmx, Yk, mx, run.rejectFactor);
         bool kept;
         if (fast == 1) {
