@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--e2e-steps", type=int, default=96)
+    ap.add_argument("--e2e-steps", type=int, default=384)
     ap.add_argument("--e2e-threads", type=int, default=8, help="host threads (one context each) the end-to-end steps are pipelined over")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the informational timing of the stages outside the metric")
