@@ -214,6 +214,8 @@ def main():
         c.set_upload_format(False)     # `value` is measured on int32 planes resident in HBM (the reference's Plane representation)
     sms = ctxs[0].sm_count()
     actas = args.analysis_ctas if args.analysis_ctas >= 0 else (sms // 4 if NCTX >= 8 else (sms // 2 if NCTX > 1 else 0))
+    if args.analysis_ctas < 0 and args.steps < 4:      # a timed region of one to three steps cannot fill four quarter-SM launches
+        actas = 0 if args.steps <= 1 else sms // args.steps
     for c in ctxs:
         c.set_analysis_ctas(actas)     # launches of neighbouring steps run side by side on disjoint SMs: ramp and tail of one hide behind the others
     ctx, stream = ctxs[0], streams[0]
