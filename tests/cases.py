@@ -56,6 +56,20 @@ def _alpha_island(w, h, x0, y0, x1, y1, holes=()):
 
 ALL = ("alpha", "grad", "r2", "r1")
 
+
+def _stride_quirk128():
+    """Quarter-size chroma reads the full-size mask with the REDUCED width as row stride (Plane.cpp:516): the second-row
+    samples of a reduced pixel at (xx, yy) lie 64 pixels to the right of (2xx, yy).  Here the alpha tile under (2xx, yy) is
+    rejected while the tile 64 pixels to the right is kept by the alpha stage but claimed by a 16x16 gradient tile, and
+    the block still has coded pixels (its coding rule looks at rows 2yy..): the min/max rule must see mipmapMask == 0
+    there (FittingQuadSmooth zeroes it, EC.cpp:4035), not just "alpha kept"."""
+    rgb = _noise(128, 128, 3, 38, 40, 200)
+    rgb[:, 0:33, 64:97] = 90                       # tile (4, 0) and its corner samples: accepted at 16x16
+    a = np.full((128, 128), 255, np.int32)
+    a[0:16, 0:16] = 0                              # tile (0, 0) rejected
+    a[:, 112:128] = 0                              # keeps the kept-tile box smaller than the image (no reset)
+    return _with_alpha(rgb, a)
+
 SMALL_CASES = {
     # synthetic illustration-like content
     "synth128_rgb": lambda: (make_image(128, 128, 3, SEED_BASE + 11), ("grad", "r2", "r1")),
@@ -91,6 +105,7 @@ SMALL_CASES = {
                                             _alpha_island(256, 256, 64, 16, 250, 200, [(96, 32, 160, 96), (170, 100, 171, 101)])), ALL),
     "alpha_full_reset64": lambda: (_with_alpha(_noise(64, 64, 3, 35, 90, 99),
                                                _alpha_island(64, 64, 0, 0, 64, 64, [(16, 16, 48, 32)])), ALL),
+    "alpha_stride_quirk128": lambda: (_stride_quirk128(), ALL),
     "alpha_corner_only": lambda: (_with_alpha(_patchy(64, 64, 29, 4, 3), _alpha_island(64, 64, 40, 40, 64, 64)), ALL),
 }
 
@@ -104,6 +119,7 @@ CHROMA_CASES = [
     ("alpha_island256", ("alpha", "grad"), (1, 1, 1, 1), (3, 4)),  # max / min box
     ("noise64", (), (1, 0, 1, 0), (2, 2)),                         # no gradient stage before (all pixels coded)
     ("alpha_corner_only", ("alpha", "grad"), (1, 1, 1, 0), (1, 2)),
+    ("alpha_stride_quirk128", ("alpha", "grad"), (1, 1, 1, 1), (2, 2)),   # reduced-stride mask samples on claimed cells
 ]
 
 

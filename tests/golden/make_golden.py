@@ -26,7 +26,7 @@ GOLDEN_CASES = ["ramp64_a2", "patchy128", "patchy_72x40", "noise_delta1", "noise
 
 
 # chroma front-end fixtures: indices into cases.CHROMA_CASES (the CLI configuration, quarter size with alpha, one axis each)
-CHROMA_GOLDEN = [0, 1, 2]
+CHROMA_GOLDEN = [0, 1, 2, 7]
 
 
 def digest(a):

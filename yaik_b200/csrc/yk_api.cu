@@ -72,7 +72,7 @@ struct YkSlotHost {
     // alpha results (host)
     int bound[4] = { 0, 0, 0, 0 }, remaining = 0, wroteChunk = 0, chunkBBox[4] = { 0, 0, 0, 0 };
     std::vector<uint8_t> alphaBitmap;
-    void* devAllocs[64]; int nAllocs = 0;
+    std::vector<void*> devAllocs;        // every device allocation of the slot (freed by yk_destroy)
     // strip mode: one allocation [3 * w int32 pixel row][latW touch words from above][latW touch words from below]
     uint8_t* haloIn = nullptr; size_t haloBytes = 0;
 };
@@ -146,7 +146,7 @@ static size_t r1_status_words(int W, int H) { return ((size_t)(W / 8 + 1) * (H /
 template <class T> static int dev_alloc(YkSlotHost& s, T** out, size_t count) {
     void* p = nullptr;
     CK(cudaMalloc(&p, (count ? count : 1) * sizeof(T) + 64));
-    if (s.nAllocs < 64) s.devAllocs[s.nAllocs++] = p;
+    s.devAllocs.push_back(p);
     *out = (T*)p;
     return YK_OK;
 }
@@ -192,6 +192,9 @@ static int encode_slot_tmaps(YkSlotHost& s) {
     return YK_OK;
 }
 
+static int create_fill(yk_ctx* c);
+extern "C" void yk_destroy(yk_ctx* c);
+
 extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPlanes, int maxSlots) {
     if (!out || maxW < 4 || maxH < 4 || (maxW & 3) || (maxH & 3) || maxPlanes < 3 || maxPlanes > 4 || maxSlots < 1) return YK_ERR_ARG;
     if (maxW > 32764 || maxH > 32764) return YK_ERR_ARG;      // BoundingBox is s16 in the stream headers (YAIK_private.h:15-20)
@@ -202,6 +205,14 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
     yk_ctx* c = new yk_ctx();
     c->device = device; c->maxW = maxW; c->maxH = maxH; c->maxPlanes = maxPlanes; c->maxSlots = maxSlots;
     c->slots.resize(maxSlots);
+    const int rcCreate = create_fill(c);
+    if (rcCreate) { yk_destroy(c); return rcCreate; }        // releases the stream and every allocation made so far
+    *out = c;
+    return YK_OK;
+}
+
+static int create_fill(yk_ctx* c) {
+    const int maxW = c->maxW, maxH = c->maxH, maxPlanes = c->maxPlanes, maxSlots = c->maxSlots;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->ownStream = true;
     { const int e = yk_analyze_setup(&c->numSMs); if (e) { g_lastCuda = std::string("yk_analyze_setup: ") + cudaGetErrorString((cudaError_t)e); return YK_ERR_CUDA; } }
@@ -238,7 +249,7 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
     }
     c->zeroStride = off;
     CK(cudaMalloc((void**)&c->zeroArea, c->zeroStride * maxSlots));
-    CK(cudaMemset(c->zeroArea, 0, c->zeroStride * maxSlots));
+    CK(cudaMemsetAsync(c->zeroArea, 0, c->zeroStride * maxSlots, c->stream));     // on the context's own (non-blocking) stream: ordered before its first launch
     for (int i = 0; i < maxSlots; i++) {
         YkSlotHost& s = c->slots[i];
         memset(&s.d, 0, sizeof s.d);
@@ -272,16 +283,16 @@ extern "C" int yk_create(yk_ctx** out, int device, int maxW, int maxH, int maxPl
         }
     }
     { const char* e = getenv("YK_PACK_THREADS"); c->packer = yk_hostpack_create(e ? atoi(e) : 0); }
-    *out = c;
+    CK(cudaStreamSynchronize(c->stream));
     return YK_OK;
 }
 
 extern "C" void yk_destroy(yk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->ownStream || c->stream) cudaStreamSynchronize(c->stream);
     for (auto& s : c->slots) {
-        for (int i = 0; i < s.nAllocs; i++) cudaFree(s.devAllocs[i]);
+        for (void* p : s.devAllocs) cudaFree(p);
         if (s.haloIn) cudaFree(s.haloIn);
         if (s.stageHost) cudaFreeHost(s.stageHost);
         if (s.arena) cudaFreeHost(s.arena);
@@ -738,7 +749,6 @@ extern "C" int yk_gradient_pass(yk_ctx* c, int slot, int rejectFactor, int shX, 
         // results of the fused cascade are only what the reference would compute if the passes are consumed in
         // Convert()'s order with the same rejectFactor
         if (pid != s.nextPass || rejectFactor != s.preparedReject) return YK_ERR_STATE;
-        s.nextPass++;
     } else {
         YkRun run; memset(&run, 0, sizeof run);
         run.nPasses = 1; run.passId[0] = pid; run.rejectFactor = rejectFactor;
@@ -753,6 +763,7 @@ extern "C" int yk_gradient_pass(yk_ctx* c, int slot, int rejectFactor, int shX, 
     if (nb > bitmapCap || nrgb > rgbCap) return YK_ERR_CAPACITY;
     if (bitmap) memcpy(bitmap, s.arena + s.arBitmap[pid], nb);
     if (rgb && nrgb) memcpy(rgb, s.arena + s.arRgb[pid], nrgb);
+    if (s.prepared) s.nextPass++;          // consumed only now: a capacity / CUDA error above leaves the pass available for a retry
     if (bitmapBytes) *bitmapBytes = nb;
     if (rgbBytes) *rgbBytes = nrgb;
     if (tileDone) *tileDone = st[YK_ST_TILEDONE];
@@ -832,7 +843,11 @@ static int ensure_r1_lut(yk_ctx* c) {
         }
     }
     CK(cudaMalloc((void**)&c->lutDev, lut.size() * sizeof(int)));
-    CK(cudaMemcpy(c->lutDev, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // on the context's stream (non-blocking: it does not order itself after the legacy stream), and complete before the
+    // pageable host vector goes away
+    cudaError_t e = cudaMemcpyAsync(c->lutDev, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { cudaFree(c->lutDev); c->lutDev = nullptr; g_lastCuda = std::string("R1 table upload: ") + cudaGetErrorString(e); return YK_ERR_CUDA; }
     return YK_OK;
 }
 
@@ -982,7 +997,8 @@ extern "C" int yk_download_state(yk_ctx* c, int slot, int32_t* smoothMap, int32_
     if (rc) return rc;
     if (recon && (rc = ensure_int32(c, slot))) return rc;
     const size_t n = (size_t)s.d.w * s.d.h, n1 = (size_t)(s.d.w + 1) * (s.d.h + 1);
-    int32_t *dSmooth = nullptr, *dMask = nullptr, *dMapped = nullptr, *dRec = nullptr;
+    struct Tmp { int32_t* p = nullptr; ~Tmp() { if (p) cudaFree(p); } } gSmooth, gMask, gMapped, gRec;     // freed on every way out
+    int32_t *&dSmooth = gSmooth.p, *&dMask = gMask.p, *&dMapped = gMapped.p, *&dRec = gRec.p;
     const bool wantSmooth = smoothMap || mapSmoothTile, wantRec = recon != nullptr;
     if (wantSmooth) CK(cudaMalloc((void**)&dSmooth, n * 4));
     if (mipmapMask) CK(cudaMalloc((void**)&dMask, n * 4));
@@ -997,7 +1013,6 @@ extern "C" int yk_download_state(yk_ctx* c, int slot, int32_t* smoothMap, int32_
     if (mappedRGB) for (int p = 0; p < 3; p++) if (mappedRGB[p]) CK(cudaMemcpyAsync(mappedRGB[p], dMapped, n1 * 4, cudaMemcpyDeviceToHost, c->stream));
     if (recon) for (int p = 0; p < 3; p++) if (recon[p]) CK(cudaMemcpyAsync(recon[p], dRec + p * n, n * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(dSmooth); cudaFree(dMask); cudaFree(dMapped); cudaFree(dRec);
     return YK_OK;
 }
 
@@ -1072,7 +1087,10 @@ extern "C" int yk_strip_config(yk_ctx* c, int slot, int imgH, int y0) {
         CK(cudaMalloc((void**)&s.haloIn, need));
         s.haloBytes = need;
     }
+    // complete before this returns: the neighbour strips write into this buffer from other streams / processes, and
+    // nothing else orders their copies after a clear still queued here
     CK(cudaMemsetAsync(s.haloIn, 0, need, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     s.d.imgH = imgH; s.d.y0 = y0;
     s.d.hasAbove = y0 > 0; s.d.hasBelow = y0 + h < imgH;
     for (int p = 0; p < 3; p++) s.d.rowBelow[p] = s.d.hasBelow ? (const void*)(s.haloIn + p * rowBytes) : nullptr;

@@ -216,6 +216,12 @@ static __device__ __forceinline__ bool yk_r1_smooth_at(const YkSlotDev& S, int f
     return (S.cellMask[(size_t)(fy >> 2) * S.nbx + (cx >> 4)] >> (cx & 15)) & 1u;
 }
 
+// mipmapMask != 0 at linear index i of the full-size mask plane
+static __device__ __forceinline__ bool yk_r1_valid_at(const YkSlotDev& S, size_t i) {
+    const int fx = (int)(i % (size_t)S.w), fy = (int)(i / (size_t)S.w);
+    return yk_r1_mask_at(S, fx, fy) && !yk_r1_smooth_at(S, fx, fy);
+}
+
 // The walk of LeftRightOrder (framework.h:228-256) over the constraint box of a plane of pw x ph samples: rows of
 // nbw = ceil(cw / 8) blocks while y < cy + ch, then one more block at the start of the next row when that row still
 // lies inside the plane (HasNextBlock tests `y < h` after the wrap).  Block sizes: the reference compares with the
@@ -304,10 +310,13 @@ yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, const YkR1Args A, 
                 for (int q = 0; q < 2; q++) {
                     const size_t vi = ((size_t)(x + c0 + q) << A.shX) + (size_t)((y + r) << A.shY) * A.pw;
                     const int W = S.w;
-                    bool any = yk_r1_mask_at(S, (int)(vi % W), (int)(vi / W));
-                    if (A.shX) any |= yk_r1_mask_at(S, (int)((vi + 1) % W), (int)((vi + 1) / W));
-                    if (A.shY) any |= yk_r1_mask_at(S, (int)((vi + A.pw) % W), (int)((vi + A.pw) / W));
-                    if (A.shX && A.shY) any |= yk_r1_mask_at(S, (int)((vi + A.pw + 1) % W), (int)((vi + A.pw + 1) / W));
+                    // every covered sample is a mipmapMask value: kept by the alpha stage AND not claimed by a gradient
+                    // tile (FittingQuadSmooth zeroes the mask over accepted tiles, EC.cpp:4035); with the reduced width as
+                    // row stride the samples of the second row lie in another cell than vi
+                    bool any = yk_r1_valid_at(S, vi);
+                    if (A.shX) any |= yk_r1_valid_at(S, vi + 1);
+                    if (A.shY) any |= yk_r1_valid_at(S, vi + A.pw);
+                    if (A.shX && A.shY) any |= yk_r1_valid_at(S, vi + A.pw + 1);
                     const bool ok = any && !yk_r1_smooth_at(S, (int)(vi % W), (int)(vi / W));
                     if (q) m1 = ok; else m0 = ok;
                 }
