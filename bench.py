@@ -37,6 +37,37 @@ UNIT = "MP/s"
 WORKLOAD = "single synthetic 2048x2048 RGBA texture with alpha holes (alpha bitmap + full tile cascade + R2 range stage) per step"
 
 
+def n_regions(steps):
+    """Timed regions of K steps each in one run of the GPU arm (the mean is reported): a single region of 20 steps lasts
+    about a millisecond, which measures launch jitter rather than the GPU."""
+    return max(1, min(10, 400 // max(1, steps)))
+
+
+def base_config(args):
+    """`config` of both arms' lines (identical dictionaries: the driver compares them)."""
+    return {"workload": WORKLOAD, "images_per_step_per_gpu": 1, "sharding": "by image, no collective",
+            "stages": "MipPrefilter + 7x FittingQuadSmooth + 3x DynamicTileCompressor, results left in HBM",
+            "l2": "GPU arm: inputs rotate over 8 distinct resident 64 MiB textures (512 MiB > 126 MB L2), so every step reads cold planes",
+            "timed_regions": f"GPU arm: {n_regions(args.steps)} regions of {args.steps} steps, each bracketed by barrier + synchronize, mean reported"}
+
+
+def results_digest(r) -> str:
+    """SHA-1 over everything yk_fetch_all returned for one image (the same fields tests/parity.py digests)."""
+    import hashlib
+    h = hashlib.sha1()
+    for p in r["passes"]:
+        if p is None:
+            h.update(b"-")
+            continue
+        h.update(p["bitmap"].tobytes()); h.update(p["rgb"].tobytes()); h.update(str((p["tiledone"], list(p["bbox"]))).encode())
+    for q in r["r2"]:
+        h.update(q["idx"].tobytes()); h.update(q["type"].tobytes())
+    a = r.get("alpha")
+    if a:
+        h.update(a["bitmap"].tobytes()); h.update(str((a["bound"], a["remaining"], a["wrote"], a["chunk_bbox"])).encode())
+    return h.hexdigest()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -163,7 +194,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_side": side},
+            "config": base_config(args), "sample_side": side,
             "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -220,10 +251,12 @@ def main():
         c.set_analysis_ctas(actas)     # launches of neighbouring steps run side by side on disjoint SMs: ramp and tail of one hide behind the others
     ctx, stream = ctxs[0], streams[0]
 
-    # two distinct textures per rank, uploaded alternately into the 8 slots (distinct HBM addresses are what defeats L2)
-    imgs = [make_image(W, H, CH, SEED_BASE + 1 + 16 * rank + i) for i in range(2)]
+    # eight distinct textures per rank, one per slot (distinct contents and distinct HBM addresses)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(4) as ex:
+        imgs = list(ex.map(lambda i: make_image(W, H, CH, SEED_BASE + 1 + 16 * rank + i), range(NSLOTS)))
     for s in range(NSLOTS):
-        ctxs[s % NCTX].set_image(imgs[(s // NCTX) % 2], s // NCTX)
+        ctxs[s % NCTX].set_image(imgs[s], s // NCTX)
     STAGES = capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D
 
     def step(i):
@@ -257,28 +290,37 @@ def main():
     lib.yk_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     sampler = ClockSampler(physical_gpu_index(local))
     launches0 = sum(c.launch_count() for c in ctxs)
-    barrier()
     for c in ctxs:
         lib.yk_profile(c.ctx, 1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     joins = [torch.cuda.Event() for _ in streams]
     sampler.sample()
     sampler.start()
-    ev0.record(stream)                      # every stream starts after ev0 ...
-    for st in streams[1:]:
-        st.wait_event(ev0)
-    for i in range(args.steps):
-        step(i)
-    for st, j in zip(streams[1:], joins[1:]):
-        j.record(st)
-        stream.wait_event(j)                # ... and ev1 is recorded after all of them have finished
-    ev1.record(stream)
-    sampler.sample()
-    barrier()
+    NREG = n_regions(args.steps)
+    region_ms = []
+    for reg in range(NREG):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)                      # every stream starts after ev0 ...
+        for st in streams[1:]:
+            st.wait_event(ev0)
+        for i in range(args.steps):
+            step(i)
+        for st, j in zip(streams[1:], joins[1:]):
+            j.record(st)
+            stream.wait_event(j)                # ... and ev1 is recorded after all of them have finished
+        ev1.record(stream)
+        sampler.sample()
+        barrier()
+        t_ms = ev0.elapsed_time(ev1)
+        if dist is not None:                    # a region lasts as long as its slowest rank
+            t = torch.tensor([t_ms], device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        region_ms.append(t_ms)
     sampler.stop_flag = True
     sampler.sample()
-    ms = ev0.elapsed_time(ev1)
-    launches = sum(c.launch_count() for c in ctxs) - launches0
+    ms = sum(region_ms) / len(region_ms)
+    launches = (sum(c.launch_count() for c in ctxs) - launches0) // NREG
     kms = (C.c_double * 8)(); kcnt = (C.c_longlong * 8)()
     for c in ctxs:
         a = (C.c_double * 8)(); b = (C.c_longlong * 8)()
@@ -286,11 +328,24 @@ def main():
         lib.yk_profile(c.ctx, 0)
         for k in range(8):
             kms[k] += a[k]; kcnt[k] += b[k]
-    if dist is not None:
-        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     mp_per_step = W * H / 1e6
+
+    # ---- parity of what was just timed: every context's streams (as left by the last timed step on it) against an untimed
+    # run of the same texture on a fresh context with one CTA per SM (the configuration tests/test_gpu_parity.py compares
+    # with the oracle at this size).  A mismatch fails the run.
+    sync_all()
+    got = [results_digest(ctxs[s % NCTX].fetch_all(s // NCTX)) for s in range(NSLOTS)]
+    cref = capi.Context(W, H, planes=CH, slots=1, device=local, lib=lib)
+    cref.set_upload_format(False)
+    want = []
+    for s in range(NSLOTS):
+        cref.set_image(imgs[s], 0)
+        cref.analyze(STAGES)
+        want.append(results_digest(cref.fetch_all(0)))
+    cref.close()
+    if got != want:
+        raise SystemExit(f"bench.py: results of the timed configuration differ from the single-context run: {got} vs {want}")
+    parity_checked = True
     value = world * mp_per_step * args.steps / (ms / 1e3)
 
     # algorithmic bytes per image: every input plane read once + every emitted pre-entropy stream
@@ -323,7 +378,7 @@ def main():
         if dom:
             ach = alg_bytes / (dom * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "yk_k_analyze", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                    "traffic": None, "peak_source": peak_src + ", burst copy figure (kernel timed alone)", "algorithmic_bytes_per_launch": alg_bytes,
+                    "traffic": None, "traffic_source": None, "peak_source": peak_src + ", burst copy figure (kernel timed alone)", "algorithmic_bytes_per_launch": alg_bytes,
                     "how": f"{int(akcnt[0])} launches timed alone after the pipelined region: one stream at a time, one CTA per SM, CUDA event pair around each launch",
                     "kernel_ms": {k: (round(v, 5) if v else None) for k, v in kern_ms.items()},
                     "kernel_ms_inside_pipelined_region": {k: (round(v, 5) if v else None) for k, v in kern_ms_pipe.items()},
@@ -331,7 +386,9 @@ def main():
             tp = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tp):
                 try:
-                    roof["traffic"] = json.load(open(tp)).get("yk_k_analyze_dram_bytes_per_launch")
+                    tj = json.load(open(tp))
+                    roof["traffic"] = tj.get("yk_k_analyze_dram_bytes_per_launch")
+                    roof["traffic_source"] = "constant from the committed ncu --set full capture, profiles/traffic.json: " + str(tj.get("source", "r01q"))
                 except Exception:
                     pass
 
@@ -351,7 +408,7 @@ def main():
         for t in range(nthr):
             hp = [lib.yk_host_alloc(nbytes) for _ in range(CH)]
             for c in range(CH):
-                C.memmove(hp[c], imgs[t % 2][c].ctypes.data, nbytes)
+                C.memmove(hp[c], imgs[t % NSLOTS][c].ctypes.data, nbytes)
             hps.append(hp)
         moved = [0] * nthr
 
@@ -385,7 +442,8 @@ def main():
         e2e = {"value": round(world * mp_per_step * per * nthr / dt, 2), "unit": UNIT, "h2d_bytes_per_step": CH * pitch * H,
                "d2h_bytes_per_step": int(moved[0]), "steps": per * nthr, "host_threads": nthr,
                "what": "per step: yk_set_image from pinned host int32 planes (64 MiB, packed to bytes by host threads, 16 MiB over PCIe) "
-                       "+ yk_analyze + yk_fetch_all (all result streams to pinned host memory); wall clock"}
+                       "+ yk_analyze + yk_fetch_all (all result streams to pinned host memory); wall clock. The reference's host tails "
+                       "(PaletteCompressor + ZSTD-18 inside FittingQuadSmooth, about 3 % of the CPU arm's time) are not part of this figure"}
         for c in ectx:
             c.close()
         for hp in hps:
@@ -432,10 +490,11 @@ def main():
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "images_per_step_per_gpu": 1, "sharding": "by image, no collective",
-                           "pipelining": f"steps are independent textures, issued round-robin on {NCTX} CUDA streams (contexts); analysis launches of {actas or sms} CTAs on {sms} SMs",
-                           "l2": "inputs rotate over 8 resident 64 MiB images (512 MiB > 126 MB L2), so every step reads cold planes",
-                           "stages": "MipPrefilter + 7x FittingQuadSmooth + 3x DynamicTileCompressor, results left in HBM", "kernels_per_step": "yk_k_analyze (persistent, TMA-staged, range stage fused) + yk_k_owner + yk_k_emit"},
+                "config": base_config(args),
+                "run": {"pipelining": f"steps are independent textures, issued round-robin on {NCTX} CUDA streams (contexts); analysis launches of {actas or sms} CTAs on {sms} SMs",
+                        "kernels_per_step": "yk_k_analyze (persistent, TMA-staged, range stage fused) + yk_k_owner + yk_k_emit",
+                        "region_ms": [round(x, 4) for x in region_ms]},
+                "parity_checked": parity_checked,
                 "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "stages_outside_metric": other}
         print(json.dumps(line), flush=True)

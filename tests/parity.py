@@ -16,11 +16,33 @@ def _eq(a, b, what):
                              f"(got {a.ravel()[first:first + 8].tolist()} want {b.ravel()[first:first + 8].tolist()}), {diff.size} differ")
 
 
-def check_image(ctx: "capi.Context", planes: np.ndarray, stages, *, fused=True, state=True, slot=0):
-    """stages as in tests/cases.py.  fused=True: one yk_analyze then getters; False: stage-by-stage calls."""
+def results_digest(r) -> str:
+    """SHA-1 over everything Context.fetch_all() returned for one image (bitmaps, rgbStreams, TileDone, boxes, R2 streams,
+    alpha results): equal digests == identical streams."""
+    import hashlib
+    h = hashlib.sha1()
+    for p in r["passes"]:
+        if p is None:
+            h.update(b"-")
+            continue
+        h.update(p["bitmap"].tobytes()); h.update(p["rgb"].tobytes()); h.update(str((p["tiledone"], list(p["bbox"]))).encode())
+    for q in r["r2"]:
+        h.update(q["idx"].tobytes()); h.update(q["type"].tobytes())
+    a = r.get("alpha")
+    if a:
+        h.update(a["bitmap"].tobytes()); h.update(str((a["bound"], a["remaining"], a["wrote"], a["chunk_bbox"])).encode())
+    return h.hexdigest()
+
+
+def check_image(ctx: "capi.Context", planes: np.ndarray, stages, *, fused=True, state=True, slot=0, load=None):
+    """stages as in tests/cases.py.  fused=True: one yk_analyze then getters; False: stage-by-stage calls.
+    load(ctx, planes, slot): how the samples get into the context (default: yk_set_image from host planes)."""
     c, h, w = planes.shape
     o = Oracle(planes)
-    ctx.set_image(planes, slot)
+    if load is None:
+        ctx.set_image(planes, slot)
+    else:
+        load(ctx, planes, slot)
     do_alpha = "alpha" in stages and c == 4
     do_grad = "grad" in stages
     do_r2 = "r2" in stages

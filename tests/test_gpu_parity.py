@@ -143,6 +143,82 @@ def test_config1_2048_rgba_properties(lib):
         c.close()
 
 
+def _load_device_planes(c, planes, slot):
+    """int32 planes the caller put in HBM, handed over with yk_set_image_device (what bench.py's `value` runs on)."""
+    ch, h, w = planes.shape
+    ptrs = []
+    for i in range(ch):
+        ptrs.append(c.device_plane(slot, i))
+        c.copy_from_host(ptrs[-1], np.ascontiguousarray(planes[i], dtype=np.int32))
+    c.set_image_device(ptrs, ch, w, h, slot)
+
+
+@pytest.mark.parametrize("how", ["int32_upload", "device_planes"])
+def test_config1_2048_rgba_int32_kernel_full_compare(lib, how):
+    """BASELINE.json configs[1] through the int32 variant of the analysis kernel (yk_k_analyze, the one bench.py times):
+    yk_set_upload_format(0) + yk_set_image, and yk_set_image_device on resident planes; every stream against the oracle."""
+    planes = make_image(2048, 2048, 4, SEED_BASE + 1)
+    c = capi.Context(2048, 2048, planes=4, slots=1, lib=lib)
+    try:
+        c.set_upload_format(False)
+        check_image(c, planes, ("alpha", "grad", "r2"), state=False, load=_load_device_planes if how == "device_planes" else None)
+    finally:
+        c.close()
+
+
+def test_bench_configuration_matches_oracle(lib):
+    """The configuration bench.py times: 8 contexts on 8 CUDA streams, analysis launches of a quarter of the SMs, int32 planes
+    resident in HBM, 8 distinct 2048x2048 RGBA textures issued round-robin without synchronising in between.  Every
+    context's result must equal the digest of a single-context, full-SM run that was itself compared with the oracle."""
+    import torch
+    from parity import results_digest
+    st = capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D
+    imgs = [make_image(2048, 2048, 4, SEED_BASE + 1 + i) for i in range(8)]
+    c0 = capi.Context(2048, 2048, planes=4, slots=1, lib=lib)
+    want = []
+    try:
+        c0.set_upload_format(False)
+        for k, im in enumerate(imgs):
+            if k < 2:
+                check_image(c0, im, ("alpha", "grad", "r2"), state=False)      # oracle-verified
+            else:
+                c0.set_image(im); c0.analyze(st)
+            want.append(results_digest(c0.fetch_all(0)))
+    finally:
+        c0.close()
+    ctxs = [capi.Context(2048, 2048, planes=4, slots=1, lib=lib) for _ in range(8)]
+    streams = [torch.cuda.Stream() for _ in range(8)]
+    try:
+        for c, s, im in zip(ctxs, streams, imgs):
+            c.set_stream(s.cuda_stream); c.set_upload_format(False); c.set_analysis_ctas(c.sm_count() // 4)
+            _load_device_planes(c, im, 0)
+        for rep in range(6):
+            for c in ctxs:
+                c.reset_state(0); c.analyze(st)
+        got = [results_digest(c.fetch_all(0)) for c in ctxs]
+        assert got == want
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_config4_mip_chain_4096(lib):
+    """BASELINE.json configs[4] at the size it is quoted on: RGBA mip chain 4096 -> 4, every level against the oracle."""
+    chain = mip_chain(4096, SEED_BASE + 4)
+    c = capi.Context(4096, 4096, planes=4, slots=1, lib=lib)
+    try:
+        for lvl in chain:
+            s = lvl.shape[1]
+            stages = ["grad"]
+            if s >= 16 and lvl[3].any():
+                stages.append("alpha")
+            if s >= 8:
+                stages.append("r2")
+            check_image(c, lvl, tuple(stages), state=(s <= 512))
+    finally:
+        c.close()
+
+
 def test_config4_mip_chain(lib):
     """BASELINE.json configs[4]: RGBA mip chain down to 4x4 (small-tile and alpha-rejection paths); levels run the
     stages the reference itself supports at that size (SURVEY.md hazards 7, 11)."""
@@ -233,18 +309,13 @@ def test_streams_decode_with_the_reference_decoders_corner_rule(lib, w, h, ch, s
 def test_repeatability_under_concurrency(lib):
     """The persistent kernel's queue / barrier protocol under load: four contexts on four host threads analyse the same
     1024x1024 textures over and over, with full and half-size analysis launches; every run must give the same streams."""
-    import hashlib, threading
+    import threading
+    from parity import results_digest
     imgs = [make_image(1024, 1024, 4, SEED_BASE + 40 + i) for i in range(2)]
     st = capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D
 
     def digest(c):
-        r = c.fetch_all(0, copy=True)
-        h = hashlib.sha1()
-        for p in r["passes"]:
-            h.update(p["bitmap"].tobytes()); h.update(p["rgb"].tobytes()); h.update(str((p["tiledone"], p["bbox"])).encode())
-        for q in r["r2"]:
-            h.update(q["idx"].tobytes()); h.update(q["type"].tobytes())
-        return h.hexdigest()
+        return results_digest(c.fetch_all(0, copy=True))
 
     ref = []
     c0 = capi.Context(1024, 1024, planes=4, slots=1, lib=lib)
@@ -284,6 +355,23 @@ def test_strips_on_one_gpu_match_whole_image(lib, w, h, n):
     ctxs = [capi.Context(w, h, planes=3, slots=1, lib=lib) for _ in range(n)]
     try:
         merged = strips.LocalTransport(ctxs).run(planes, n_strips=n)
+        check_against_oracle(merged, planes)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_strips_4096x16384_match_oracle(lib):
+    """configs[3] at a quarter of its width and its full height (67 Mpixel RGB, 4 strips of 4096 rows): the merged streams
+    against the oracle on the whole image."""
+    from strips_check import check_against_oracle
+    from yaik_b200 import strips
+    base = make_image(2048, 2048, 3, SEED_BASE + 3)
+    planes = np.ascontiguousarray(np.tile(base, (1, 8, 2)))
+    assert planes.shape == (3, 16384, 4096)
+    ctxs = [capi.Context(4096, 4096, planes=3, slots=1, lib=lib) for _ in range(4)]
+    try:
+        merged = strips.LocalTransport(ctxs).run(planes, n_strips=4)
         check_against_oracle(merged, planes)
     finally:
         for c in ctxs:
