@@ -127,6 +127,7 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
 }
 static inline int __vimax3_s32(int a, int b, int c) { return std::max(a, std::max(b, c)); }
 static inline int __vimin3_s32(int a, int b, int c) { return std::min(a, std::min(b, c)); }
+static inline unsigned __vmaxu2(unsigned a, unsigned b) { return std::max(a & 0xFFFFu, b & 0xFFFFu) | (std::max(a >> 16, b >> 16) << 16); }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __int2float_rn(int a) { return (float)a; }

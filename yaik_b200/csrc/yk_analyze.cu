@@ -76,7 +76,10 @@ struct YkaSlotC {
 #define YKA_NSTAT YK_HD_INTS                         // per-pass counters + alpha box / count, laid out like the image header
 
 struct YkaShared {
-    uint2    passLane[YK_NPASS][32];    // per pass and lane: lanes sharing its tile (x), packed geometry of the lane in that pass (y)
+    uint4    passLane[YK_NPASS][32];    // per pass and lane: see yka_pass_lane_entry
+    unsigned long long runTiles;    // bits (of the 41 tiles of a macro tile) of the passes this launch runs
+    int      rpOf[8];               // pass id -> its position in the run
+    uint8_t  passOfTile[48];        // tile bit -> pass id
     uint32_t pretestTab[41];
     int      queueHead;             // next (unit sequence number * 8 + macro tile) to hand out
     int      endSeq;                // first unit sequence number that does not exist
@@ -87,15 +90,21 @@ struct YkaShared {
     unsigned long long rawFull[YKA_NR];     // raw buffer i: its TMA boxes have landed
     unsigned long long rawFree[YKA_NR];     // raw buffer i: the four macro tiles of the row have been packed out of it
     YkaUnit  unit[YKA_NR];
-    uint32_t touch[YKA_CONS_WARPS][25];     // touch words of the 5x5 lattice points of the macro tile a warp works on
-    YkaSlotC slotc[YKA_CONS_WARPS];
+};
+
+// everything a consumer warp owns, in one block (one base address serves all of it)
+struct alignas(128) YkaWarpArea {
+    uint8_t  priv[YKP_TILE];        // the macro tile's 17x17 samples, three channels, as bytes
+    uint8_t  hist[768];             // byte counters of the range stage, one 256-byte histogram per plane
+    uint32_t touch[28];             // touch words of the 5x5 lattice points of the macro tile
+    int      wstat[40];             // 8 groups x 5 counters (see yka_stat_add)
+    YkaSlotC slotc;
 };
 
 #define YKA_SMEM_RAW   (YKA_NR * YKA_RAW_STAGE_INTS * 4)
-#define YKA_SMEM_PIX   ((YKA_CONS_WARPS * YKP_TILE + 127) / 128 * 128)
-#define YKA_SMEM_HIST  (YKA_CONS_WARPS * 3 * 256)
-#define YKA_SMEM_BYTES (YKA_SMEM_RAW + YKA_SMEM_PIX + YKA_SMEM_HIST + 1024 + (int)sizeof(YkaShared))
-static_assert(YKA_SMEM_PIX % 128 == 0 && (YKA_CONS_WARPS * 3 * 256) % 128 == 0, "shared-memory carving keeps 128-byte alignment");
+#define YKA_SMEM_WARPS (YKA_CONS_WARPS * (int)sizeof(YkaWarpArea))
+#define YKA_SMEM_BYTES (YKA_SMEM_RAW + YKA_SMEM_WARPS + 1024 + (int)sizeof(YkaShared))
+static_assert(sizeof(YkaWarpArea) % 128 == 0 && YKP_TILE % 16 == 0, "shared-memory carving keeps 128-byte alignment");
 
 // ------------------------------------------------------------------------------------------------------------------
 // mbarrier / TMA / shared-flag primitives (inline PTX), with stand-ins for the CPU logic emulation (tests/emu)
@@ -175,21 +184,32 @@ static __device__ __forceinline__ unsigned yka_pack4(int4 v) {      // low bytes
 }
 static __device__ __forceinline__ int yka_byte(unsigned word, int k) { return (int)__byte_perm(word, 0u, 0x4440u | (unsigned)k); }
 
-// Lane geometry of one pass, computed once per CTA.  Lane (row = lane >> 1, half = lane & 1) owns the eight pixels
-// (8*half .. 8*half+7, row) of the macro tile in every pass.  y: lyT | dy << 5 | leader << 9 | lxT(sub 0) << 10 | dx0 << 14 |
-// t(sub 0) << 18 | lxT(sub 1) << 22 | t(sub 1) << 26   (sub 1 only for 4-pixel-wide tiles: the lane's right quad)
-static __device__ __forceinline__ uint2 yka_pass_lane_entry(int pid, int lane) {
+// Lane geometry of one pass, computed once per CTA.  Every lane owns two quads (four consecutive pixels of a row) of
+// the macro tile, both inside one tile of the pass:
+//   tiles 8 or 16 wide   lane (row = lane >> 1, half = lane & 1): the quads at x = 8*half and 8*half + 4 of that row
+//   tiles 4 wide         lane (tx = lane & 3, rp = lane >> 2): the quads at x = 4*tx of rows 2*rp and 2*rp + 1
+// (so a pass over 4-wide tiles is one sweep as well).  Entry: x = lanes sharing my tile; y = byte offset of quad 0 | of
+// quad 1 << 16 inside a channel of the private tile; z = offset of the tile's top-left sample | the tile's 4x4 cells
+// (bit = 4*cellY + cellX) << 16; w = dx0 | dy << 8 | tile index << 16 | leader << 24 (dx0, dy: quad 0 inside the tile).
+static __device__ __forceinline__ uint4 yka_pass_lane_entry(int pid, int lane) {
     const YkGeomS g = yk_geom_s(pid);
-    const int row = lane >> 1, half = lane & 1, shx = g.shx, shy = g.shy, TH = 1 << shy;
-    const int ty = row >> shy, lyT = ty << shy, dy = row - lyT;
-    const unsigned rowMask = (shy == 4) ? YK_FULL : (((1u << (2 * TH)) - 1u) << (2 * lyT));
-    const unsigned gmask = (shx == 4) ? rowMask : (rowMask & (0x55555555u << half));
+    const int shx = g.shx, shy = g.shy, TW = 1 << shx, TH = 1 << shy;
+    int x0, y0, x1, y1;
+    if (shx == 2) { x0 = x1 = 4 * (lane & 3); y0 = 2 * (lane >> 2); y1 = y0 + 1; }
+    else { x0 = 8 * (lane & 1); x1 = x0 + 4; y0 = y1 = lane >> 1; }
+    const int tx = x0 >> shx, ty = y0 >> shy, lxT = tx << shx, lyT = ty << shy;
+    unsigned gmask = 0;
+    for (int l = 0; l < 32; l++) {
+        const int lx = (shx == 2) ? 4 * (l & 3) : 8 * (l & 1), ly = (shx == 2) ? 2 * (l >> 2) : (l >> 1);
+        if ((lx >> shx) == tx && (ly >> shy) == ty) gmask |= 1u << l;
+    }
     const int leader = lane == __ffs((int)gmask) - 1;
-    const int tx0 = (shx == 2) ? (2 * half) : ((8 * half) >> shx), tx1 = 2 * half + 1;
-    const int lxT0 = tx0 << shx, lxT1 = tx1 << 2;
-    const int dx0 = (shx == 2) ? 0 : (8 * half - lxT0);
-    const int t0 = ty * (16 >> shx) + tx0, t1 = ty * 4 + tx1;
-    return make_uint2(gmask, (unsigned)(lyT | (dy << 5) | (leader << 9) | (lxT0 << 10) | (dx0 << 14) | (t0 << 18) | ((lxT1 & 15) << 22) | ((t1 & 15) << 26)));
+    const unsigned cols = ((1u << (TW >> 2)) - 1u) << (lxT >> 2);
+    unsigned cells = 0;
+    for (int cy = lyT >> 2; cy < (lyT + TH) >> 2; cy++) cells |= cols << (4 * cy);
+    const int t = ty * (16 >> shx) + tx;
+    return make_uint4(gmask, (unsigned)(y0 * YKP_RS + x0) | ((unsigned)(y1 * YKP_RS + x1) << 16), (unsigned)(lyT * YKP_RS + lxT) | (cells << 16),
+                      (unsigned)(x0 - lxT) | ((unsigned)(y0 - lyT) << 8) | ((unsigned)t << 16) | ((unsigned)leader << 24));
 }
 
 // table entry of tile ti (0..40) of a macro tile: offX | offY << 4 | shx << 8 | shy << 11 | cell << 14
@@ -202,16 +222,33 @@ static __device__ __forceinline__ uint32_t yka_pretest_entry(int ti) {
     return (uint32_t)(offX | (offY << 4) | (shx << 8) | (shy << 11) | (((offY >> 2) * 4 + (offX >> 2)) << 14));
 }
 
-// per-pass counters / alpha box: summed in shared memory for the CTA's main image, else straight in the image's header.
-// Slot k of a group of five: 0 = count (added), 1..4 = min x, min y (stored as extent - value), max x, max y (maxima).
-static __device__ __forceinline__ void yka_stat5(YkaShared& sh, const YkaSlotC& C, int idx0, int n, int a, int b, int c, int d) {
-    if (C.slot == sh.statSlot) {
-        atomicAdd(&sh.stat[idx0], n); atomicMax(&sh.stat[idx0 + 1], a); atomicMax(&sh.stat[idx0 + 2], b);
-        atomicMax(&sh.stat[idx0 + 3], c); atomicMax(&sh.stat[idx0 + 4], d);
-    } else {
-        atomicAdd(&C.hdr[idx0], n); atomicMax(&C.hdr[idx0 + 1], a); atomicMax(&C.hdr[idx0 + 2], b);
-        atomicMax(&C.hdr[idx0 + 3], c); atomicMax(&C.hdr[idx0 + 4], d);
+// per-pass counters / alpha box.  Slot k of a group of five: 0 = count (added), 1..4 = min x, min y (stored as extent -
+// value), max x, max y (maxima).  A consumer warp keeps its own sums in shared memory (group p = pass id p, group 7 = the
+// alpha stage; lane k owns slot k of every group, so no atomics and no barrier) and adds them to the CTA's sums (or, for
+// an image other than the CTA's main one, to the image's header) when its items move to another image and when it retires.
+typedef int YkaStat;                // a warp's 8 groups x 5 slots
+static __device__ __forceinline__ void yka_stat_add(YkaStat* st, int group, int n, int a, int b, int c, int d) {
+    if ((threadIdx.x & 31) == 0) {      // warp-private words: the atomics are fire-and-forget read-modify-writes without contention
+        int* p = st + group * 5;
+        atomicAdd(&p[0], n); atomicMax(&p[1], a); atomicMax(&p[2], b); atomicMax(&p[3], c); atomicMax(&p[4], d);
     }
+}
+static __device__ __forceinline__ void yka_stat_flush(YkaShared& sh, const YkaSlotC& C, YkaStat* st) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (lane < 8 && st[lane * 5]) {
+        const int idx0 = lane < 7 ? YK_HD_PASS0 + lane * YK_ST_STRIDE : YK_HD_ALPHA_KEPT0;
+        int* dst = (C.slot == sh.statSlot) ? &sh.stat[idx0] : &C.hdr[idx0];
+        atomicAdd(&dst[0], st[lane * 5]);
+#pragma unroll
+        for (int k = 1; k < 5; k++) atomicMax(&dst[k], st[lane * 5 + k]);
+    }
+    __syncwarp();
+    if (lane < 8) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) st[lane * 5 + k] = 0;
+    }
+    __syncwarp();
 }
 
 // Consumer warp: its copy of the slot descriptor fields (refreshed when the warp's items move to another image)
@@ -356,26 +393,25 @@ static __device__ __forceinline__ void yka_quad(unsigned word, int s, int step, 
     umax = __vimax3_s32(umax, u0, u1); umax = __vimax3_s32(umax, u2, u3);
 }
 
-struct YkaTile {                    // per lane: the tile it belongs to in the current (sub-)pass
+struct YkaTile {                    // per lane: the tile it belongs to in the current pass
     int shx, shy, sh, negN, dx0, dy, R;
-    bool two;
+    bool wide;                      // tiles 8 or 16 wide: quad 1 continues the row of quad 0; 4 wide: it is the quad below
 };
 
-// one channel of one corner family: this lane's one or two quads against the bilinear fit of (tl, tr, bl, br)
+// one channel of one corner family: this lane's two quads against the bilinear fit of (tl, tr, bl, br)
 static __device__ __forceinline__ void yka_channel(const YkaTile& T, unsigned w0, unsigned w1, int tl, int tr, int bl, int br, int& umin, int& umax) {
     const int B = (tr - tl) << T.shy, C = (bl - tl) << T.shx, D = tl - tr - bl + br;
-    const int step = B + D * T.dy;
-    const int s = ((tl + T.R) << T.sh) + B * T.dx0 + T.dy * (C + D * T.dx0);
+    const int step = B + D * T.dy, down = C + D * T.dx0;
+    const int s = ((tl + T.R) << T.sh) + B * T.dx0 + T.dy * down;
     yka_quad(w0, s, step, T.negN, umin, umax);
-    if (T.two) yka_quad(w1, s + 4 * step, step, T.negN, umin, umax);
+    yka_quad(w1, T.wide ? s + 4 * step : s + down, T.wide ? step : step + D, T.negN, umin, umax);
 }
 
 // The accept test of FittingQuadSmooth (EC.cpp:3810-3998) for the tile this lane belongs to.  The lanes in `gmask` share
-// the tile; each holds one or two quads of one pixel row of it (quad 0 at dx0, quad 1 at dx0 + 4, row dy): both words of
-// `pw`, or for a 4-pixel-wide tile one of them (`second`).
+// the tile; each holds two quads of it (w0 / w1 per channel, see yka_pass_lane_entry).
 // Returns, uniformly over the group, whether any of the six variants (3 corner families x rounded / truncated) keeps
 // every pixel of every channel within the reject factor.
-static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__ corner, const YkaTile& T, const uint2 (&pw)[3], bool second,
+static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__ corner, const YkaTile& T, const unsigned (&w0)[3], const unsigned (&w1)[3],
                                                      unsigned gmask, bool active) {
     const int N = 1 << T.sh, TW = 1 << T.shx, THp = YKP_RS << T.shy;
     const int hiT = (2 * T.R + 1) * N;                  // |cur - S/N| <= R            <=>  0 <= U < hiT
@@ -390,14 +426,14 @@ static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__
     bool resolved = !active;
     // ---- raw corners
     int umin = INT_MAX, umax = INT_MIN;
-    yka_channel(T, second ? pw[0].y : pw[0].x, pw[0].y, cr[0][0], cr[0][1], cr[0][2], cr[0][3], umin, umax);
+    yka_channel(T, w0[0], w1[0], cr[0][0], cr[0][1], cr[0][2], cr[0][3], umin, umax);
     {   // one channel with the raw corners proves most non-gradient tiles hopeless for every variant
         const unsigned bH = __ballot_sync(YK_FULL, (umin < loWide) || (umax >= hiWide));
         if (bH & gmask) resolved = true;
         if (!__any_sync(YK_FULL, !resolved)) return false;
     }
-    yka_channel(T, second ? pw[1].y : pw[1].x, pw[1].y, cr[1][0], cr[1][1], cr[1][2], cr[1][3], umin, umax);
-    yka_channel(T, second ? pw[2].y : pw[2].x, pw[2].y, cr[2][0], cr[2][1], cr[2][2], cr[2][3], umin, umax);
+    yka_channel(T, w0[1], w1[1], cr[1][0], cr[1][1], cr[1][2], cr[1][3], umin, umax);
+    yka_channel(T, w0[2], w1[2], cr[2][0], cr[2][1], cr[2][2], cr[2][3], umin, umax);
     const unsigned bT = __ballot_sync(YK_FULL, (umin < 0) || (umax >= hiT));
     const unsigned bR = __ballot_sync(YK_FULL, (umin < loR) || (umax >= hiT + loR));
     const unsigned bH = __ballot_sync(YK_FULL, (umin < loWide) || (umax >= hiWide));
@@ -409,7 +445,7 @@ static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__
         int umin1 = INT_MAX, umax1 = INT_MIN;
 #pragma unroll
         for (int c = 0; c < 3; c++)
-            yka_channel(T, second ? pw[c].y : pw[c].x, pw[c].y, yk_round6(cr[c][0]), yk_round6(cr[c][1]), yk_round6(cr[c][2]), yk_round6(cr[c][3]), umin1, umax1);
+            yka_channel(T, w0[c], w1[c], yk_round6(cr[c][0]), yk_round6(cr[c][1]), yk_round6(cr[c][2]), yk_round6(cr[c][3]), umin1, umax1);
         const unsigned bT1 = __ballot_sync(YK_FULL, (umin1 < 0) || (umax1 >= hiT));
         const unsigned bR1 = __ballot_sync(YK_FULL, (umin1 < loR) || (umax1 >= hiT + loR));
         if (!resolved && (((bT1 & gmask) == 0u) || ((bR1 & gmask) == 0u))) { accepted = true; resolved = true; }
@@ -420,7 +456,7 @@ static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__
         int umin2 = INT_MAX, umax2 = INT_MIN;
 #pragma unroll
         for (int c = 0; c < 3; c++)
-            yka_channel(T, second ? pw[c].y : pw[c].x, pw[c].y, yk_round6p(cr[c][0]), yk_round6p(cr[c][1]), yk_round6p(cr[c][2]), yk_round6p(cr[c][3]), umin2, umax2);
+            yka_channel(T, w0[c], w1[c], yk_round6p(cr[c][0]), yk_round6p(cr[c][1]), yk_round6p(cr[c][2]), yk_round6p(cr[c][3]), umin2, umax2);
         const unsigned bT2 = __ballot_sync(YK_FULL, (umin2 < 0) || (umax2 >= hiT));
         const unsigned bR2 = __ballot_sync(YK_FULL, (umin2 < loR) || (umax2 >= hiT + loR));
         if (!resolved && (((bT2 & gmask) == 0u) || ((bR2 & gmask) == 0u))) accepted = true;
@@ -428,16 +464,14 @@ static __device__ __forceinline__ bool yka_tile_test(const uint8_t* __restrict__
     return accepted;
 }
 
-// Side effects of an accepted tile (EC.cpp:3998-4132): bitmap bit, TileDone / bounding box, the four lattice points it
+// Side effects of an accepted tile (EC.cpp:3998-4132) other than its counters: bitmap bit, the four lattice points it
 // touches with its role at each.  (gx0, gy0) = tile origin in the image, (tlx, tly) = inside the macro tile.
-static __device__ __forceinline__ void yka_commit(YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch, const YkGeomS& g, int pid, int rp,
+static __device__ __forceinline__ void yka_commit(const YkaSlotC& C, uint32_t* __restrict__ touch, const YkGeomS& g, int pid, int rp,
                                                   int gx0, int gy0, int tlx, int tly) {
     const int TW = 1 << g.shx, TH = 1 << g.shy;
     const int nSwzX = (C.w + (1 << g.lbw) - 1) >> g.lbw;
     const int pos = yk_pos_s(g, nSwzX, gx0 >> g.shx, gy0 >> g.shy);
     atomicOr(&C.bitmap32[pid][pos >> 5], 1u << (pos & 31));                    // EC.cpp:4026
-    // EC.cpp:4039-4044 (mins stored as extent - value)
-    yka_stat5(sh, C, YK_HD_PASS0 + pid * YK_ST_STRIDE, 1, C.w - gx0, INT_MAX / 2 - (C.yOrg + gy0), gx0 + TW, C.yOrg + gy0 + TH);
     const int i0 = tlx >> 2, j0 = tly >> 2;                                    // mappedRGB claim, EC.cpp:4001-4021
     atomicOr(&touch[j0 * 5 + i0], 1u << (4 * rp + 0));
     atomicOr(&touch[j0 * 5 + i0 + (TW >> 2)], 1u << (4 * rp + 1));
@@ -445,43 +479,56 @@ static __device__ __forceinline__ void yka_commit(YkaShared& sh, const YkaSlotC&
     atomicOr(&touch[(j0 + (TH >> 2)) * 5 + i0 + (TW >> 2)], 1u << (4 * rp + 3));
 }
 
-// One FittingQuadSmooth pass over one 16x16 macro tile, by one warp.  Lane (row = lane >> 1, half = lane & 1) owns the
-// eight pixels (8*half .. 8*half+7, row) of the macro tile in every pass, so a tile
-// of 8 or 16 pixels width is shared by the lanes of its rows, and a 4-pixel-wide pass is run as two sub-passes (left and
-// right quad of every lane).  `claimed` (16 bits, bit = 4*cellY + cellX) is warp-uniform and returned updated.
-static __device__ __forceinline__ unsigned yka_macro_pass(const uint8_t* __restrict__ priv, YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch,
-                                                          int pid, int rp, int gmx, int gmy, unsigned claimed, unsigned poss, int rej) {
+// One FittingQuadSmooth pass over one 16x16 macro tile, by one warp, all tiles of the pass in one sweep (lane geometry:
+// yka_pass_lane_entry).  `poss`: the tiles to test (eligible - EC.cpp:3818, 3826, 3871-3875 - and not proven hopeless).
+// Returns (uniformly) the cells the accepted tiles claim (16 bits, bit = 4*cellY + cellX) and counts them in `st`.
+static __device__ __forceinline__ unsigned yka_macro_pass(const uint8_t* __restrict__ priv, const YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch,
+                                                          YkaStat* st, int pid, int gmx, int gmy, unsigned poss, int rej) {
     const YkGeomS g = yk_geom_s(pid);
     const int lane = threadIdx.x & 31;
-    const uint2 e = sh.passLane[pid][lane];
-    const int shx = g.shx, shy = g.shy;
-    const unsigned gmask = e.x;
-    const int lyT = e.y & 31;
-    const bool leader = (e.y >> 9) & 1u;
-    const int nSub = (shx == 2) ? 2 : 1;
+    const uint4 e = sh.passLane[pid][lane];
     YkaTile T;
-    T.shx = shx; T.shy = shy; T.sh = shx + shy; T.negN = -(1 << T.sh); T.dy = (e.y >> 5) & 15; T.R = rej; T.two = shx != 2;
-    T.dx0 = (e.y >> 14) & 15;
-    unsigned newCells = 0;
-    for (int sub = 0; sub < nSub; sub++) {
-        const int lxT = (e.y >> (sub ? 22 : 10)) & 15, t = (e.y >> (sub ? 26 : 18)) & 15;
-        const bool active = (poss >> t) & 1u;               // eligible (EC.cpp:3818, 3826, 3871-3875) and not proven hopeless: see the caller
-        if (!__any_sync(YK_FULL, active)) continue;
-        uint2 pw[3];                                        // this lane's eight pixels of the macro tile, three channels
+    T.shx = g.shx; T.shy = g.shy; T.sh = g.shx + g.shy; T.negN = -(1 << T.sh); T.R = rej; T.wide = g.shx != 2;
+    T.dx0 = e.w & 255u; T.dy = (e.w >> 8) & 255u;
+    const bool active = (poss >> ((e.w >> 16) & 255u)) & 1u;
+    unsigned w0[3], w1[3];
 #pragma unroll
-        for (int c = 0; c < 3; c++) pw[c] = *reinterpret_cast<const uint2*>(priv + c * YKP_CH + (lane >> 1) * YKP_RS + 8 * (lane & 1));
-        const bool acc = yka_tile_test(priv + lyT * YKP_RS + lxT, T, pw, sub != 0, gmask, active);
-        unsigned mine = 0;
-        if (acc && leader) {
-            yka_commit(sh, C, touch, g, pid, rp, gmx + lxT, gmy + lyT, lxT, lyT);
-            // EC.cpp:4029-4037: the tile's cells become claimed
-            const unsigned cols = ((1u << (1 << (shx - 2))) - 1u) << (lxT >> 2);
-            const unsigned rowsPat = (0x1111u & ((1u << (4 << (shy - 2))) - 1u)) << (lyT & ~3);
-            mine = cols * rowsPat;
-        }
-        newCells |= __reduce_or_sync(YK_FULL, mine);
+    for (int c = 0; c < 3; c++) {
+        w0[c] = *reinterpret_cast<const unsigned*>(priv + c * YKP_CH + (e.y & 0xFFFFu));
+        w1[c] = *reinterpret_cast<const unsigned*>(priv + c * YKP_CH + (e.y >> 16));
     }
-    return claimed | newCells;
+    const int cornerOff = e.z & 0xFFFFu;
+    const bool acc = yka_tile_test(priv + cornerOff, T, w0, w1, e.x, active);
+    const bool mineAcc = acc && (e.w >> 24);
+    const unsigned accB = __ballot_sync(YK_FULL, mineAcc);
+    if (!accB) return 0u;
+    if (mineAcc) {
+        const int tly = cornerOff / YKP_RS, tlx = cornerOff - tly * YKP_RS;
+        yka_commit(C, touch, g, pid, sh.rpOf[pid], gmx + tlx, gmy + tly, tlx, tly);
+    }
+    const unsigned cells = __reduce_or_sync(YK_FULL, mineAcc ? (e.z >> 16) : 0u);          // EC.cpp:4029-4037
+    // TileDone and the bounding box of the accepted tiles (EC.cpp:4039-4044) from the cells they cover
+    const unsigned colm = (cells | (cells >> 4) | (cells >> 8) | (cells >> 12)) & 15u;
+    const unsigned rowm = ((cells & 0x000Fu) ? 1u : 0u) | ((cells & 0x00F0u) ? 2u : 0u) | ((cells & 0x0F00u) ? 4u : 0u) | ((cells & 0xF000u) ? 8u : 0u);
+    const int x0 = gmx + 4 * (__ffs((int)colm) - 1), x1 = gmx + 4 * (32 - __clz((int)colm));
+    const int y0 = gmy + 4 * (__ffs((int)rowm) - 1), y1 = gmy + 4 * (32 - __clz((int)rowm));
+    yka_stat_add(st, pid, __popc(accB), C.w - x0, INT_MAX / 2 - (C.yOrg + y0), x1, C.yOrg + y1);
+    return cells;
+}
+
+// Tiles (bits as in the pre-test: start(pid) + t) whose top-left cell is unclaimed (EC.cpp:3871-3875), from the claimed
+// cells of the macro tile (bit = 4*cellY + cellX).  Warp-uniform bit arithmetic.
+static __device__ __forceinline__ unsigned long long yka_eligible(unsigned claimed) {
+    const unsigned f = ~claimed & 0xFFFFu;
+    unsigned e = f & 0x5555u;                           // cells with even x, compressed: bit i = cell 2*i
+    e = (e | (e >> 1)) & 0x3333u; e = (e | (e >> 2)) & 0x0F0Fu; e = (e | (e >> 4)) & 0x00FFu;
+    const unsigned lo = (f & 1u)                                              // 16x16: cell 0
+                      | (((e & 1u) | ((e >> 3) & 2u)) << 1)                   // 16x8: cells 0, 8
+                      | ((e & 3u) << 3)                                       // 8x16: cells 0, 2
+                      | (((e & 3u) | ((e >> 2) & 12u)) << 5)                  // 8x8: cells 0, 2, 8, 10
+                      | (e << 9)                                              // 8x4: cells 0, 2, .. 14
+                      | (((f & 15u) | ((f >> 4) & 0xF0u)) << 17);             // 4x8: cells 0..3, 8..11
+    return (unsigned long long)lo | ((unsigned long long)f << 25);           // 4x4: every cell
 }
 
 // DynamicTileCompressor (EC.cpp:8398-8522) for the 8x8 tile at (lx8, ly8) of the macro tile; q = its quadrants to code
@@ -540,13 +587,8 @@ static __device__ __forceinline__ void yka_range_tile(const uint8_t* __restrict_
     __syncwarp();       // the histogram entries are clean again before the next tile fills them
 }
 
-// The 16x16 pass of an interior macro tile straight from the raw rows, before anything is packed: about half of all macro
-// tiles of illustration-like content are accepted here by the raw-corner family, and for those the byte tile is never
-// built (compile-time tile size, no per-pass set-up).  Returns 1 = accepted (all side effects done, the macro tile is
-// finished), 2 = proven hopeless for every variant (the cascade can skip the 16x16 pass), 0 = undecided (the cascade
-// repeats the pass with all three families).  Only used on a fresh state with the 16x16 pass first.
 template <bool U8>
-static __device__ __forceinline__ int yka_pass16_raw(const void* __restrict__ rawv, YkaShared& sh, const YkaSlotC& C, int gmx, int gmy, int mx, int R) {
+static __device__ __forceinline__ int yka_pass16_raw(const void* __restrict__ rawv, const YkaSlotC& C, YkaStat* st, int gmx, int gmy, int mx, int R) {
     const int lane = threadIdx.x & 31, row = lane >> 1, half = lane & 1;
     constexpr int N = 256;
     const int hiT = (2 * R + 1) * N, loR = -(N / 2 - 1), loWide = -(4 * N + N / 2 - 1), hiWide = hiT + 3 * N;
@@ -591,8 +633,8 @@ static __device__ __forceinline__ int yka_pass16_raw(const void* __restrict__ ra
         const int nSwzX = (C.w + 63) >> 6;
         const int pos = yk_pos_s(g, nSwzX, gmx >> 4, gmy >> 4);
         atomicOr(&C.bitmap32[0][pos >> 5], 1u << (pos & 31));
-        yka_stat5(sh, C, YK_HD_PASS0, 1, C.w - gmx, INT_MAX / 2 - (C.yOrg + gmy), gmx + 16, C.yOrg + gmy + 16);
     }
+    yka_stat_add(st, 0, 1, C.w - gmx, INT_MAX / 2 - (C.yOrg + gmy), gmx + 16, C.yOrg + gmy + 16);
     const int cx0 = gmx >> 2, cy0 = gmy >> 2;
     if (lane < 4) {
         const int e = (cy0 + lane) * C.nbx + (cx0 >> 4);
@@ -618,8 +660,8 @@ extern "C" void yk_debug_timing(unsigned long long* out, int reset) {
 
 // One macro tile after its pixels have been packed: the cascade of Convert()'s passes (EC.cpp:9057-9093), its results,
 // the corner colours of its lattice points, then the range stage.  (gmx, gmy) = origin of the macro tile in the image.
-static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch, uint8_t* hist,
-                                      const uint32_t* magicTab, int gmx, int gmy, bool pass16Hopeless) {
+static __device__ __forceinline__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShared& sh, const YkaSlotC& C, uint32_t* __restrict__ touch, uint8_t* hist,
+                                      const uint32_t* magicTab, YkaStat* st, int gmx, int gmy, bool pass16Hopeless) {
     const int lane = threadIdx.x & 31;
     const YkRun& run = sh.run;
     YKT_DECL;
@@ -642,28 +684,24 @@ static __device__ void yka_macro_tile(const uint8_t* __restrict__ priv, YkaShare
         claimed |= ~inside & 0xFFFFu;
     }
     const unsigned claimed0 = claimed;
-    const int nPasses = run.nPasses;
-    if (nPasses > 0) {
+    if (run.nPasses > 0) {
         if (lane < 25) touch[lane] = 0;
         __syncwarp();
         if (claimed != 0xFFFFu) {
-            // the 16x16 pass usually runs first and straight away (most macro tiles of illustration-like content end there);
-            // the other shapes are pre-tested together, once, the first time one of them comes up
-            unsigned long long P = (wIn >= 16 && hIn >= 16 && !pass16Hopeless) ? 1ull : 0ull;
-            bool pretested = false;
+            // All 41 tiles of the seven shapes are pre-tested together; `todo` = the tiles of the run's passes that are
+            // inside the image, eligible and not proven hopeless.  The passes run in Convert()'s order = bit order, and only
+            // those that still have a tile to test; a pass that accepts tiles makes the tiles under them ineligible.
             const int rej = run.rejectFactor;
-            for (int rp = 0; rp < nPasses && claimed != 0xFFFFu; rp++) {
-                const int pid = run.passId[rp];
-                if (pid != 0 && !pretested) {
-                    P = yka_pretest(priv, sh.pretestTab, wIn, hIn, claimed, rej); pretested = true;
-                    if (pass16Hopeless) P &= ~1ull;
-                }
+            unsigned long long todo = yka_pretest(priv, sh.pretestTab, wIn, hIn, claimed, rej) & sh.runTiles;
+            if (pass16Hopeless) todo &= ~1ull;
+            while (todo) {
+                const int pid = sh.passOfTile[__ffsll((long long)todo) - 1];
                 const YkGeomS g = yk_geom_s(pid);
-                // tiles of this shape that are possible and whose top-left cell is still unclaimed (EC.cpp:3871-3875): lane = tile
-                bool freeTile = false;
-                if (lane < (256 >> (g.shx + g.shy))) freeTile = !((claimed >> (sh.pretestTab[g.start + lane] >> 14)) & 1u);
-                const unsigned poss = (unsigned)(P >> g.start) & __ballot_sync(YK_FULL, freeTile);
-                if (poss) claimed = yka_macro_pass(priv, sh, C, touch, pid, rp, gmx, gmy, claimed, poss, rej);
+                const int nT = 256 >> (g.shx + g.shy);
+                const unsigned poss = (unsigned)(todo >> g.start) & ((1u << nT) - 1u);
+                todo &= ~0ull << (g.start + nT);
+                const unsigned cells = yka_macro_pass(priv, sh, C, touch, st, pid, gmx, gmy, poss, rej);
+                if (cells) { claimed |= cells; todo &= yka_eligible(claimed); }
             }
             if (threadIdx.x == 32) YKT(11);
             // EC.cpp:4029-4037: newly claimed cells
@@ -720,10 +758,9 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
     unsigned char* raw = smem;
     constexpr int STAGE_BYTES = U8 ? YKA_RAWB_STAGE : YKA_RAW_STAGE_INTS * 4;
     constexpr int PLANE_BYTES = U8 ? YKA_RAWB_PLANE : YKA_RAW_PLANE_INTS * 4;
-    uint8_t* privAll = smem + YKA_SMEM_RAW;
-    uint8_t* histAll = smem + YKA_SMEM_RAW + YKA_SMEM_PIX;
-    uint32_t* sMagic = reinterpret_cast<uint32_t*>(smem + YKA_SMEM_RAW + YKA_SMEM_PIX + YKA_SMEM_HIST);    // ceil(2^20 / d): exact floor(n / d) for n < 4112, d <= 255
-    YkaShared& sh = *reinterpret_cast<YkaShared*>(smem + YKA_SMEM_RAW + YKA_SMEM_PIX + YKA_SMEM_HIST + 1024);
+    YkaWarpArea* warpAreas = reinterpret_cast<YkaWarpArea*>(smem + YKA_SMEM_RAW);
+    uint32_t* sMagic = reinterpret_cast<uint32_t*>(smem + YKA_SMEM_RAW + YKA_SMEM_WARPS);    // ceil(2^20 / d): exact floor(n / d) for n < 4112, d <= 255
+    YkaShared& sh = *reinterpret_cast<YkaShared*>(smem + YKA_SMEM_RAW + YKA_SMEM_WARPS + 1024);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // units of one image: (pair of regions, macro-tile row); every image of a launch has the same size
@@ -732,14 +769,22 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
 
     // ---- start-up (the only block-wide barriers)
     for (int i = tid; i < (int)(sizeof(YkaShared) / 4); i += YKA_THREADS) reinterpret_cast<uint32_t*>(&sh)[i] = 0;
-    for (int i = tid; i < YKA_SMEM_HIST / 4; i += YKA_THREADS) reinterpret_cast<uint32_t*>(histAll)[i] = 0;
+    for (int i = tid; i < YKA_SMEM_WARPS / 4; i += YKA_THREADS) reinterpret_cast<uint32_t*>(warpAreas)[i] = 0;
     if (tid < 256) sMagic[tid] = tid ? ((1u << 20) + (unsigned)tid - 1u) / (unsigned)tid : 0u;
     __syncthreads();
     if (tid < 41) sh.pretestTab[tid] = yka_pretest_entry(tid);
     if (tid >= 128 && tid < 128 + YK_NPASS * 32) sh.passLane[(tid - 128) >> 5][(tid - 128) & 31] = yka_pass_lane_entry((tid - 128) >> 5, (tid - 128) & 31);
-    if (tid >= 64 && tid < 64 + YKA_CONS_WARPS) sh.slotc[tid - 64].slot = -1;
+    if (tid >= 64 && tid < 64 + YKA_CONS_WARPS) warpAreas[tid - 64].slotc.slot = -1;
+    if (tid < 41) sh.passOfTile[tid] = (uint8_t)((tid >= 1) + (tid >= 3) + (tid >= 5) + (tid >= 9) + (tid >= 17) + (tid >= 25));
     if (tid == 96) {
         sh.run = runArg;
+        unsigned long long rt = 0;
+        for (int rp = 0; rp < sh.run.nPasses; rp++) {
+            const YkGeomS g = yk_geom_s(sh.run.passId[rp]);
+            rt |= ((1ull << (256 >> (g.shx + g.shy))) - 1ull) << g.start;
+            sh.rpOf[sh.run.passId[rp]] = rp;
+        }
+        sh.runTiles = rt;
         sh.endSeq = INT_MAX;
         sh.statSlot = -1;
         sh.consLeft = YKA_CONS_WARPS;
@@ -818,10 +863,12 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
 
     // ===================================================== consumers =====================================================
     const int cw = warp - 1;                                 // consumer index
-    uint8_t* hist = histAll + cw * 3 * 256;
-    uint8_t* priv = privAll + cw * YKP_TILE;
-    uint32_t* touch = sh.touch[cw];
-    YkaSlotC& C = sh.slotc[cw];
+    YkaWarpArea& WA = warpAreas[cw];
+    uint8_t* hist = WA.hist;
+    uint8_t* priv = WA.priv;
+    uint32_t* touch = WA.touch;
+    YkaSlotC& C = WA.slotc;
+    YkaStat* st = WA.wstat;
     YKT_DECL;
     const bool fast16 = run.fresh && run.nPasses > 0 && run.passId[0] == 0;      // uniform for the launch
     for (;;) {
@@ -845,14 +892,17 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         const YkaUnit U = sh.unit[i];
         const int cachedSlot = C.slot;
         __syncwarp();                                       // every lane has read the cached id before lane 0 may rewrite it
-        if (cachedSlot != U.slot) yka_slot_refresh(slots[U.slot], C, U.slot);
+        if (cachedSlot != U.slot) {
+            if (cachedSlot >= 0) yka_stat_flush(sh, C, st);     // the counters so far belong to the previous image
+            yka_slot_refresh(slots[U.slot], C, U.slot);
+        }
         const int X0 = U.bx * 64, Yk = U.by * 64 + 16 * U.k;
         const int gmx = X0 + 16 * mx;
         const unsigned char* rawU = raw + i * STAGE_BYTES;
         // fresh state, 16x16 pass first, interior macro tile: try that pass straight from the raw rows
         int fast = 0;
         if (fast16 && gmx + 20 <= C.w && Yk + YK_RAW_ROWS <= C.h)
-            fast = yka_pass16_raw<U8>(rawU, sh, C, gmx, Yk, mx, run.rejectFactor);
+            fast = yka_pass16_raw<U8>(rawU, C, st, gmx, Yk, mx, run.rejectFactor);
         bool kept;
         if (fast == 1) {
             // accepted: the macro tile is finished without a byte tile; alpha test and the corner colours of its 4x4
@@ -875,18 +925,17 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         if (lane == 0) yka_mbar_arrive(&sh.rawFree[i]);      // this warp is done with the raw rows
         if (tid == 32) YKT(9);
         if (gmx >= C.w) continue;                            // the unit's second region does not exist (odd number of region columns)
-        if (U.alpha && Yk < C.h && lane == 0) {
-            C.alphaKept[(size_t)(Yk >> 4) * ((C.w + 15) >> 4) + (gmx >> 4)] = kept ? 1 : 0;
-            if (kept) {
-                // bounding box of kept tiles (EC.cpp:416-422), mins stored as extent - value so that zero means "none"
-                yka_stat5(sh, C, YK_HD_ALPHA_KEPT0, 1, C.w - gmx, INT_MAX / 2 - (C.yOrg + Yk), min(gmx + 16, C.w), C.yOrg + min(Yk + 16, C.h));
-            }
+        if (U.alpha && Yk < C.h) {
+            if (lane == 0) C.alphaKept[(size_t)(Yk >> 4) * ((C.w + 15) >> 4) + (gmx >> 4)] = kept ? 1 : 0;
+            // bounding box of kept tiles (EC.cpp:416-422), mins stored as extent - value so that zero means "none"
+            if (kept) yka_stat_add(st, 7, 1, C.w - gmx, INT_MAX / 2 - (C.yOrg + Yk), min(gmx + 16, C.w), C.yOrg + min(Yk + 16, C.h));
         }
         if (fast == 1) continue;
-        yka_macro_tile(priv, sh, C, touch, hist, sMagic, gmx, Yk, fast == 2);
+        yka_macro_tile(priv, sh, C, touch, hist, sMagic, st, gmx, Yk, fast == 2);
         __syncwarp();
         if (tid == 32) YKT(10);
     }
+    if (C.slot >= 0) yka_stat_flush(sh, C, st);
     // the last consumer warp of the CTA adds the CTA's counters to the image's header
     __threadfence_block();
     int left = 0;

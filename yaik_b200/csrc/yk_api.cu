@@ -533,6 +533,7 @@ static int fetch_hdr(yk_ctx* c, YkSlotHost& s) {
 static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEmit, bool doR2, int phases = 3) {
     int rc = check_batch(c, slot0, nSlots);
     if (rc) return rc;
+    for (int p = 1; p < run.nPasses; p++) if (run.passId[p] <= run.passId[p - 1]) return YK_ERR_ARG;   // the kernel runs a launch's passes in Convert()'s order
     CK(cudaSetDevice(c->device));
     const YkSlotHost& a = c->slots[slot0];
     const int nRegions = a.d.nbx * a.d.nby;
