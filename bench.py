@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=384)
     ap.add_argument("--e2e-threads", type=int, default=8, help="host threads (one context each) the end-to-end steps are pipelined over")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-r1", action="store_true", help="skip the second timed region (the step with DynamicTileEncode behind it)")
     ap.add_argument("--no-other", action="store_true", help="skip the informational timing of the stages outside the metric")
     ap.add_argument("--streams", type=int, default=8, help="contexts/streams the steps are pipelined over (1, 2, 4 or 8)")
     ap.add_argument("--analysis-ctas", type=int, default=-1, help="CTAs of the persistent analysis kernel in the pipelined region (-1: a quarter of the SMs with 8 streams, half with 2-4, else one per SM)")
@@ -392,6 +393,79 @@ def main():
                 except Exception:
                     pass
 
+    # ---- the same step with DynamicTileEncode (the README's 3 / 4 bits-per-pixel range stage, R1) of R, G, B behind it:
+    # one more launch per step (yk_k_r1_encode, three planes), everything left in HBM.  Timed like `value` (one region),
+    # then the kernel alone (one step at a time), then its streams compared with the per-plane API path.
+    with_r1 = None
+    if not args.no_r1:
+        STAGES_R1 = STAGES | capi.STAGE_RANGEDYN
+
+        def step_r1(i):
+            c = ctxs[i % NCTX]
+            s = (i // NCTX) % (NSLOTS // NCTX)
+            c.reset_state(s)
+            c.analyze(STAGES_R1, slot0=s)
+
+        for c in ctxs:
+            c.set_analysis_ctas(actas)
+        for i in range(2 * NCTX):
+            step_r1(i)
+        sync_all()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for st in streams[1:]:
+            st.wait_event(ev0)
+        n_r1 = max(args.steps, 2 * NCTX)
+        for i in range(n_r1):
+            step_r1(i)
+        for st, j in zip(streams[1:], joins[1:]):
+            j.record(st)
+            stream.wait_event(j)
+        ev1.record(stream)
+        barrier()
+        r1_ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([r1_ms], device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            r1_ms = float(t.item())
+        # the kernel alone: one step at a time, one CTA per SM for the analysis before it
+        for c in ctxs:
+            c.set_analysis_ctas(0)
+            lib.yk_profile(c.ctx, 1)
+        for i in range(max(8, args.roofline_steps // 4)):
+            step_r1(i)
+            ctxs[i % NCTX].sync()
+        rk = (C.c_double * 8)(); rc_ = (C.c_longlong * 8)()
+        for c in ctxs:
+            a = (C.c_double * 8)(); b = (C.c_longlong * 8)()
+            lib.yk_profile_read(c.ctx, a, b)
+            lib.yk_profile(c.ctx, 0)
+            for k in range(8):
+                rk[k] += a[k]; rc_[k] += b[k]
+        r1_alone_ms = rk[3] / rc_[3] if rc_[3] else None
+        # parity of the fused launch: its streams against the per-plane path (yk_range_dyn, which tests/ compare with the oracle)
+        fused = [ctxs[0].range_dyn(p) for p in range(3)]
+        cchk = capi.Context(W, H, planes=CH, slots=1, device=local, lib=lib)
+        cchk.set_upload_format(False)
+        cchk.set_image(imgs[0], 0)
+        cchk.analyze(STAGES)
+        r1_bytes = 0
+        for p in range(3):
+            single = cchk.range_dyn(p)
+            if not (np.array_equal(single["nibbles"], fused[p]["nibbles"]) and np.array_equal(single["defs"], fused[p]["defs"])):
+                raise SystemExit("bench.py: DynamicTileEncode streams of the fused launch differ from the per-plane path")
+            r1_bytes += 4 * single["n_nibbles"] + single["nibbles"].size + 2 * single["defs"].size
+        cchk.close()
+        with_r1 = {"value": round(world * mp_per_step * n_r1 / (r1_ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(r1_ms / n_r1, 5), "steps": n_r1,
+                   "stages": "MipPrefilter + 7x FittingQuadSmooth + 3x DynamicTileCompressor + 3x DynamicTileEncode (six LUT modes)",
+                   "parity_checked": True,
+                   "r1_kernel": {"name": "yk_k_r1_encode (R, G, B in one launch)", "ms_alone": round(r1_alone_ms, 5) if r1_alone_ms else None,
+                                 "algorithmic_bytes_per_launch": int(r1_bytes),
+                                 "bytes_note": "int32 samples of the coded pixels + the nibble and tile-definition streams, three planes",
+                                 "hbm_frac": round(r1_bytes / (r1_alone_ms * 1e-3) / 1e9 / peak, 4) if r1_alone_ms else None,
+                                 "bound": "instruction issue / latency (six LUT modes per pixel, an ordered float32 sum per block), not HBM"}}
+
     # ---- end to end through the public C ABI with HOST buffers: pinned int32 planes in (yk_set_image packs them to bytes
     # on the host and uploads those), every result stream out (yk_fetch_all: pinned arena).  Textures are independent, so
     # the steps are pipelined over a few host threads with one context each (upload, analysis and download overlap).
@@ -496,7 +570,7 @@ def main():
                         "region_ms": [round(x, 4) for x in region_ms]},
                 "parity_checked": parity_checked,
                 "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "stages_outside_metric": other}
+                "with_r1": with_r1, "stages_outside_metric": other}
         print(json.dumps(line), flush=True)
     for c in ctxs:
         c.close()

@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #define YK_EMULATE 1
+#include <math.h>
 #define __global__
 #define __device__
 #define __host__
@@ -37,6 +38,8 @@ struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c 
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
+static inline float2 make_float2(float a, float b) { return float2{ a, b }; }
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
 struct uchar4 { unsigned char x, y, z, w; };
@@ -130,6 +133,10 @@ static inline int __vimin3_s32(int a, int b, int c) { return std::min(a, std::mi
 static inline unsigned __vmaxu2(unsigned a, unsigned b) { return std::max(a & 0xFFFFu, b & 0xFFFFu) | (std::max(a >> 16, b >> 16) << 16); }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __int2float_rn(int a) { return (float)a; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 using std::max; using std::min;

@@ -46,8 +46,12 @@ def check_image(ctx: "capi.Context", planes: np.ndarray, stages, *, fused=True, 
     do_alpha = "alpha" in stages and c == 4
     do_grad = "grad" in stages
     do_r2 = "r2" in stages
+    do_r1 = "r1" in stages or "r1_3bit" in stages
+    r1_fused = fused and do_r1 and w >= 32 and h >= 32 and w % 8 == 0 and h % 8 == 0
     if fused:
         st = (capi.STAGE_ALPHA if do_alpha else 0) | (capi.STAGE_GRADIENT if do_grad else 0) | (capi.STAGE_RANGE1D if do_r2 else 0)
+        if r1_fused:        # DynamicTileEncode of R, G, B in the same call (one launch behind the analysis)
+            st |= capi.STAGE_RANGEDYN3 if "r1_3bit" in stages else capi.STAGE_RANGEDYN
         ctx.analyze(st, slot0=slot)
     if do_alpha:
         want = o.alpha()
@@ -80,9 +84,17 @@ def check_image(ctx: "capi.Context", planes: np.ndarray, stages, *, fused=True, 
             _eq(s["mapSmoothTile"][n].ravel(), o.state(2 + n), f"mapSmoothTile{n}")
             _eq(s["mappedRGB"][n].ravel(), o.state(5 + n), f"mappedRGB{n}")
             _eq(s["recon"][n].ravel(), o.state(8 + n), f"recon{n}")
-    if "r1" in stages or "r1_3bit" in stages:
+    if do_r1:
+        wants = [o.range_dyn(n, mode3="r1_3bit" in stages, want_dst=True) for n in range(3)]
+        if r1_fused:        # the streams yk_analyze left on the device
+            for n in range(3):
+                got = ctx.range_dyn(n, mode3="r1_3bit" in stages, slot=slot, want_dst=False)
+                assert got["constraint"] == wants[n]["constraint"]
+                _eq(got["defs"], wants[n]["defs"], f"fused R1 defs plane {n}")
+                assert got["n_nibbles"] == wants[n]["n_nibbles"]
+                _eq(got["nibbles"], wants[n]["nibbles"], f"fused R1 nibbles plane {n}")
         for n in range(3):
-            want = o.range_dyn(n, mode3="r1_3bit" in stages, want_dst=True)
+            want = wants[n]
             got = ctx.range_dyn(n, mode3="r1_3bit" in stages, slot=slot, want_dst=True)
             assert got["constraint"] == want["constraint"]
             _eq(got["defs"], want["defs"], f"R1 defs plane {n}")

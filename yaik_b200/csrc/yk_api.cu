@@ -64,6 +64,8 @@ struct YkSlotHost {
     bool pendingHarvest = false; // a run's header has not been copied back yet
     int  lastRunPasses = 0;      // bit p: pass p was in the last run; bit 8: alpha
     int  rangeErr = 0;
+    int32_t* r1DstDev = nullptr;  // write-back plane of DynamicTileEncode (allocated on first use, one plane at a time)
+    int  r1Fused = 0;            // DynamicTileEncode results of the three colour planes present from yk_analyze: 1 = six modes, 2 = 3-bit only
     int32_t* chroma[3] = { nullptr, nullptr, nullptr };   // Y, workCo, workCg of the chroma front-end (allocated on first use)
     int  chromaHalf[4] = { 0, 0, 0, 0 };
     bool chromaReady = false;
@@ -85,7 +87,9 @@ struct yk_ctx {
     // per slot one contiguous zeroable area: part A (header, look-back status words) is cleared before every launch,
     // part B (claimed cells, touch map = the persistent analysis state) only by yk_reset_state
     uint8_t* zeroArea = nullptr; size_t zeroStride = 0, zeroABytes = 0;
-    int* lutDev = nullptr;       // R1 tables
+    int* lutDev = nullptr;       // R1 tables: LUTs + thresholds, and the per-value entry table (see yk_k_r1_encode)
+    uint16_t* rtabDev = nullptr;
+    int16_t* r7Dev = nullptr;    // range7 code per (base6, clamped difference)
     int numSMs = 1;              // SMs of the device
     int analysisCtas = 1;        // grid of the persistent analysis kernel (default: one CTA per SM)
     YkHostPacker* packer = nullptr;
@@ -277,6 +281,7 @@ static int create_fill(yk_ctx* c) {
             if ((rc = dev_alloc(s, &s.d.r2Type[p], 3 * (W / 8 + 1) * (H / 8 + 1)))) return rc;
         }
         if ((rc = dev_alloc(s, &s.d.r1Status, r1_status_words(W, H)))) return rc;
+        { uint4* list = nullptr; if ((rc = dev_alloc(s, &list, (W / 8 + 1) * (H / 8 + 1) + 1))) return rc; s.d.r1List = list; }
         for (int p = 0; p < 3; p++) {
             if ((rc = dev_alloc(s, &s.d.r1Nib[p], (W / 8) * (H / 8) * 8 + 4))) return rc;
             if ((rc = dev_alloc(s, &s.d.r1Defs[p], (W / 8) * (H / 8) + 4))) return rc;
@@ -301,6 +306,8 @@ extern "C" void yk_destroy(yk_ctx* c) {
     if (c->packer) yk_hostpack_destroy(c->packer);
     cudaFree(c->slotsDev); cudaFree(c->zeroArea);
     if (c->lutDev) cudaFree(c->lutDev);
+    if (c->rtabDev) cudaFree(c->rtabDev);
+    if (c->r7Dev) cudaFree(c->r7Dev);
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -370,6 +377,7 @@ static void mark_reset(YkSlotHost& s) {
     if (s.d.alphaReset || s.d.alphaValid) s.dirty = true;
     s.d.alphaReset = 0; s.d.alphaValid = 0;
     s.k1Ran = s.alphaRan = s.alphaFetched = s.prepared = s.r2Valid = s.pendingHarvest = false;
+    s.r1Fused = 0;
     s.nextPass = 0; s.rangeErr = 0; s.lastRunPasses = 0;
     memset(s.hdr, 0, sizeof s.hdr);
 }
@@ -591,6 +599,7 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     for (int i = slot0; i < slot0 + nSlots; i++) {
         YkSlotHost& s = c->slots[i];
         s.k1Ran = true; s.pendingHarvest = true; s.harvested = false; s.lastRunPasses = (run.doAlpha ? 256 : 0);
+        if (run.nPasses > 0 || run.doAlpha) s.r1Fused = 0;       // the masks DynamicTileEncode works on are changing
         for (int p = 0; p < run.nPasses; p++) s.lastRunPasses |= 1 << run.passId[p];
         if (run.doAlpha && s.d.nPlanes == 4) { s.alphaRan = true; s.alphaFetched = false; }
         if (run.nPasses > 0) { s.r2Valid = false; s.touchDirty = true; s.cellsClean = false; }
@@ -599,9 +608,11 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     return YK_OK;
 }
 
+static int enqueue_r1_fused(yk_ctx* c, int slot, int mode3BitOnly, bool useAlpha);
+
 extern "C" int yk_analyze(yk_ctx* c, int slot0, int nSlots, int stages, int rejectFactor) {
     if (!c || rejectFactor < 0 || rejectFactor > 64) return YK_ERR_ARG;
-    if (stages & (YK_STAGE_RANGEDYN | YK_STAGE_RANGEDYN3)) return YK_ERR_UNSUPPORTED;   // R1 is driven per plane through yk_range_dyn
+    if ((stages & YK_STAGE_RANGEDYN) && (stages & YK_STAGE_RANGEDYN3)) return YK_ERR_ARG;
     YkRun run; memset(&run, 0, sizeof run);
     run.rejectFactor = rejectFactor;
     run.doAlpha = (stages & YK_STAGE_ALPHA) ? 1 : 0;
@@ -614,6 +625,14 @@ extern "C" int yk_analyze(yk_ctx* c, int slot0, int nSlots, int stages, int reje
     if (rc) return rc;
     if (stages & YK_STAGE_GRADIENT)
         for (int i = slot0; i < slot0 + nSlots; i++) { c->slots[i].prepared = true; c->slots[i].preparedReject = rejectFactor; c->slots[i].nextPass = 0; }
+    if (stages & (YK_STAGE_RANGEDYN | YK_STAGE_RANGEDYN3))
+        for (int i = slot0; i < slot0 + nSlots; i++) {
+            const YkSlotHost& s = c->slots[i];
+            // the alpha box the coder works in: of this run, or (host-side flags) of an earlier yk_alpha_reject
+            const bool alphaThisRun = (stages & YK_STAGE_ALPHA) && s.d.nPlanes == 4;
+            if (!alphaThisRun && s.alphaRan) return YK_ERR_STATE;       // an earlier alpha stage: code the planes with yk_range_dyn
+            if ((rc = enqueue_r1_fused(c, i, (stages & YK_STAGE_RANGEDYN3) != 0, alphaThisRun))) return rc;
+        }
     return YK_OK;
 }
 
@@ -808,52 +827,118 @@ extern "C" int yk_range1d(yk_ctx* c, int slot, int plane, uint8_t* idx, int idxC
 // is "number of thresholds below the value".
 #define YK_R1_R7MAX 176
 #define YK_R1_LUT_INTS 144
-static int ensure_r1_lut(yk_ctx* c) {
-    if (c->lutDev) return YK_OK;
-    std::vector<int> lut((size_t)64 * YK_R1_R7MAX * YK_R1_LUT_INTS, 0);
-    for (int b6 = 0; b6 < 64; b6++) {
-        const int BN = (b6 * 224) / 63, scale = 223 - BN;
-        for (int r7 = 0; r7 < YK_R1_R7MAX; r7++) {
-            const int D = (r7 * scale) / 127 + 32;                 // DiffRangeDecode, EC.cpp:620-623
-            const float DistNormF = (float)D;
-            int* T = &lut[((size_t)b6 * YK_R1_R7MAX + r7) * YK_R1_LUT_INTS];
-            for (int input = 0; input < 16; input++) {              // EC.cpp:662-677
-                float pos = input / 15.0f;
-                float ExpNormV = powf(pos, 1.4f), LogNormV = 1.0f - powf((1.0f - pos), 1.4f);
-                float outLinear = pos * DistNormF, outExp = ExpNormV * DistNormF, outLog = LogNormV * DistNormF;
-                T[input] = (int)(BN + outLinear); T[16 + input] = (int)(BN + outExp); T[32 + input] = (int)(BN + outLog);
+#define YK_R1_RTAB_VALUES 384
+#define YK_R1_RTAB_R7 128           // range7 values the per-value table covers: every entry of those LUTs is a byte
+struct YkR1HostTables { std::vector<int> lut; std::vector<uint16_t> rtab; std::vector<int16_t> r7; bool ok = false; };
+static const YkR1HostTables& r1_host_tables() {
+    static YkR1HostTables t;            // built once per process (thread-safe static initialisation), shared by every context
+    static const bool built = [] {
+        t.lut.assign((size_t)64 * YK_R1_R7MAX * YK_R1_LUT_INTS, 0);
+        t.rtab.assign((size_t)64 * YK_R1_RTAB_R7 * 6 * YK_R1_RTAB_VALUES, 0);
+        t.r7.assign((size_t)64 * 224, 0);
+        for (int b6 = 0; b6 < 64; b6++) {
+            const int BN = (b6 * 224) / 63, scale = 223 - BN;
+            for (int dd = 0; dd < 224; dd++) {                          // DiffRangeEncode with the clamped difference, EC.cpp:643-650 (C division)
+                const int r7 = (dd * 127 + scale - 1) / scale;
+                if (r7 < -32768 || r7 > 32767) return false;
+                t.r7[(size_t)b6 * 224 + dd] = (int16_t)r7;
             }
-            for (int input = 0; input < 8; input++) {               // EC.cpp:680-696
-                float pos = input / 7.0f;
-                float ExpNormV = powf(pos, 1.4f), LogNormV = 1.0f - powf((1.0f - pos), 1.4f);
-                float outLinear = pos * DistNormF, outExp = ExpNormV * DistNormF, outLog = LogNormV * DistNormF;
-                T[48 + input] = (int)(BN + outLinear); T[56 + input] = (int)(BN + outExp); T[64 + input] = (int)(BN + outLog);
-            }
-            for (int m = 0; m < 6; m++) {
-                const int off = m < 3 ? 16 * m : 48 + 8 * (m - 3), count = m < 3 ? 16 : 8;
-                const int* L = T + off;
-                int* TH = T + 72 + off;
-                TH[0] = INT_MIN;
-                int next = INT_MAX;                                  // threshold of the next distinct entry
-                for (int n = count - 1; n >= 1; n--) {
-                    if (L[n] < L[n - 1]) return YK_ERR_STATE;        // never: every curve is monotone
-                    if (L[n] > L[n - 1]) next = (L[n - 1] + L[n]) >> 1;
-                    TH[n] = next;
+            for (int r7 = 0; r7 < YK_R1_R7MAX; r7++) {
+                const int D = (r7 * scale) / 127 + 32;                 // DiffRangeDecode, EC.cpp:620-623
+                const float DistNormF = (float)D;
+                int* T = &t.lut[((size_t)b6 * YK_R1_R7MAX + r7) * YK_R1_LUT_INTS];
+                for (int input = 0; input < 16; input++) {              // EC.cpp:662-677
+                    float pos = input / 15.0f;
+                    float ExpNormV = powf(pos, 1.4f), LogNormV = 1.0f - powf((1.0f - pos), 1.4f);
+                    float outLinear = pos * DistNormF, outExp = ExpNormV * DistNormF, outLog = LogNormV * DistNormF;
+                    T[input] = (int)(BN + outLinear); T[16 + input] = (int)(BN + outExp); T[32 + input] = (int)(BN + outLog);
+                }
+                for (int input = 0; input < 8; input++) {               // EC.cpp:680-696
+                    float pos = input / 7.0f;
+                    float ExpNormV = powf(pos, 1.4f), LogNormV = 1.0f - powf((1.0f - pos), 1.4f);
+                    float outLinear = pos * DistNormF, outExp = ExpNormV * DistNormF, outLog = LogNormV * DistNormF;
+                    T[48 + input] = (int)(BN + outLinear); T[56 + input] = (int)(BN + outExp); T[64 + input] = (int)(BN + outLog);
+                }
+                for (int m = 0; m < 6; m++) {
+                    const int off = m < 3 ? 16 * m : 48 + 8 * (m - 3), count = m < 3 ? 16 : 8;
+                    const int* L = T + off;
+                    int* TH = T + 72 + off;
+                    TH[0] = INT_MIN;
+                    int next = INT_MAX;                                  // threshold of the next distinct entry
+                    for (int n = count - 1; n >= 1; n--) {
+                        if (L[n] < L[n - 1]) return false;                // never: every curve is monotone
+                        if (r7 < YK_R1_RTAB_R7 && b6 < 63 && (L[n] > 255 || L[n - 1] < 0)) return false;     // never: BN + D <= 255 there
+                        if (L[n] > L[n - 1]) next = (L[n - 1] + L[n]) >> 1;
+                        TH[n] = next;
+                    }
+                    // the entry the search picks for every value of the tables' domain: code = #{n >= 1 : value > TH[n]}
+                    if (r7 >= YK_R1_RTAB_R7 || b6 == 63) continue;      // range codes beyond 7 bits (a reference quirk for bases close to 224) and base 63 (entries up to 256) are searched
+                    uint16_t* R = &t.rtab[(((size_t)b6 * YK_R1_RTAB_R7 + r7) * 6 + m) * YK_R1_RTAB_VALUES];
+                    int code = 0;
+                    for (int v = 0; v < YK_R1_RTAB_VALUES; v++) {
+                        while (code + 1 < count && v > TH[code + 1]) code++;
+                        R[v] = (uint16_t)((code << 8) | L[code]);
+                    }
                 }
             }
         }
-    }
-    CK(cudaMalloc((void**)&c->lutDev, lut.size() * sizeof(int)));
-    // on the context's stream (non-blocking: it does not order itself after the legacy stream), and complete before the
-    // pageable host vector goes away
-    cudaError_t e = cudaMemcpyAsync(c->lutDev, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+        t.ok = true;
+        return true;
+    }();
+    (void)built;
+    return t;
+}
+static int ensure_r1_lut(yk_ctx* c) {
+    if (c->lutDev && c->rtabDev && c->r7Dev) return YK_OK;
+    const YkR1HostTables& t = r1_host_tables();
+    if (!t.ok) return YK_ERR_STATE;
+    CK(cudaMalloc((void**)&c->lutDev, t.lut.size() * sizeof(int)));
+    CK(cudaMalloc((void**)&c->rtabDev, t.rtab.size() * sizeof(uint16_t)));
+    CK(cudaMalloc((void**)&c->r7Dev, t.r7.size() * sizeof(int16_t)));
+    // on the context's stream (non-blocking: it does not order itself after the legacy stream), complete before this returns
+    cudaError_t e = cudaMemcpyAsync(c->lutDev, t.lut.data(), t.lut.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->rtabDev, t.rtab.data(), t.rtab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->r7Dev, t.r7.data(), t.r7.size() * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) { cudaFree(c->lutDev); c->lutDev = nullptr; g_lastCuda = std::string("R1 table upload: ") + cudaGetErrorString(e); return YK_ERR_CUDA; }
+    if (e != cudaSuccess) {
+        cudaFree(c->lutDev); c->lutDev = nullptr; cudaFree(c->rtabDev); c->rtabDev = nullptr; cudaFree(c->r7Dev); c->r7Dev = nullptr;
+        g_lastCuda = std::string("R1 table upload: ") + cudaGetErrorString(e); return YK_ERR_CUDA;
+    }
+    return YK_OK;
+}
+
+// Geometry of DynamicTileEncode's walk over a plane of pw x ph samples for the bound box `bound` (EC.cpp:4386-4401,
+// LeftRightOrder framework.h:228-256): full rows of the box, then the first block of the row below it if the plane has one
+static void r1_geometry(YkR1Args& a, const int bound[4], int pw, int ph, int halfX, int halfY) {
+    a.pw = pw; a.ph = ph; a.shX = halfX ? 1 : 0; a.shY = halfY ? 1 : 0;
+    a.cx = (bound[0] >> 3) << 3; a.cy = (bound[1] >> 3) << 3;                      // EC.cpp:4386-4391
+    a.cw = (((bound[2] + 7) >> 3) << 3) - a.cx; a.ch = (((bound[3] + 7) >> 3) << 3) - a.cy;
+    if (halfX) { a.cx >>= 1; a.cw >>= 1; }                                          // EC.cpp:4393-4401
+    if (halfY) { a.cy >>= 1; a.ch >>= 1; }
+    a.nbw = (a.cw + 7) >> 3;
+    const int rows = (a.ch + 7) >> 3;
+    a.nBlocks = a.nbw * rows;
+    if (a.nBlocks > 0 && a.cy + 8 * rows < ph) a.nBlocks += 1;
+}
+
+// the coded streams of plane `out` of the last DynamicTileEncode launch to the caller's buffers
+static int r1_fetch(yk_ctx* c, YkSlotHost& s, int out, uint8_t* nibbles, int nibCap, int* nNibbles, uint16_t* defs, int defsCap, int* nDefs) {
+    int tot[2] = { 0, 0 };
+    CK(cudaMemcpyAsync(&tot[0], s.d.hdr + YK_HD_R1_NIB0 + out, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&tot[1], s.d.hdr + YK_HD_R1_DEF0 + out, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int nb = (tot[0] + 1) / 2;
+    if (nNibbles) *nNibbles = tot[0];
+    if (nDefs) *nDefs = tot[1];
+    if (nb > nibCap || tot[1] > defsCap) return YK_ERR_CAPACITY;
+    if (nibbles && nb) CK(cudaMemcpyAsync(nibbles, s.d.r1Nib[out], nb, cudaMemcpyDeviceToHost, c->stream));
+    if (defs && tot[1]) CK(cudaMemcpyAsync(defs, s.d.r1Defs[out], (size_t)tot[1] * 2, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return YK_OK;
 }
 
 // DynamicTileEncode on one device plane (the slot's colour planes, or Y / reduced Co / Cg of the chroma front-end)
-static int range_dyn_impl(yk_ctx* c, int slot, const int32_t* src, int pw, int ph, int out, int mode3BitOnly, int chroma, int halfX, int halfY,
+static int range_dyn_impl(yk_ctx* c, int slot, const int32_t* src, const uint8_t* srcU8, int pitchU8, int pw, int ph, int out, int mode3BitOnly, int chroma, int halfX, int halfY,
                           uint8_t* nibbles, int nibCap, int* nNibbles, uint16_t* defs, int defsCap, int* nDefs, int constraint[4], int32_t* dst) {
     YkSlotHost& s = c->slots[slot];
     const int w = s.d.w, h = s.d.h;
@@ -862,54 +947,59 @@ static int range_dyn_impl(yk_ctx* c, int slot, const int32_t* src, int pw, int p
     if ((rc = ensure_r1_lut(c))) return rc;
     int bound[4] = { 0, 0, w, h };                               // CheckMipmapMask: full image (EC.cpp:2784-2794)
     if (s.alphaRan) { if ((rc = alpha_finish(c, s))) return rc; memcpy(bound, s.bound, sizeof bound); }
-    YkR1Args a;
-    memset(&a, 0, sizeof a);
-    a.src = src; a.pw = pw; a.ph = ph; a.shX = halfX ? 1 : 0; a.shY = halfY ? 1 : 0; a.chroma = chroma; a.mode3 = mode3BitOnly ? 1 : 0; a.out = out;
-    a.cx = (bound[0] >> 3) << 3; a.cy = (bound[1] >> 3) << 3;                      // EC.cpp:4386-4391
-    a.cw = (((bound[2] + 7) >> 3) << 3) - a.cx; a.ch = (((bound[3] + 7) >> 3) << 3) - a.cy;
-    if (halfX) { a.cx >>= 1; a.cw >>= 1; }                                          // EC.cpp:4393-4401
-    if (halfY) { a.cy >>= 1; a.ch >>= 1; }
+    YkR1Launch L;
+    memset(&L, 0, sizeof L);
+    L.nJobs = 1;
+    YkR1Args& a = L.job[0];
+    a.src = src; a.srcU8 = srcU8; a.pitchU8 = pitchU8; a.chroma = chroma; a.mode3 = mode3BitOnly ? 1 : 0; a.out = out;
+    r1_geometry(a, bound, pw, ph, halfX, halfY);
     if (constraint) { constraint[0] = a.cx; constraint[1] = a.cy; constraint[2] = a.cw; constraint[3] = a.ch; }
-    // LeftRightOrder (framework.h:228-256): full rows of the box, then the first block of the row below it if the plane has one
-    a.nbw = (a.cw + 7) >> 3;
-    const int rows = (a.ch + 7) >> 3;
-    a.nBlocks = a.nbw * rows;
-    if (a.nBlocks > 0 && a.cy + 8 * rows < ph) a.nBlocks += 1;
     if (s.pendingHarvest) { rc = fetch_hdr(c, s); if (rc && rc != YK_ERR_RANGE) return rc; }
-    // the optional full-size write-back plane lives on the device for the duration of the call (freed on every way out)
-    struct DstGuard { int32_t* p = nullptr; YkSlotHost* s; ~DstGuard() { if (p) cudaFree(p); s->d.r1Dst = nullptr; s->dirty = true; } } guard;
-    guard.s = &s;
+    // the optional full-size write-back plane: a device copy of the caller's plane, kept by the slot between calls
     if (dst) {
-        CK(cudaMalloc((void**)&guard.p, (size_t)w * h * 4));
-        CK(cudaMemcpyAsync(guard.p, dst, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream));
+        if (!s.r1DstDev && (rc = dev_alloc(s, &s.r1DstDev, (size_t)c->maxW * c->maxH))) return rc;
+        CK(cudaMemcpyAsync(s.r1DstDev, dst, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream));
+        a.dst = s.r1DstDev;
     }
-    int32_t* const dDst = guard.p;
-    s.d.r1Dst = dDst; s.dirty = true;
     if ((rc = upload_slots(c, slot, 1))) return rc;
-    if (a.nBlocks > 0) {
-        CK(cudaMemsetAsync(s.d.r1Status, 0, r1_status_words(w, h) * sizeof(unsigned long long), c->stream));
-        { YkTimed t(c, 3); yk_launch_range_dyn_encode(c->slotsDev, slot, a, c->lutDev, c->stream); }
-        c->launches += 1;
-    }
+    s.r1Fused = 0;                                               // the streams of plane `out` are about to be replaced
+    CK(cudaMemsetAsync(s.d.r1Status, 0, r1_status_words(w, h) * sizeof(unsigned long long), c->stream));
+    { YkTimed t(c, 3); yk_launch_range_dyn_encode(c->slotsDev, slot, L, a.nBlocks, c->numSMs, c->lutDev, c->rtabDev, c->r7Dev, c->stream); }
+    c->launches += 2;
     CK(cudaGetLastError());
-    int tot[2] = { 0, 0 };
-    if (a.nBlocks > 0) {
-        CK(cudaMemcpyAsync(&tot[0], s.d.hdr + YK_HD_R1_NIB0 + out, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(&tot[1], s.d.hdr + YK_HD_R1_DEF0 + out, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    }
-    CK(cudaStreamSynchronize(c->stream));
-    const int nb = (tot[0] + 1) / 2;
-    rc = YK_OK;
-    if (nb > nibCap || tot[1] > defsCap) rc = YK_ERR_CAPACITY;
-    if (!rc) {
-        if (nibbles && nb) CK(cudaMemcpyAsync(nibbles, s.d.r1Nib[out], nb, cudaMemcpyDeviceToHost, c->stream));
-        if (defs && tot[1]) CK(cudaMemcpyAsync(defs, s.d.r1Defs[out], (size_t)tot[1] * 2, cudaMemcpyDeviceToHost, c->stream));
-        if (dst) CK(cudaMemcpyAsync(dst, dDst, (size_t)w * h * 4, cudaMemcpyDeviceToHost, c->stream));
+    rc = r1_fetch(c, s, out, nibbles, nibCap, nNibbles, defs, defsCap, nDefs);
+    if (!rc && dst) {
+        CK(cudaMemcpyAsync(dst, s.r1DstDev, (size_t)w * h * 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
-    if (nNibbles) *nNibbles = tot[0];
-    if (nDefs) *nDefs = tot[1];
     return rc;
+}
+
+// DynamicTileEncode of the three colour planes right behind the analysis, one launch, nothing comes back to the host:
+// the constraint box is derived on the device from the alpha stage's box in the image header
+static int enqueue_r1_fused(yk_ctx* c, int slot, int mode3BitOnly, bool useAlpha) {
+    YkSlotHost& s = c->slots[slot];
+    const int w = s.d.w, h = s.d.h;
+    if ((w & 7) || (h & 7) || w < 32 || h < 32) return YK_ERR_ARG;      // the reference's own domain (SURVEY.md hazard 11)
+    if (s.d.hasAbove || s.d.hasBelow) return YK_ERR_UNSUPPORTED;
+    int rc;
+    if ((rc = ensure_r1_lut(c))) return rc;
+    YkR1Launch L;
+    memset(&L, 0, sizeof L);
+    L.nJobs = 3; L.fromHdr = 1; L.useAlpha = useAlpha ? 1 : 0;
+    const int full[4] = { 0, 0, w, h };
+    for (int p = 0; p < 3; p++) {
+        YkR1Args& a = L.job[p];
+        a.src = s.d.plane[p]; a.srcU8 = s.d.isU8 ? s.d.planeU8[p] : nullptr; a.pitchU8 = s.d.pitchU8;
+        a.mode3 = mode3BitOnly ? 1 : 0; a.out = p;
+        r1_geometry(a, full, w, h, 0, 0);                       // the largest possible box: the launch covers it
+    }
+    CK(cudaMemsetAsync(s.d.r1Status, 0, r1_status_words(w, h) * sizeof(unsigned long long), c->stream));
+    { YkTimed t(c, 3); yk_launch_range_dyn_encode(c->slotsDev, slot, L, L.job[0].nBlocks, c->numSMs, c->lutDev, c->rtabDev, c->r7Dev, c->stream); }
+    c->launches += 2;
+    CK(cudaGetLastError());
+    s.r1Fused = mode3BitOnly ? 2 : 1;
+    return YK_OK;
 }
 
 extern "C" int yk_range_dyn(yk_ctx* c, int slot, int plane, int mode3BitOnly, uint8_t* nibbles, int nibCap, int* nNibbles,
@@ -919,8 +1009,21 @@ extern "C" int yk_range_dyn(yk_ctx* c, int slot, int plane, int mode3BitOnly, ui
     if (!s.haveImage) return YK_ERR_STATE;
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = ensure_int32(c, slot))) return rc;
-    return range_dyn_impl(c, slot, s.d.plane[plane], s.d.w, s.d.h, plane, mode3BitOnly, 0, 0, 0, nibbles, nibCap, nNibbles, defs, defsCap, nDefs, constraint, dst);
+    if (!dst && s.r1Fused == (mode3BitOnly ? 2 : 1)) {
+        // coded by yk_analyze already: only the streams come back
+        if (s.pendingHarvest) { rc = fetch_hdr(c, s); if (rc && rc != YK_ERR_RANGE) return rc; }
+        int bound[4] = { 0, 0, s.d.w, s.d.h };
+        if (s.alphaRan) { if ((rc = alpha_finish(c, s))) return rc; memcpy(bound, s.bound, sizeof bound); }
+        YkR1Args a; memset(&a, 0, sizeof a);
+        r1_geometry(a, bound, s.d.w, s.d.h, 0, 0);
+        if (constraint) { constraint[0] = a.cx; constraint[1] = a.cy; constraint[2] = a.cw; constraint[3] = a.ch; }
+        return r1_fetch(c, s, plane, nibbles, nibCap, nNibbles, defs, defsCap, nDefs);
+    }
+    // samples outside 0..255 were uploaded as int32 by yk_set_image; packed planes are read as bytes
+    const bool u8 = s.d.isU8 != 0;
+    if (!u8 && !s.int32Valid && (rc = ensure_int32(c, slot))) return rc;
+    return range_dyn_impl(c, slot, s.d.plane[plane], u8 ? s.d.planeU8[plane] : nullptr, s.d.pitchU8, s.d.w, s.d.h, plane, mode3BitOnly, 0, 0, 0,
+                          nibbles, nibCap, nNibbles, defs, defsCap, nDefs, constraint, dst);
 }
 
 // ---- chroma front-end ----------------------------------------------------------------
@@ -983,7 +1086,7 @@ extern "C" int yk_range_dyn_chroma(yk_ctx* c, int slot, int which, int mode3BitO
     int pw, ph;
     chroma_dims(s, which, &pw, &ph);
     const int hx = pw != s.d.w, hy = ph != s.d.h;
-    return range_dyn_impl(c, slot, s.chroma[which], pw, ph, which, mode3BitOnly, which != 0, hx, hy, nibbles, nibCap, nNibbles, defs, defsCap, nDefs, constraint, dst);
+    return range_dyn_impl(c, slot, s.chroma[which], nullptr, 0, pw, ph, which, mode3BitOnly, which != 0, hx, hy, nibbles, nibCap, nNibbles, defs, defsCap, nDefs, constraint, dst);
 }
 
 // ---- compat state download --------------------------------------------------------------------------------

@@ -78,10 +78,10 @@ struct alignas(128) YkSlotDev {
     uint8_t*  r2Idx[3];         // the streams in the reference's order (gathered by yk_k_emit)
     uint8_t*  r2Type[3];
     // ---- range stage R1 (DynamicTileEncode)
-    unsigned long long* r1Status;   // look-back words of yk_k_r1_encode's units (256 blocks of the walk each) + the unit ticket; zeroed per call
+    unsigned long long* r1Status;   // look-back words of yk_k_r1_offsets' units (256 blocks of the walk each) + the unit ticket; zeroed per call
+    void*     r1List;           // the blocks that hold valid pixels, in walk order (16 bytes each, see yk_k_r1_offsets)
     uint32_t* r1Nib[3];         // nibble stream (two nibbles per byte, written pairwise)
     uint16_t* r1Defs[3];
-    int32_t*  r1Dst;            // optional w*h int32 (one plane at a time)
     int       alphaReset;       // set by the host after the alpha stage: bbox == full image -> mask all 255 (EC.cpp:1400-1403)
     int       alphaValid;       // alpha stage has been run for this image
 };
@@ -111,6 +111,8 @@ void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t*
 // DynamicTileEncode on one plane: the source samples, the (possibly halved) constraint box and the walk over it
 struct YkR1Args {
     const int32_t* src; int pw, ph;      // plane coded: pw x ph int32 samples on the device
+    const uint8_t* srcU8; int pitchU8;   // ... or, when not NULL, one byte per sample (a colour plane uploaded packed)
+    int32_t* dst;                        // optional write-back plane (w x h int32, full size), else NULL
     int shX, shY;                        // 1 = the plane is SampleDown'ed on that axis (isHalfX / isHalfY)
     int chroma, mode3;                   // isCo | isCg; mode3BitOnly
     int cx, cy, cw, ch;                  // constraint box in the plane's own coordinates (EC.cpp:4386-4401)
@@ -118,7 +120,10 @@ struct YkR1Args {
     int out;                             // index of r1Nib / r1Defs / header counters written
 };
 struct YkChromaArgs { int32_t *y, *co, *cg; int half[4]; int mode[2]; };
-void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, const YkR1Args& args, const int* lutDev, cudaStream_t st);
+// one launch: 1..3 planes with the same geometry and validity (job[0]'s); fromHdr: the constraint box is derived on the
+// device from the alpha stage's box in the image header (the fused yk_analyze path, no host round trip)
+struct YkR1Launch { int nJobs, fromHdr, useAlpha, pad; YkR1Args job[3]; };
+void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, const YkR1Launch& launch, int maxBlocks, int numSMs, const int* lutDev, const uint16_t* rtabDev, const int16_t* r7Dev, cudaStream_t st);
 void yk_launch_chroma(const YkSlotDev* slotsDev, int slot, int w, int h, const YkChromaArgs& args, cudaStream_t st);
 #ifdef __cplusplus
 }

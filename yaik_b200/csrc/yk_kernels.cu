@@ -157,14 +157,6 @@ yk_k_state(const YkSlotDev* __restrict__ slots, int slot, int32_t* smoothMap, in
 // Block i of the walk is (cx + 8*(i % nbw), cy + 8*(i / nbw)); the reference's size quirk
 // `w = (x+8 > constraint.w) ? x%8 : 8` (compares with the width, not the right edge) empties blocks with
 // x + 8 > cw or y + 8 > ch.  valid pixel = mipmapMask != 0 && smoothMap == 0 (Plane.cpp:525-527).
-static __device__ __forceinline__ unsigned yk_r1_cells(const YkSlotDev& S, int x, int y) {
-    // unclaimed-and-kept 4x4 cells of the 8x8 block at (x, y): bit0 TL, bit1 TR, bit2 BL, bit3 BR
-    if (S.alphaValid && !S.alphaReset && !S.alphaKept[(size_t)(y >> 4) * ((S.w + 15) >> 4) + (x >> 4)]) return 0u;
-    const int cx = x >> 2, cy = y >> 2;
-    const unsigned r0 = S.cellMask[(size_t)cy * S.nbx + (cx >> 4)], r1 = S.cellMask[(size_t)(cy + 1) * S.nbx + (cx >> 4)];
-    return (~(((r0 >> (cx & 15)) & 3u) | (((r1 >> (cx & 15)) & 3u) << 2))) & 15u;
-}
-
 // block-wide exclusive scan of one int per thread (used by the R1 offset scan)
 static __device__ int yk_block_exclusive(int v, int* sWarp, int& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -187,39 +179,55 @@ static __device__ int yk_block_exclusive(int v, int* sWarp, int& total) {
     return r;
 }
 
-// One launch per plane.  A CTA takes a unit of YK_R1_UNIT consecutive blocks of the walk (global ticket): one thread
-// per block counts its valid pixels, a block scan + one decoupled look-back turn the counts into nibble / tile-def
-// offsets, the blocks that hold valid pixels are compacted into a list in shared memory and the warps encode them one
-// block per warp.  Small units: the per-block work is a long dependent chain (min/max -> table -> search -> ordered
-// float sum), so the kernel wants as many warps in flight as the SM holds.
+// Two launches code up to three planes that share their geometry and validity (the colour planes R, G, B; or one plane:
+// Y / reduced Co / Cg of the chroma front-end):
+//   yk_k_r1_offsets   one thread per block of the walk: which pixel pairs of the block are coded (that only depends on
+//                     the alpha / claimed-cell masks, not on the samples), a block scan + one decoupled look-back per
+//                     256 blocks give the nibble / tile-def offsets - the same for every plane - and the blocks that
+//                     hold valid pixels are listed in walk order {x | y << 16, pairs, nibble offset}.
+//   yk_k_r1_encode    warps take (listed block, plane) items with a grid stride and code them independently of each
+//                     other (no block barrier, no waiting): min / max, table, mode search, ordered error sums, output
+//                     at the final stream position.
 //
 // lut: [64 base6][176 range7][144] ints.  [0,72) = the six LUTs (16,16,16,8,8,8 entries) of DynamicTile::buildTable
 // (EC.cpp:625-699); [72,144) = their decision thresholds, same layout.  Every LUT is non-decreasing, so the reference's
 // "first strict minimum of |entry - value|" scan (EC.cpp:873-881) picks entry n over all earlier ones exactly when
 // value > floor((L[n-1] + L[n]) / 2) with L[n] > L[n-1]; a repeated entry is never picked and inherits the threshold of
-// the next distinct one (INT_MAX if none), which keeps the thresholds non-decreasing: code = #{n >= 1 : value > thr[n]}.
+// the next distinct one (INT_MAX if none), which keeps the thresholds non-decreasing: code = #{n >= 1 : value > thr[n]}
+// = the largest n with value > thr[n] (binary search).
+// rtab: [64][128 range7 < 128][6 modes][384] u16 = code << 8 | LUT entry that search picks, for every value 0..383 (the
+// domain of the reference's tables: samples -128..255, shifted by 128 when the block's minimum is negative), built on
+// the host from the same thresholds: the per-pixel, per-mode work of the mode search is one 16-bit load.
 #ifndef YK_R1_UNIT
-#define YK_R1_UNIT 32
+#define YK_R1_UNIT 512
 #endif
 #ifndef YK_R1_THREADS
 #define YK_R1_THREADS 128
 #endif
 #define YK_R1_LUT_INTS 144
+#define YK_R1_RTAB_VALUES 384
+#define YK_R1_RTAB_R7 128
 
 // Validity of one full-resolution pixel as DynamicTileEncode sees it: mipmapMask != 0 (kept by the alpha stage) and
 // smoothMap == 0 (its 4x4 cell not claimed by a gradient tile).
-static __device__ __forceinline__ bool yk_r1_mask_at(const YkSlotDev& S, int fx, int fy) {
-    return !(S.alphaValid && !S.alphaReset && !S.alphaKept[(size_t)(fy >> 4) * ((S.w + 15) >> 4) + (fx >> 4)]);
+static __device__ __forceinline__ bool yk_r1_mask_at(const YkSlotDev& S, bool maskActive, int fx, int fy) {
+    return !(maskActive && !S.alphaKept[(size_t)(fy >> 4) * ((S.w + 15) >> 4) + (fx >> 4)]);
 }
 static __device__ __forceinline__ bool yk_r1_smooth_at(const YkSlotDev& S, int fx, int fy) {
     const int cx = fx >> 2;
     return (S.cellMask[(size_t)(fy >> 2) * S.nbx + (cx >> 4)] >> (cx & 15)) & 1u;
 }
-
 // mipmapMask != 0 at linear index i of the full-size mask plane
-static __device__ __forceinline__ bool yk_r1_valid_at(const YkSlotDev& S, size_t i) {
+static __device__ __forceinline__ bool yk_r1_valid_at(const YkSlotDev& S, bool maskActive, size_t i) {
     const int fx = (int)(i % (size_t)S.w), fy = (int)(i / (size_t)S.w);
-    return yk_r1_mask_at(S, fx, fy) && !yk_r1_smooth_at(S, fx, fy);
+    return yk_r1_mask_at(S, maskActive, fx, fy) && !yk_r1_smooth_at(S, fx, fy);
+}
+// unclaimed-and-kept 4x4 cells of the 8x8 block at (x, y): bit0 TL, bit1 TR, bit2 BL, bit3 BR
+static __device__ __forceinline__ unsigned yk_r1_cells(const YkSlotDev& S, bool maskActive, int x, int y) {
+    if (!yk_r1_mask_at(S, maskActive, x, y)) return 0u;
+    const int cx = x >> 2, cy = y >> 2;
+    const unsigned r0 = S.cellMask[(size_t)cy * S.nbx + (cx >> 4)], r1 = S.cellMask[(size_t)(cy + 1) * S.nbx + (cx >> 4)];
+    return (~(((r0 >> (cx & 15)) & 3u) | (((r1 >> (cx & 15)) & 3u) << 2))) & 15u;
 }
 
 // The walk of LeftRightOrder (framework.h:228-256) over the constraint box of a plane of pw x ph samples: rows of
@@ -227,50 +235,100 @@ static __device__ __forceinline__ bool yk_r1_valid_at(const YkSlotDev& S, size_t
 // lies inside the plane (HasNextBlock tests `y < h` after the wrap).  Block sizes: the reference compares with the
 // constraint's width / height, not its right / bottom edge, and falls back to x % 8 (framework.h:251-252) - 0 for the
 // full-resolution planes, possibly 4 for a reduced chroma plane whose box starts on an odd multiple of 4.
+struct YkR1Geom { int cx, cy, cw, ch, nbw, nBlocks, maskActive, pad; };
 struct YkR1Block { int x, y, rw, rh; };
-static __device__ __forceinline__ YkR1Block yk_r1_block(const YkR1Args& A, int i) {
+static __device__ __forceinline__ YkR1Block yk_r1_block(const YkR1Geom& G, int i) {
     YkR1Block b;
-    b.x = A.cx + 8 * (i % A.nbw); b.y = A.cy + 8 * (i / A.nbw);
-    b.rw = (b.x + 8 > A.cw) ? (b.x & 7) : 8;
-    b.rh = (b.y + 8 > A.ch) ? (b.y & 7) : 8;
+    b.x = G.cx + 8 * (i % G.nbw); b.y = G.cy + 8 * (i / G.nbw);
+    b.rw = (b.x + 8 > G.cw) ? (b.x & 7) : 8;
+    b.rh = (b.y + 8 > G.ch) ? (b.y & 7) : 8;
     return b;
 }
 
-#ifndef YK_R1_MINB
-#define YK_R1_MINB 10      // 48 registers: 3-bit-only launches 44.6 -> 40.6 us, six-mode launches unchanged
-#endif
-__global__ void __launch_bounds__(YK_R1_THREADS, YK_R1_MINB)
-yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, const YkR1Args A, const int* __restrict__ lut) {
-    __shared__ __align__(16) float sTerm[YK_R1_THREADS / 32][6][64];
-    __shared__ int sBlock[YK_R1_UNIT], sNibOff[YK_R1_UNIT];      // sBlock: block index of the walk
-    __shared__ unsigned sMask[YK_R1_UNIT];                       // coded pixel pairs of the block: bit = 4 * row + pair
+// float(d) / float(o), correctly rounded, for the small integers of this stage: with r = RN(1 / o) the residual
+// correction below reproduces IEEE division for all 1 <= d, o <= 2048 (checked exhaustively on the host);
+// anything larger takes the division itself.
+static __device__ __forceinline__ float yk_r1_quot(int d, float fo, float r) {
+    const float fd = __int2float_rn(d);
+    const float q0 = __fmul_rn(fd, r);
+    return __fmaf_rn(__fmaf_rn(-q0, fo, fd), r, q0);                // r == 0 (a dropped term) gives exactly +0
+}
+
+struct YkR1Item { unsigned xy, pairs, nibOff, pad; };        // one listed block: see yk_k_r1_offsets
+
+static __device__ YkR1Geom yk_r1_geometry(const YkSlotDev& S, const YkR1Launch& LP) {
+    const YkR1Args& A0 = LP.job[0];
+    YkR1Geom G;
+    G.cx = A0.cx; G.cy = A0.cy; G.cw = A0.cw; G.ch = A0.ch; G.nbw = A0.nbw; G.nBlocks = A0.nBlocks;
+    G.maskActive = S.alphaValid && !S.alphaReset; G.pad = 0;
+    if (LP.fromHdr) {
+        // the bound box of the alpha stage straight from the image header the analysis kernel has just written
+        // (MipPrefilter, EC.cpp:1287-1291, 1400-1403; CheckMipmapMask's full image without an alpha stage)
+        int L = 0, T = 0, R = S.w, B = S.h, any = 1;
+        G.maskActive = 0;
+        if (LP.useAlpha && S.nPlanes == 4) {
+            const int* h = S.hdr;
+            any = h[YK_HD_ALPHA_KEPT0] > 0;
+            if (any) {
+                L = S.w - h[YK_HD_ALPHA_MINX]; T = INT_MAX / 2 - h[YK_HD_ALPHA_MINY]; R = h[YK_HD_ALPHA_MAXX]; B = h[YK_HD_ALPHA_MAXY];
+                G.maskActive = !(L == 0 && T == 0 && R == S.w && B == S.imgH);
+            }
+        }
+        G.cx = (L >> 3) << 3; G.cy = (T >> 3) << 3;                                   // EC.cpp:4386-4391
+        G.cw = (((R + 7) >> 3) << 3) - G.cx; G.ch = (((B + 7) >> 3) << 3) - G.cy;
+        G.nbw = (G.cw + 7) >> 3;
+        const int rows = (G.ch + 7) >> 3;
+        G.nBlocks = any ? G.nbw * rows : 0;
+        if (G.nBlocks > 0 && G.cy + 8 * rows < A0.ph) G.nBlocks += 1;
+    }
+    return G;
+}
+
+__global__ void __launch_bounds__(YK_R1_UNIT)
+yk_k_r1_offsets(const YkSlotDev* __restrict__ slots, int slot, const YkR1Launch LP) {
     __shared__ int sWarp[33];
     __shared__ int sUnit;
     __shared__ unsigned sBase[2];
+    __shared__ YkR1Geom sG;
     const YkSlotDev& S = slots[slot];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nUnits = (A.nBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT;
-    const bool reduced = (A.shX | A.shY) != 0;
+    const YkR1Args& A0 = LP.job[0];
+    const bool reduced = (A0.shX | A0.shY) != 0;
     unsigned long long* status = S.r1Status;
-    if (tid == 0) sUnit = (int)atomicAdd(reinterpret_cast<unsigned*>(&status[nUnits]), 1u);
+    if (tid == 0) {
+        const YkR1Geom G = yk_r1_geometry(S, LP);
+        sG = G;
+        const int nU = (G.nBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT;
+        sUnit = (int)atomicAdd(reinterpret_cast<unsigned*>(&status[nU]), 1u);
+    }
     __syncthreads();
+    const YkR1Geom G = sG;
+    const bool maskActive = G.maskActive != 0;
+    const int nUnits = (G.nBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT;
     const int u = sUnit;
+    if (u >= nUnits) {                                            // launched for the largest possible box
+        if (nUnits == 0 && u == 0 && tid == 0) {
+            for (int j = 0; j < LP.nJobs; j++) { S.hdr[YK_HD_R1_NIB0 + LP.job[j].out] = 0; S.hdr[YK_HD_R1_DEF0 + LP.job[j].out] = 0; }
+        }
+        return;
+    }
     // ---- count: which pixel pairs of my block are coded (EC.cpp:826-861; the 2x2 / 2x1 / 1x2 mask samples a reduced
     // pixel covers lie in one 16x16 alpha tile, so "all of them" is the top-left one)
     const int i = u * YK_R1_UNIT + tid;
     unsigned pairs = 0;
-    if (tid < YK_R1_UNIT && i < A.nBlocks) {
-        const YkR1Block b = yk_r1_block(A, i);
+    YkR1Block b = { 0, 0, 0, 0 };
+    if (i < G.nBlocks) {
+        b = yk_r1_block(G, i);
         if (!reduced) {
             if (b.rw == 8 && b.rh == 8 && b.x + 8 <= S.w && b.y + 8 <= S.h) {
-                const unsigned cells = yk_r1_cells(S, b.x, b.y);
+                const unsigned cells = yk_r1_cells(S, maskActive, b.x, b.y);
                 pairs = ((cells & 1u) ? 0x00003333u : 0u) | ((cells & 2u) ? 0x0000CCCCu : 0u) | ((cells & 4u) ? 0x33330000u : 0u) | ((cells & 8u) ? 0xCCCC0000u : 0u);
             }
         } else {
             for (int r = 0; r < b.rh; r++)
                 for (int p = 0; 2 * p < b.rw; p++) {
-                    const int fx = (b.x + 2 * p) << A.shX, fy = (b.y + r) << A.shY;
-                    if (yk_r1_mask_at(S, fx, fy) && !yk_r1_smooth_at(S, fx, fy)) pairs |= 1u << (4 * r + p);
+                    const int fx = (b.x + 2 * p) << A0.shX, fy = (b.y + r) << A0.shY;
+                    if (yk_r1_mask_at(S, maskActive, fx, fy) && !yk_r1_smooth_at(S, fx, fy)) pairs |= 1u << (4 * r + p);
                 }
         }
     }
@@ -282,30 +340,79 @@ yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, const YkR1Args A, 
         const unsigned long long base = yk_lookback64(status, u, (unsigned)(tot & 0xFFFF), (unsigned)(tot >> 16));
         if (lane == 0) {
             sBase[0] = (unsigned)(base >> 32); sBase[1] = (unsigned)base;
-            if (u == nUnits - 1) {
-                S.hdr[YK_HD_R1_NIB0 + A.out] = (int)(base >> 32) + (tot & 0xFFFF);
-                S.hdr[YK_HD_R1_DEF0 + A.out] = (int)(unsigned)base + (tot >> 16);
-            }
+            if (u == nUnits - 1)
+                for (int j = 0; j < LP.nJobs; j++) {
+                    S.hdr[YK_HD_R1_NIB0 + LP.job[j].out] = (int)(base >> 32) + (tot & 0xFFFF);
+                    S.hdr[YK_HD_R1_DEF0 + LP.job[j].out] = (int)(unsigned)base + (tot >> 16);
+                }
         }
     }
-    if (n > 0) { sBlock[ex >> 16] = i; sMask[ex >> 16] = pairs; sNibOff[ex >> 16] = ex & 0xFFFF; }
     __syncthreads();
-    const int nList = tot >> 16;
-    const int nibBase = (int)sBase[0], defBase = (int)sBase[1];
+    if (n > 0) {
+        YkR1Item it;
+        it.xy = (unsigned)b.x | ((unsigned)b.y << 16); it.pairs = pairs; it.nibOff = sBase[0] + (unsigned)(ex & 0xFFFF); it.pad = (unsigned)b.rw | ((unsigned)b.rh << 8);
+        reinterpret_cast<uint4*>(S.r1List)[sBase[1] + (unsigned)(ex >> 16)] = make_uint4(it.xy, it.pairs, it.nibOff, it.pad);
+    }
+}
+
+#ifndef YK_R1_MINB
+#define YK_R1_MINB 9
+#endif
+#ifndef YK_R1_CAP
+#define YK_R1_CAP 12
+#endif
+__global__ void __launch_bounds__(YK_R1_THREADS, YK_R1_MINB)
+yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, const YkR1Launch LP, const int* __restrict__ lut, const unsigned short* __restrict__ rtab, const short* __restrict__ r7tab) {
+    __shared__ __align__(16) float sTerm[YK_R1_THREADS / 32][6][64];
+    const YkSlotDev& S = slots[slot];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const YkR1Args& A0 = LP.job[0];
+    const bool reduced = (A0.shX | A0.shY) != 0;
+    const bool maskActive = reduced ? (yk_r1_geometry(S, LP).maskActive != 0) : false;      // only the reduced planes look at the masks again
+    const int nList = __ldg(&S.hdr[YK_HD_R1_DEF0 + A0.out]);                                // written by yk_k_r1_offsets
     const int r = lane >> 2, c0 = (lane & 3) * 2;
-    const int startMode = A.mode3 ? 3 : 0;
-    for (int k = warp; k < nList; k += YK_R1_THREADS / 32) {
-        const YkR1Block b = yk_r1_block(A, sBlock[k]);
-        const int x = b.x, y = b.y;
-        const bool valid = (sMask[k] >> lane) & 1u;
+    const int startMode = A0.mode3 ? 3 : 0;
+    const int nItems = nList * LP.nJobs;
+    float (*term)[64] = sTerm[warp];
+    // the next item's list entry and (full-resolution planes) its samples are fetched while the current item is coded
+    const int stride = gridDim.x * (YK_R1_THREADS / 32);
+    int it = blockIdx.x * (YK_R1_THREADS / 32) + warp;
+    uint4 nItem = make_uint4(0u, 0u, 0u, 0u);
+    int nv0 = 0, nv1 = 0;
+    auto fetch = [&](int at) {
+        if (at >= nItems) return;
+        const int kk = LP.nJobs == 3 ? at / 3 : at / LP.nJobs;
+        const YkR1Args& An = LP.job[at - kk * LP.nJobs];
+        nItem = __ldg(reinterpret_cast<const uint4*>(S.r1List) + kk);
+        nv0 = 0; nv1 = 0;
+        if (!reduced && ((nItem.y >> lane) & 1u)) {
+            const int xx = nItem.x & 0xFFFF, yy = nItem.x >> 16;
+            if (An.srcU8) {
+                const unsigned short two = __ldg(reinterpret_cast<const unsigned short*>(An.srcU8 + (size_t)(yy + r) * An.pitchU8 + xx + c0));
+                nv0 = two & 255; nv1 = two >> 8;
+            } else {
+                const int2 p = __ldg(reinterpret_cast<const int2*>(An.src + (size_t)(yy + r) * An.pw + xx + c0));
+                nv0 = p.x; nv1 = p.y;
+            }
+        }
+    };
+    fetch(it);
+    for (; it < nItems; it += stride) {
+        const int k = LP.nJobs == 3 ? it / 3 : it / LP.nJobs, j = it - k * LP.nJobs;
+        const YkR1Args& A = LP.job[j];
+        const uint4 item = nItem;
+        int v0 = nv0, v1 = nv1;
+        fetch(it + stride);
+        const int x = item.x & 0xFFFF, y = item.x >> 16;
+        const int brw = item.w & 255, brh = (item.w >> 8) & 255;
+        const bool valid = (item.y >> lane) & 1u;
         // ---- min / max of the block (Plane::GetMinMax_Y, Plane.cpp:489-587).  Full resolution: over the coded pixels.
         // Reduced planes: over "not smooth and any covered mask sample set", where the reference addresses the
         // full-size mask with the REDUCED plane's width as row stride (Plane.cpp:516, 538-553) - restated literally.
         bool m0 = valid, m1 = valid;
-        const bool inRect = r < b.rh && c0 < b.rw;
         if (reduced) {
             m0 = m1 = false;
-            if (inRect) {
+            if (r < brh && c0 < brw) {
 #pragma unroll
                 for (int q = 0; q < 2; q++) {
                     const size_t vi = ((size_t)(x + c0 + q) << A.shX) + (size_t)((y + r) << A.shY) * A.pw;
@@ -313,19 +420,18 @@ yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, const YkR1Args A, 
                     // every covered sample is a mipmapMask value: kept by the alpha stage AND not claimed by a gradient
                     // tile (FittingQuadSmooth zeroes the mask over accepted tiles, EC.cpp:4035); with the reduced width as
                     // row stride the samples of the second row lie in another cell than vi
-                    bool any = yk_r1_valid_at(S, vi);
-                    if (A.shX) any |= yk_r1_valid_at(S, vi + 1);
-                    if (A.shY) any |= yk_r1_valid_at(S, vi + A.pw);
-                    if (A.shX && A.shY) any |= yk_r1_valid_at(S, vi + A.pw + 1);
+                    bool any = yk_r1_valid_at(S, maskActive, vi);
+                    if (A.shX) any |= yk_r1_valid_at(S, maskActive, vi + 1);
+                    if (A.shY) any |= yk_r1_valid_at(S, maskActive, vi + A.pw);
+                    if (A.shX && A.shY) any |= yk_r1_valid_at(S, maskActive, vi + A.pw + 1);
                     const bool ok = any && !yk_r1_smooth_at(S, (int)(vi % W), (int)(vi / W));
                     if (q) m1 = ok; else m0 = ok;
                 }
             }
-        }
-        int v0 = 0, v1 = 0;
-        if (valid || m0 || m1) {
-            int2 p = __ldg(reinterpret_cast<const int2*>(A.src + (size_t)(y + r) * A.pw + x + c0));
-            v0 = p.x; v1 = p.y;
+            if (valid || m0 || m1) {
+                const int2 p = __ldg(reinterpret_cast<const int2*>(A.src + (size_t)(y + r) * A.pw + x + c0));
+                v0 = p.x; v1 = p.y;
+            }
         }
         int mn = __reduce_min_sync(YK_FULL, min(m0 ? v0 : INT_MAX, m1 ? v1 : INT_MAX));
         int mx = __reduce_max_sync(YK_FULL, max(m0 ? v0 : INT_MIN, m1 ? v1 : INT_MIN));
@@ -337,68 +443,85 @@ yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, const YkR1Args A, 
         const int m = min(mn, 224);
         const int diff = max(mx - m, 16);
         const int b6 = (m * 63 + 112) / 224, BN = (b6 * 224) / 63;
-        const int scale = 223 - BN;
-        const int r7 = ((max(diff, 32) - 32) * 127 + scale - 1) / scale;
-        const int* T = lut + ((size_t)b6 * 176 + min(r7, 175)) * YK_R1_LUT_INTS;
+        (void)BN;
+        const int r7 = __ldg(r7tab + b6 * 224 + (max(diff, 32) - 32));          // ((max(diff,32) - 32) * 127 + scale - 1) / scale, scale = 223 - BN (EC.cpp:643-650)
+        const int* T = lut + (size_t)(b6 * 176 + min(r7, 175)) * YK_R1_LUT_INTS;
+        const unsigned short* RT = rtab + (size_t)(b6 * YK_R1_RTAB_R7 + min(r7, YK_R1_RTAB_R7 - 1)) * (6 * YK_R1_RTAB_VALUES);
         const int o0 = v0 + sgn, o1 = v1 + sgn;
-        unsigned codes0 = 0, codes1 = 0;                                       // 4 bits per mode
+        // the per-value table covers range codes below 128, bases below 63 (the other LUTs have entries above 255: reference
+        // quirks) and samples 0..383; anything else takes the search and the division themselves
+        const bool tabled = r7 < YK_R1_RTAB_R7 && b6 < 63 && __all_sync(YK_FULL, (unsigned)o0 < (unsigned)YK_R1_RTAB_VALUES && (unsigned)o1 < (unsigned)YK_R1_RTAB_VALUES);
+        // cumulated relative error term, float32 (EC.cpp:884-886): float(|entry - value|) / float(value) summed in
+        // row-major valid-pixel order.  Invalid pixels and zero samples add +0.0f, which leaves the sum unchanged: their
+        // reciprocal is set to zero here, and a zero difference gives a zero quotient by itself.
+        const bool use0 = valid && o0 != 0, use1 = valid && o1 != 0;
+        const float f0 = __int2float_rn(use0 ? o0 : 1), f1 = __int2float_rn(use1 ? o1 : 1);
+        const float rc0 = use0 ? __frcp_rn(f0) : 0.0f, rc1 = use1 ? __frcp_rn(f1) : 0.0f;
+        if (tabled) {
 #pragma unroll
-        for (int mode = 0; mode < 6; mode++) {
-            if (mode < startMode) continue;
-            const int off = mode < 3 ? 16 * mode : 48 + 8 * (mode - 3);
-            const int4* H = reinterpret_cast<const int4*>(T + 72 + off);
-            int f0 = 0, f1 = 0;
-#pragma unroll
-            for (int q = 0; q < (mode < 3 ? 4 : 2); q++) {
-                const int4 t = __ldg(H + q);
-                if (q) { f0 += (o0 > t.x); f1 += (o1 > t.x); }                  // threshold 0 of a LUT is unused
-                f0 += (o0 > t.y); f1 += (o1 > t.y);
-                f0 += (o0 > t.z); f1 += (o1 > t.z);
-                f0 += (o0 > t.w); f1 += (o1 > t.w);
+            for (int mode = 0; mode < 6; mode++) {
+                if (mode < startMode) continue;
+                const int L0 = __ldg(RT + mode * YK_R1_RTAB_VALUES + o0) & 255, L1 = __ldg(RT + mode * YK_R1_RTAB_VALUES + o1) & 255;
+                *reinterpret_cast<float2*>(&term[mode][2 * lane]) = make_float2(yk_r1_quot(abs(L0 - o0), f0, rc0), yk_r1_quot(abs(L1 - o1), f1, rc1));
             }
-            const int d0 = abs(__ldg(T + off + f0) - o0), d1 = abs(__ldg(T + off + f1) - o1);
-            codes0 |= (unsigned)f0 << (4 * mode); codes1 |= (unsigned)f1 << (4 * mode);
-            // cumulated relative error term, float32 (EC.cpp:884-886); invalid pixels add +0.0f which leaves the sum unchanged.
-            // The quotient is taken on operands that are never zero (a zero on either side sends the whole warp down the
-            // slow path of the IEEE division) and dropped afterwards: 0 / o is +-0 and adds nothing either.
-            const float q0 = (float)(d0 ? d0 : 1) / (float)(o0 ? o0 : 1), q1 = (float)(d1 ? d1 : 1) / (float)(o1 ? o1 : 1);
-            sTerm[warp][mode][2 * lane] = (valid && o0 != 0 && d0 != 0) ? q0 : 0.0f;
-            sTerm[warp][mode][2 * lane + 1] = (valid && o1 != 0 && d1 != 0) ? q1 : 0.0f;
+        } else {
+#pragma unroll 1
+            for (int mode = startMode; mode < 6; mode++) {
+                const int off = mode < 3 ? 16 * mode : 48 + 8 * (mode - 3);
+                int g0 = 0, g1 = 0;
+                for (int st = (mode < 3 ? 8 : 4); st > 0; st >>= 1) {
+                    if (o0 > __ldg(T + 72 + off + g0 + st)) g0 += st;
+                    if (o1 > __ldg(T + 72 + off + g1 + st)) g1 += st;
+                }
+                const int d0 = abs(__ldg(T + off + g0) - o0), d1 = abs(__ldg(T + off + g1) - o1);
+                term[mode][2 * lane] = (use0 && d0 != 0) ? __fdiv_rn(__int2float_rn(d0), f0) : 0.0f;
+                term[mode][2 * lane + 1] = (use1 && d1 != 0) ? __fdiv_rn(__int2float_rn(d1), f1) : 0.0f;
+            }
         }
         __syncwarp();
         float err = 0.0f;
         if (lane >= startMode && lane < 6) {
             // the reference sums in row-major valid-pixel order; float addition is not associative, so one lane per mode
-            const float4* P = reinterpret_cast<const float4*>(sTerm[warp][lane]);
+            const float4* P = reinterpret_cast<const float4*>(term[lane]);
 #pragma unroll 4
             for (int q = 0; q < 16; q++) {
                 const float4 t = P[q];
                 err = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(err, t.x), t.y), t.z), t.w);
             }
         }
-        int bestMode = -1;
-        float bestErr = 99999999.0f;
-        for (int mode = startMode; mode < 6; mode++) {                          // `<=`: later modes win ties, EC.cpp:897-905
-            const float e = __shfl_sync(YK_FULL, err, mode);
-            if (e <= bestErr) { bestErr = e; bestMode = mode; }
-        }
-        __syncwarp();                                                           // sTerm is rewritten by the next block
+        // `<=`: later modes win ties (EC.cpp:897-905).  Sums can be negative on signed chroma planes: compare through the
+        // order-preserving map of the bit patterns (-0 counted as +0, as `<=` does)
+        const unsigned eraw = __float_as_uint(__fadd_rn(err, 0.0f));
+        const unsigned ebits = (lane >= startMode && lane < 6) ? (eraw ^ ((eraw >> 31) ? 0xFFFFFFFFu : 0x80000000u)) : 0xFFFFFFFFu;
+        const unsigned emin = __reduce_min_sync(YK_FULL, ebits);
+        const int bestMode = 31 - __clz((int)__ballot_sync(YK_FULL, ebits == emin && lane < 6));
+        __syncwarp();                                                           // the terms are rewritten by the next item
         const unsigned bv0 = __ballot_sync(YK_FULL, valid);
         if (valid) {
+            // the codes of the chosen mode: from the table again, or the largest n with value > threshold[n]
+            const int boff = bestMode < 3 ? 16 * bestMode : 48 + 8 * (bestMode - 3);
+            int c0v = 0, c1v = 0;
+            if (tabled) {
+                c0v = __ldg(RT + bestMode * YK_R1_RTAB_VALUES + o0) >> 8; c1v = __ldg(RT + bestMode * YK_R1_RTAB_VALUES + o1) >> 8;
+            } else {
+                for (int st = (bestMode < 3 ? 8 : 4); st > 0; st >>= 1) {
+                    if (o0 > __ldg(T + 72 + boff + c0v + st)) c0v += st;
+                    if (o1 > __ldg(T + 72 + boff + c1v + st)) c1v += st;
+                }
+            }
             const int before = 2 * __popc(bv0 & ((1u << lane) - 1u));           // both pixels of a lane share validity
-            const int c0v = (codes0 >> (4 * bestMode)) & 15, c1v = (codes1 >> (4 * bestMode)) & 15;
-            const int n0 = nibBase + sNibOff[k] + before;                       // even: the two nibbles share a byte
+            const int n0 = (int)item.z + before;                                // even: the two nibbles share a byte
             reinterpret_cast<uint8_t*>(S.r1Nib[A.out])[n0 >> 1] = (uint8_t)(c0v | (c1v << 4));   // low nibble first, EC.cpp:1180-1184
-            if (S.r1Dst) {
+            if (A.dst) {
                 // EC.cpp:4441-4502: chroma blocks with a negative minimum go back minus 128; reduced planes are
                 // written at their top-left full-size position only ("interpolation comes later")
-                const int* L = T + (bestMode < 3 ? 16 * bestMode : 48 + 8 * (bestMode - 3));
+                const int off = boff;
                 const int offset = (A.chroma && sgn) ? -128 : 0;
-                int* d = S.r1Dst + (size_t)((y + r) << A.shY) * S.w + ((x + c0) << A.shX);
-                d[0] = __ldg(L + c0v) + offset; d[1 << A.shX] = __ldg(L + c1v) + offset;
+                int* d = A.dst + (size_t)((y + r) << A.shY) * S.w + ((x + c0) << A.shX);
+                d[0] = __ldg(T + off + c0v) + offset; d[1 << A.shX] = __ldg(T + off + c1v) + offset;
             }
         }
-        if (lane == 0) S.r1Defs[A.out][defBase + k] = (uint16_t)((bestMode << 13) | (r7 << 7) | b6);    // EncodeTileType, YAIK_private.h:358
+        if (lane == 0) S.r1Defs[A.out][k] = (uint16_t)((bestMode << 13) | (r7 << 7) | b6);    // EncodeTileType, YAIK_private.h:358
     }
 }
 
@@ -460,8 +583,15 @@ void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t*
                      int32_t* mappedRGB, int32_t* recon0, int32_t* recon1, int32_t* recon2, cudaStream_t st) {
     YK_LAUNCH(yk_k_state, dim3(nRegions), dim3(YK_THREADS), 0, st, slotsDev, slot, smoothMap, mipmapMask, mappedRGB, recon0, recon1, recon2);
 }
-void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, const YkR1Args& args, const int* lutDev, cudaStream_t st) {
-    YK_LAUNCH(yk_k_r1_encode, dim3((args.nBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT), dim3(YK_R1_THREADS), 0, st, slotsDev, slot, args, lutDev);
+void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, const YkR1Launch& launch, int maxBlocks, int numSMs, const int* lutDev, const uint16_t* rtabDev, const int16_t* r7Dev, cudaStream_t st) {
+    const int units = (maxBlocks + YK_R1_UNIT - 1) / YK_R1_UNIT;
+    YK_LAUNCH(yk_k_r1_offsets, dim3(units > 0 ? units : 1), dim3(YK_R1_UNIT), 0, st, slotsDev, slot, launch);
+    // warps take items with a grid stride: enough CTAs to fill every SM, no more than there can be items
+    const int perCta = YK_R1_THREADS / 32;
+    long long want = ((long long)maxBlocks * launch.nJobs + perCta - 1) / perCta;
+    const long long cap = (long long)numSMs * YK_R1_CAP;
+    if (want > cap) want = cap;
+    YK_LAUNCH(yk_k_r1_encode, dim3(want > 0 ? (unsigned)want : 1u), dim3(YK_R1_THREADS), 0, st, slotsDev, slot, launch, lutDev, reinterpret_cast<const unsigned short*>(rtabDev), reinterpret_cast<const short*>(r7Dev));
 }
 void yk_launch_chroma(const YkSlotDev* slotsDev, int slot, int w, int h, const YkChromaArgs& args, cudaStream_t st) {
     const int quads = (w >> 1) * (h >> 1);
