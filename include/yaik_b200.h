@@ -238,6 +238,44 @@ int  yk_copy_async(yk_ctx* ctx, void* dst, const void* src, size_t bytes);
 int  yk_copy_to_host(yk_ctx* ctx, void* hostDst, const void* devSrc, size_t bytes);
 int  yk_copy_from_host(yk_ctx* ctx, void* devDst, const void* hostSrc, size_t bytes);
 
+/* ---- host tails behind the analysis stage: plain host code, no device involved ------
+ *
+ * PaletteCompressor (EC.cpp:3209-3502), the delta code-book coder of a gradient pass's rgbStream, as an object
+ * instead of the reference's globals CodeRGB[100000] / CodeCount (EC.cpp:3216-3217).  The reference never clears that
+ * table and FindCodeBook always scans 64 entries (EC.cpp:3248-3255), so its bytes depend on the calls made before
+ * (SURVEY.md S10).  YK_PALETTE_BUG_COMPATIBLE reproduces them call for call, starting from a fresh object = a fresh
+ * process; YK_PALETTE_DECODABLE only emits indices of the code book it writes (what PaletteDecompressor can read).
+ * yk_palette_compress returns YK_ERR_CAPACITY where the reference's WriteRAW would overflow `maxSize`. */
+#define YK_PALETTE_BUG_COMPATIBLE 0
+#define YK_PALETTE_DECODABLE      1
+typedef struct yk_palette yk_palette;
+yk_palette* yk_palette_create(int mode);
+void yk_palette_destroy(yk_palette* p);
+void yk_palette_reset(yk_palette* p);
+int  yk_palette_compress(yk_palette* p, const uint8_t* rgbStream, int size, uint8_t* out, int outCap, int* outBytes);
+
+/* Chunk serialisers of Convert() with the entropy coder as a callback: compress(user, dst, dstCap, src, srcBytes,
+ * level) returns the compressed size, 0 on failure (ZSTD_compress with its arguments in that order; the reference
+ * uses level 18, 21 for PLNT).  Every function writes one chunk at dst and returns its size in *n (0 = the reference
+ * writes no chunk for these arguments).  Layouts: include/YAIK_private.h:96-118, 172-197, 290-300, 347-356.
+ *   yk_chunk_file_header  FileHeader 'YAIK'                                  EC.cpp:9007-9016
+ *   yk_chunk_mipm         MipPrefilter's chunk                               EC.cpp:1367-1396
+ *   yk_chunk_gtil         FittingQuadSmooth's chunk (runs PaletteCompressor) EC.cpp:4239-4350; bbox = {minX,minY,maxX,maxY}
+ *   yk_chunk_1dtl         GenerateDynamicTileChunk                           EC.cpp:8524-8576
+ *   yk_chunk_plnt         DynamicTileEncode's chunk                          EC.cpp:4515-4589; planeType 0 Y, 1 Co, 2 Cg
+ *   yk_chunk_end          0xDEADBEEF                                         EC.cpp:9779-9782 */
+typedef size_t (*yk_compress_fn)(void* user, void* dst, size_t dstCap, const void* src, size_t srcBytes, int level);
+int  yk_chunk_file_header(uint8_t* dst, size_t cap, size_t* n, int width, int height, int hasAlpha);
+int  yk_chunk_mipm(uint8_t* dst, size_t cap, size_t* n, const int bboxTiles[4], const uint8_t* bitmap, int bitmapBytes);
+int  yk_chunk_gtil(uint8_t* dst, size_t cap, size_t* n, yk_palette* palette, yk_compress_fn compress, void* user,
+                   int shX, int shY, int planeBits, const int bbox[4], const uint8_t* bitmap, int bitmapBytes,
+                   const uint8_t* rgbStream, int rgbBytes, int colorCompression);
+int  yk_chunk_1dtl(uint8_t* dst, size_t cap, size_t* n, yk_compress_fn compress, void* user, const uint8_t* idx, int idxBytes,
+                   const uint8_t* type, int typeBytes, int compressionColor, int compressionRange);
+int  yk_chunk_plnt(uint8_t* dst, size_t cap, size_t* n, yk_compress_fn compress, void* user, const int constraint[4],
+                   const uint16_t* defs, int nDefs, const uint8_t* nibbles, int nNibbles, int planeType, int halfX, int halfY);
+int  yk_chunk_end(uint8_t* dst, size_t cap, size_t* n);
+
 #ifdef __cplusplus
 }
 #endif

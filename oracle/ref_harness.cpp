@@ -41,6 +41,7 @@ void DynamicTileEncoderTable();   // EC.cpp:702
 
 // ---------------------------------------------------------------- rgbStream capture
 static std::vector<std::vector<u8>> g_rgbCaptured;
+static std::vector<std::vector<u8>> g_palCaptured;        // what PaletteCompressor wrote for each captured rgbStream
 static double g_paletteSeconds = 0.0;
 
 bool PaletteCompressor(u8* input, int size, u8* output, u32* maxSize) {
@@ -51,6 +52,7 @@ bool PaletteCompressor(u8* input, int size, u8* output, u32* maxSize) {
     auto t0 = std::chrono::steady_clock::now();
     bool r = real(input, size, output, maxSize);
     g_paletteSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    g_palCaptured.emplace_back(output, output + (r ? *maxSize : 0));
     return r;
 }
 
@@ -99,6 +101,7 @@ struct Probe : EncoderContext {
             int nbytes = (mh.bbox.w * mh.bbox.h + 7) / 8;
             recInts("alpha.chunk_bbox", { mh.bbox.x, mh.bbox.y, mh.bbox.w, mh.bbox.h, mh.version, mh.mipmapLevel });
             rec("alpha.bitmap", 'B', c + sizeof(HeaderBase) + sizeof(MipmapHeader), nbytes);
+            rec("alpha.chunk", 'B', c, p1 - p0);
         } else {
             recInts("alpha.chunk_bbox", {});
             rec("alpha.bitmap", 'B', NULL, 0);
@@ -135,6 +138,11 @@ struct Probe : EncoderContext {
             snprintf(nm, sizeof nm, "grad%d.rgb", k);
             if (g_rgbCaptured.size() > cap0) rec(nm, 'B', g_rgbCaptured.back().data(), g_rgbCaptured.back().size());
             else rec(nm, 'B', NULL, 0);
+            snprintf(nm, sizeof nm, "grad%d.pal", k);          // PaletteCompressor's bytes for that stream (host tail)
+            if (g_palCaptured.size() > cap0) rec(nm, 'B', g_palCaptured.back().data(), g_palCaptured.back().size());
+            else rec(nm, 'B', NULL, 0);
+            snprintf(nm, sizeof nm, "grad%d.chunk", k);        // the raw GTIL chunk (host tail)
+            rec(nm, 'B', (const u8*)memBuf + p0, p1 - p0);
             if (dumpPerPass) { snprintf(nm, sizeof nm, "grad%d.smoothMap", k); recPlane(nm, smoothMap); }
         }
         recPlane("state.smoothMap", smoothMap);
@@ -176,6 +184,12 @@ struct Probe : EncoderContext {
             snprintf(nm, sizeof nm, "r2.type%d", c);  rec(nm, 'B', t0p, pType - t0p);
             snprintf(nm, sizeof nm, "r2.debug%d", c); recPlane(nm, debug->GetPlane(c));
         }
+        {   // the '1DTL' chunk of the three planes together (EC.cpp:9465)
+            size_t p0 = tell();
+            GenerateDynamicTileChunk(stream.data(), (int)(p - stream.data()));
+            size_t p1 = tell();
+            rec("r2.chunk", 'B', (const u8*)memBuf + p0, p1 - p0);
+        }
         (void)output;
     }
 
@@ -202,6 +216,7 @@ struct Probe : EncoderContext {
             snprintf(nm, sizeof nm, "r1.hdr%d", c);
             recInts(nm, { pt.bbox.x, pt.bbox.y, pt.bbox.w, pt.bbox.h, (int)pt.expectedSizeTileStream, pt.version, pt.format, ret });
             snprintf(nm, sizeof nm, "r1.dst%d", c);     recPlane(nm, dst);
+            snprintf(nm, sizeof nm, "r1.chunk%d", c);   rec(nm, 'B', ch, p1 - p0);
         }
     }
 

@@ -2,7 +2,12 @@
 // the reference's Convert() does (EC.cpp:9027-9093, 9451-9460, 9542-9544) and dumps the results in the same record
 // format as oracle/ref_harness.cpp, so tests/test_host_mirror.py can compare them with the golden vectors / the oracle.
 // usage: host_mirror_test <in.ykin> <out.ykout> [alpha] [grad] [r2] [r1] [r1_3bit] [noprepare]
+//                         [yaik=<file>] [zstdlib=<shared library with ZSTD_compress>] [async] [decodable]
+// yaik=: the host tails are attached (PaletteCompressor, chunk serialisers) and the chunks go to <file> in Convert()'s order;
+// the entropy coder behind the callback is ZSTD_compress of zstdlib= (e.g. the reference's own build in oracle/_ref), or a
+// stand-in that stores the bytes as they are; async: tails on the worker thread.
 #include "EncoderContext.h"
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -19,15 +24,30 @@ static void rec(const char* name, char dtype, const void* data, uint64_t count) 
 static void recPlane(const char* name, Plane* p) { rec(name, 'i', p->GetPixels(), (uint64_t)p->GetWidth() * p->GetHeight()); }
 static void recInts(const char* name, std::vector<int> v) { rec(name, 'i', v.data(), v.size()); }
 
+typedef size_t (*zstd_fn)(void*, size_t, const void*, size_t, int);
+static zstd_fn g_zstd = NULL;
+static size_t compressCallback(void*, void* dst, size_t cap, const void* src, size_t n, int level) {
+    if (g_zstd) { const size_t r = g_zstd(dst, cap, src, n, level); return r > cap ? 0 : r; }     // an error code is a huge value
+    if (n + 1 > cap) return 0;                                                                        // stand-in: one marker byte + the bytes
+    ((unsigned char*)dst)[0] = 0x53; memcpy((unsigned char*)dst + 1, src, n);
+    return n + 1;
+}
+
 int main(int argc, char** argv) {
     if (argc < 3) return 2;
     bool doAlpha = false, doGrad = false, doR2 = false, doR1 = false, r1_3bit = false, prepare = true, doChroma = false;
     int chromaCfg[4] = { 1, 0, 1, 0 }, chromaModes[2] = { 2, 2 };
+    std::string yaikPath, zstdLib;
+    bool asyncTails = false, decodable = false;
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         if (a == "alpha") doAlpha = true; else if (a == "grad") doGrad = true; else if (a == "r2") doR2 = true;
         else if (a == "r1") doR1 = true; else if (a == "r1_3bit") { doR1 = true; r1_3bit = true; }
         else if (a == "noprepare") prepare = false;
+        else if (a.rfind("yaik=", 0) == 0) yaikPath = a.substr(5);
+        else if (a.rfind("zstdlib=", 0) == 0) zstdLib = a.substr(8);
+        else if (a == "async") asyncTails = true;
+        else if (a == "decodable") decodable = true;
         else if (a.rfind("chroma=", 0) == 0 && a.size() == 14) {                  // chroma=XYXY:MM, as oracle/ref_harness.cpp
             doChroma = true;
             for (int k = 0; k < 4; k++) chromaCfg[k] = a[7 + k] == '1';
@@ -58,6 +78,18 @@ int main(int argc, char** argv) {
     }
     ctx.SetImageToEncode(img);
     Image* output = Image::CreateImage(W, H, 3, true);
+    if (!yaikPath.empty()) {
+        if (!zstdLib.empty()) {
+            void* h = dlopen(zstdLib.c_str(), RTLD_NOW | RTLD_LOCAL);
+            g_zstd = h ? (zstd_fn)dlsym(h, "ZSTD_compress") : NULL;
+            if (!g_zstd) { fprintf(stderr, "cannot load ZSTD_compress from %s\n", zstdLib.c_str()); return 1; }
+        }
+        ctx.outFile = fopen(yaikPath.c_str(), "wb");
+        if (!ctx.outFile) { perror(yaikPath.c_str()); return 1; }
+        ctx.SetCompressor(compressCallback, NULL, decodable ? YK_PALETTE_DECODABLE : YK_PALETTE_BUG_COMPATIBLE);
+        ctx.SetAsyncTails(asyncTails);
+        ctx.WriteFileHeader();                                                      // EC.cpp:9007-9016
+    }
 
     if (doAlpha && NP == 4) {
         ctx.MipPrefilter(true);                                                     // EC.cpp:9027
@@ -102,6 +134,7 @@ int main(int argc, char** argv) {
             snprintf(nm, sizeof nm, "r2.idx%d", c);  rec(nm, 'B', p0, p - p0);
             snprintf(nm, sizeof nm, "r2.type%d", c); rec(nm, 'B', t0, pType - t0);
         }
+        ctx.GenerateDynamicTileChunk(stream.data(), (int)(p - stream.data()));      // EC.cpp:9465
     }
     if (doR1) {
         for (int c = 0; c < 3; c++) {
@@ -140,6 +173,11 @@ int main(int argc, char** argv) {
                 delete dst;
             }
         }
+    }
+    if (ctx.outFile) {
+        ctx.WriteEndTag();                                                          // EC.cpp:9779-9782
+        ctx.FinishTails();
+        fclose(ctx.outFile); ctx.outFile = NULL;
     }
     recInts("meta", { W, H, NP, ctx.lastError });
     fclose(g_out);

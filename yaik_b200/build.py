@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libyaik_b200.so")
-SOURCES = ["yk_analyze.cu", "yk_emit.cu", "yk_kernels.cu", "yk_api.cu", "yk_hostpack.cpp"]
+SOURCES = ["yk_analyze.cu", "yk_emit.cu", "yk_kernels.cu", "yk_api.cu", "yk_hostpack.cpp", "yk_hosttail.cpp"]
 DEPS = SOURCES + ["yk_internal.h", "yk_device.h", os.path.join("..", "..", "include", "yaik_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

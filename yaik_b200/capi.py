@@ -27,7 +27,11 @@ EXPORTS = [
     "yk_profile", "yk_profile_read",
     "yk_strip_config", "yk_strip_halo_ptrs", "yk_strip_phase",
     "yk_ipc_export", "yk_ipc_open", "yk_ipc_close", "yk_copy_async", "yk_copy_to_host", "yk_copy_from_host",
+    "yk_palette_create", "yk_palette_destroy", "yk_palette_reset", "yk_palette_compress",
+    "yk_chunk_file_header", "yk_chunk_mipm", "yk_chunk_gtil", "yk_chunk_1dtl", "yk_chunk_plnt", "yk_chunk_end",
 ]
+
+COMPRESS_FN = C.CFUNCTYPE(C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int)
 
 
 class Results(C.Structure):
@@ -110,6 +114,22 @@ def load_library(path: str | None = None):
     L.yk_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.yk_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.yk_copy_from_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.yk_palette_create.restype = C.c_void_p
+    L.yk_palette_create.argtypes = [C.c_int]
+    L.yk_palette_destroy.restype = None
+    L.yk_palette_destroy.argtypes = [C.c_void_p]
+    L.yk_palette_reset.restype = None
+    L.yk_palette_reset.argtypes = [C.c_void_p]
+    L.yk_palette_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    szp = C.POINTER(C.c_size_t)
+    L.yk_chunk_file_header.argtypes = [C.c_void_p, C.c_size_t, szp, C.c_int, C.c_int, C.c_int]
+    L.yk_chunk_mipm.argtypes = [C.c_void_p, C.c_size_t, szp, C.POINTER(C.c_int), C.c_void_p, C.c_int]
+    L.yk_chunk_gtil.argtypes = [C.c_void_p, C.c_size_t, szp, C.c_void_p, COMPRESS_FN, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.yk_chunk_1dtl.argtypes = [C.c_void_p, C.c_size_t, szp, COMPRESS_FN, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.yk_chunk_plnt.argtypes = [C.c_void_p, C.c_size_t, szp, COMPRESS_FN, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                C.c_int, C.c_int, C.c_int]
+    L.yk_chunk_end.argtypes = [C.c_void_p, C.c_size_t, szp]
     return L
 
 

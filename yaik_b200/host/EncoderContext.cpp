@@ -11,9 +11,17 @@ EncoderContext::EncoderContext(int cudaDevice)
       colorCompressionQuad(250), colorCompression1D(255), rangeCompression1D(15),
       halfCoW(true), halfCoH(false), halfCgW(true), halfCgH(false), downSampleCo(AVERAGE_BOX), downSampleCg(AVERAGE_BOX),
       YCoCgImg(NULL), workCo(NULL), workCg(NULL), lastError(YK_OK),
+      outFile(NULL), fileOutSize(0), compressFn(NULL), compressUser(NULL), palette(NULL), asyncTails(false), workerStop(false), tailsInFlight(0),
       ctx(NULL), device(cudaDevice), capW(0), capH(0), lastTestOutput(NULL), prepared(false), useYCoCgPlanes(false) {}
 
 EncoderContext::~EncoderContext() {
+    FinishTails();
+    if (worker.joinable()) {
+        { std::lock_guard<std::mutex> lk(tailMutex); workerStop = true; }
+        tailCv.notify_all();
+        worker.join();
+    }
+    if (palette) yk_palette_destroy(palette);
     if (ctx) yk_destroy(ctx);
     delete mipmapMask; delete smoothMap; delete mapSmoothTile; delete mappedRGB;
     delete YCoCgImg; delete workCo; delete workCg;
@@ -70,7 +78,16 @@ void EncoderContext::MipPrefilter(bool active) {
     lastAlpha.bitmap.resize(nb); lastAlpha.wroteChunk = wrote != 0;
     boundX0 = lastAlpha.bbox[0]; boundY0 = lastAlpha.bbox[1]; boundX1 = lastAlpha.bbox[2]; boundY1 = lastAlpha.bbox[3];
     remainingPixels = lastAlpha.remainingPixels; mipMapTileSize = 16;       // EC.cpp:1287-1291
-    // host tail of the reference from here: fwrite 'MIPM' HeaderBase + MipmapHeader + lastAlpha.bitmap (EC.cpp:1367-1396)
+    // host tail (EC.cpp:1367-1396): 'MIPM' HeaderBase + MipmapHeader + bitmap
+    if (outFile && lastAlpha.wroteChunk) {
+        const std::vector<u8> bitmap = lastAlpha.bitmap;
+        int bb[4]; for (int k = 0; k < 4; k++) bb[k] = lastAlpha.chunkBBoxTiles[k];
+        postTail([this, bitmap, bb]() {
+            std::vector<u8> chunk(bitmap.size() + 64);
+            size_t n = 0;
+            if (yk_chunk_mipm(chunk.data(), chunk.size(), &n, bb, bitmap.data(), (int)bitmap.size()) == YK_OK) { chunk.resize(n); writeChunk(chunk); }
+        });
+    }
 }
 
 void EncoderContext::PrepareQuadSmooth() {
@@ -105,8 +122,21 @@ int EncoderContext::FittingQuadSmooth(int rejectFactor, Plane* a, Plane* b, Plan
     lastGradient.minX = bbox[0]; lastGradient.minY = bbox[1]; lastGradient.maxX = bbox[2]; lastGradient.maxY = bbox[3];
     lastGradient.tileDone = done; lastGradient.shX = tileBitSizeX; lastGradient.shY = tileBitSizeY;
     lastTestOutput = testOutput;
-    // host tail of the reference from here (EC.cpp:4239-4350): if (maxX > minX && maxY > minY && rgbStream.size() > 0)
+    // host tail (EC.cpp:4239-4350): if (maxX > minX && maxY > minY && rgbStream.size() > 0)
     //   CompressStream(bitmap), PaletteCompressor(rgbStream) -> CompressStream, fwrite 'GTIL' + HeaderGradientTile + streams
+    if (outFile && compressFn) {
+        const std::vector<u8> bitmap = lastGradient.bitmap, rgb = lastGradient.rgbStream;
+        const int shX = tileBitSizeX, shY = tileBitSizeY, cc = colorCompressionQuad;
+        int bb[4] = { bbox[0], bbox[1], bbox[2], bbox[3] };
+        postTail([this, bitmap, rgb, shX, shY, cc, bb]() {
+            std::vector<u8> chunk(bitmap.size() * 2 + rgb.size() * 6 + 4096);
+            size_t n = 0;
+            const int rc = yk_chunk_gtil(chunk.data(), chunk.size(), &n, palette, compressFn, compressUser, shX, shY, 7, bb,
+                                         bitmap.data(), (int)bitmap.size(), rgb.data(), (int)rgb.size(), cc);
+            if (rc == YK_OK && n) { chunk.resize(n); fileOutSize += (int)n - 36; writeChunk(chunk); }
+            else if (rc) lastError = rc;
+        });
+    }
     return done;
 }
 
@@ -176,7 +206,19 @@ int EncoderContext::DynamicTileEncode(bool mode3BitOnly, Plane* plane, Plane* ds
     lastDynamic.nibbles.resize((nn + 1) / 2); lastDynamic.tileDefs.resize(nd); lastDynamic.nNibbles = nn;
     lastDynamic.constraint.x = (s16)cons[0]; lastDynamic.constraint.y = (s16)cons[1];
     lastDynamic.constraint.w = (s16)cons[2]; lastDynamic.constraint.h = (s16)cons[3];
-    // host tail of the reference from here (EC.cpp:4515-4589): ZSTD-21 of tileDefs and nibbles, fwrite 'PLNT' + PlaneTile
+    // host tail (EC.cpp:4515-4589): ZSTD-21 of tileDefs and nibbles, fwrite 'PLNT' + PlaneTile
+    if (outFile && compressFn) {
+        const std::vector<u8> nib = lastDynamic.nibbles; const std::vector<u16> defs = lastDynamic.tileDefs;
+        const int nNib = 2 * (int)nib.size();           // the reference closes a half byte (EC.cpp:4524-4526)
+        const int type = isCo ? 1 : (isCg ? 2 : 0), hx = isHalfX, hy = isHalfY;
+        int cb[4] = { cons[0], cons[1], cons[2], cons[3] };
+        postTail([this, nib, defs, nNib, type, hx, hy, cb]() {
+            std::vector<u8> chunk(nib.size() * 2 + defs.size() * 4 + 4096);
+            size_t n = 0;
+            const int rc = yk_chunk_plnt(chunk.data(), chunk.size(), &n, compressFn, compressUser, cb, defs.data(), (int)defs.size(), nib.data(), nNib, type, hx, hy);
+            if (rc == YK_OK) { chunk.resize(n); writeChunk(chunk); } else lastError = rc;
+        });
+    }
     return 0;                                       // the reference returns layerSize, which it never updates (EC.cpp:4407, 4601)
 }
 
@@ -192,4 +234,79 @@ void EncoderContext::SyncStatePlanes() {
     int32_t* rec[3] = { 0, 0, 0 };
     if (lastTestOutput) for (int n = 0; n < 3; n++) rec[n] = lastTestOutput->GetPlane(n)->GetPixels();
     lastError = yk_download_state(ctx, 0, smoothMap->GetPixels(), mst, mrgb, mipmapMask->GetPixels(), lastTestOutput ? rec : NULL);
+}
+
+// ---- host tails ------------------------------------------------------------------------------------------------------
+void EncoderContext::SetCompressor(yk_compress_fn fn, void* user, int paletteMode) {
+    FinishTails();
+    compressFn = fn; compressUser = user;
+    if (palette) yk_palette_destroy(palette);
+    palette = yk_palette_create(paletteMode);
+}
+
+void EncoderContext::SetAsyncTails(bool on) {
+    FinishTails();
+    asyncTails = on;
+    if (on && !worker.joinable()) worker = std::thread(&EncoderContext::workerLoop, this);
+}
+
+void EncoderContext::workerLoop() {
+    for (;;) {
+        std::function<void()> job;
+        {
+            std::unique_lock<std::mutex> lk(tailMutex);
+            tailCv.wait(lk, [this] { return workerStop || !tailQueue.empty(); });
+            if (tailQueue.empty()) return;              // stop requested and nothing left
+            job = std::move(tailQueue.front());
+            tailQueue.pop_front();
+        }
+        job();
+        { std::lock_guard<std::mutex> lk(tailMutex); tailsInFlight--; }
+        tailIdleCv.notify_all();
+    }
+}
+
+void EncoderContext::postTail(std::function<void()> job) {
+    if (!asyncTails) { job(); return; }
+    { std::lock_guard<std::mutex> lk(tailMutex); tailQueue.push_back(std::move(job)); tailsInFlight++; }
+    tailCv.notify_one();
+}
+
+void EncoderContext::FinishTails() {
+    if (!worker.joinable()) return;
+    std::unique_lock<std::mutex> lk(tailMutex);
+    tailIdleCv.wait(lk, [this] { return tailsInFlight == 0; });
+}
+
+void EncoderContext::writeChunk(const std::vector<u8>& chunk) {        // one writer at a time: the worker, or the caller in the synchronous form
+    if (outFile && !chunk.empty()) fwrite(chunk.data(), 1, chunk.size(), outFile);
+}
+
+void EncoderContext::WriteFileHeader() {
+    if (!outFile || !original) return;
+    const int w = original->GetWidth(), h = original->GetHeight(), a = original->HasAlpha() ? 1 : 0;
+    postTail([this, w, h, a]() {
+        std::vector<u8> chunk(16); size_t n = 0;
+        if (yk_chunk_file_header(chunk.data(), chunk.size(), &n, w, h, a) == YK_OK) { chunk.resize(n); writeChunk(chunk); }
+    });
+}
+
+void EncoderContext::WriteEndTag() {
+    if (!outFile) return;
+    postTail([this]() {
+        std::vector<u8> chunk(8); size_t n = 0;
+        if (yk_chunk_end(chunk.data(), chunk.size(), &n) == YK_OK) { chunk.resize(n); writeChunk(chunk); }
+    });
+}
+
+void EncoderContext::GenerateDynamicTileChunk(u8* stream, int sizeStream) {
+    if (!outFile || !compressFn || sizeStream <= 0) return;
+    const std::vector<u8> idx(stream, stream + sizeStream), type(streamType, pType);
+    const int cc = colorCompression1D, cr = rangeCompression1D;
+    postTail([this, idx, type, cc, cr]() {
+        std::vector<u8> chunk(idx.size() * 3 + type.size() * 2 + 4096);
+        size_t n = 0;
+        const int rc = yk_chunk_1dtl(chunk.data(), chunk.size(), &n, compressFn, compressUser, idx.data(), (int)idx.size(), type.data(), (int)type.size(), cc, cr);
+        if (rc == YK_OK && n) { chunk.resize(n); writeChunk(chunk); } else if (rc) lastError = rc;
+    });
 }

@@ -6,8 +6,15 @@
 // keeps in function locals and hands to its host tail (PaletteCompressor / ZSTD / fwrite) is kept in `last*` members
 // so the tail can be attached unchanged.  There is no CPU implementation behind these members.
 #pragma once
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <stdio.h>
+#include <thread>
 #include <vector>
 #include "framework.h"
+#include "../../include/yaik_b200.h"
 
 extern u8* streamType;      // EC.cpp:8217 — the R2 type stream the reference keeps in globals
 extern u8* pType;           // EC.cpp:8218
@@ -57,7 +64,32 @@ struct EncoderContext {
     struct { std::vector<u8> bitmap, rgbStream; int minX, minY, maxX, maxY, tileDone, shX, shY; } lastGradient;                  // GTIL chunk, EC.cpp:4239-4350
     struct { std::vector<u8> nibbles; std::vector<u16> tileDefs; int nNibbles; BoundingBox constraint; } lastDynamic;            // PLNT chunk, EC.cpp:4515-4589
 
+    // ---- host tails: what the reference does after each stage - PaletteCompressor, entropy coding,
+    // fwrite of the chunk into outFile (EC.cpp:1367-1396, 4239-4350, 4515-4589, 8524-8576).  They are attached once a
+    // compressor callback is set (the reference links zstd; this library links none): every stage member then appends its
+    // chunk to outFile, in call order.  With SetAsyncTails(true) the tails run on a worker thread, so PaletteCompressor and
+    // the entropy coder of one stage (or image) overlap the GPU analysis of the next; FinishTails() waits for them.
+    FILE* outFile;              // EncoderContext.h:306 of the reference
+    int   fileOutSize;          // bytes of compressed streams written (CompressStream, EC.cpp:3703)
+    void SetCompressor(yk_compress_fn fn, void* user, int paletteMode = YK_PALETTE_BUG_COMPATIBLE);
+    void SetAsyncTails(bool on);
+    void FinishTails();
+    void WriteFileHeader();                                         // EC.cpp:9007-9016
+    void WriteEndTag();                                             // EC.cpp:9779-9782
+    void GenerateDynamicTileChunk(u8* stream, int sizeStream);      // EncoderContext.h:235, EC.cpp:8524-8576 (type stream: streamType .. pType)
+
 private:
+    yk_compress_fn compressFn; void* compressUser;
+    yk_palette* palette;
+    bool asyncTails, workerStop;
+    std::thread worker;
+    std::mutex tailMutex;
+    std::condition_variable tailCv, tailIdleCv;
+    std::deque<std::function<void()> > tailQueue;
+    int tailsInFlight;
+    void postTail(std::function<void()> job);
+    void writeChunk(const std::vector<u8>& chunk);
+    void workerLoop();
     yk_ctx* ctx;
     int device, capW, capH;
     Image* lastTestOutput;
