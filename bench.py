@@ -200,6 +200,129 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ strips (configs[3])
+def _stream_digests(res):
+    """Lengths + SHA-1 of every stream of one strip (7 bitmaps, 7 rgbStreams, 3 + 3 range streams) and its counters."""
+    import hashlib
+    out = []
+    for p in res["passes"]:
+        out.append(("bitmap", int(p["bitmap"].size), hashlib.sha1(p["bitmap"].tobytes()).hexdigest()))
+        out.append(("rgb", int(p["rgb"].size), hashlib.sha1(p["rgb"].tobytes()).hexdigest()))
+    for q in res["r2"]:
+        out.append(("idx", int(q["idx"].size), hashlib.sha1(q["idx"].tobytes()).hexdigest()))
+        out.append(("type", int(q["type"].size), hashlib.sha1(q["type"].tobytes()).hexdigest()))
+    return out, [(p["tiledone"], list(p["bbox"])) for p in res["passes"]]
+
+
+def run_strips(args, torch, dist, lib, rank, world, local, steps, warmup):
+    """One side x side RGB image (a seeded 2048x2048 texture tiled over the plane) in tile-row strips, one strip per rank /
+    GPU, int32 planes resident in HBM.  Every rank enqueues whole images on its stream (yk_strip_run): the halo exchanges
+    are NVLink peer copies into the neighbour's halo (CUDA IPC mapping) ordered by epoch flags on the device - no host
+    barrier inside the timed region, no collective on the data path.  Returns the result dictionary on rank 0."""
+    import hashlib
+    from yaik_b200 import capi, strips
+    from yaik_b200.synth import make_image, SEED_BASE
+    side = args.strips_side
+    rows = strips.strip_rows(side, world)
+    active = rank < len(rows)
+    base = make_image(2048, 2048, 3, SEED_BASE + 3)
+    reps = (side + 2047) // 2048
+
+    def rows_of(y0, sh):
+        return np.ascontiguousarray(np.tile(base, (1, reps, reps))[:, y0:y0 + sh, :side])
+
+    ctx = halo = None
+    st = torch.cuda.Stream(device=local)
+    if active:
+        y0, sh = rows[rank]
+        ctx = capi.Context(side, sh, planes=3, slots=1, device=local, lib=lib)
+        ctx.set_stream(st.cuda_stream)
+        ctx.set_upload_format(False)
+        ctx.set_image(rows_of(y0, sh), 0)
+        ctx.strip_config(side, y0)
+        halo = ctx.strip_halo()
+    peers = {}
+    if dist is not None:
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.ipc_export(halo.haloIn) if active else None)      # control plane only
+        for r in (rank - 1, rank + 1):
+            if active and 0 <= r < len(rows):
+                peers[r] = ctx.ipc_open(handles[r])
+        dist.barrier()                                   # every halo is cleared before a neighbour writes into it
+    if active:
+        ctx.strip_set_peers(peers.get(rank - 1), peers.get(rank + 1))
+
+    def barrier():
+        torch.cuda.synchronize(local)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(local)
+
+    for _ in range(max(3, warmup)):
+        if active:
+            ctx.strip_run()
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.sample(); sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(st)
+    for _ in range(steps):
+        if active:
+            ctx.strip_run()
+    ev1.record(st)
+    barrier()
+    sampler.stop_flag = True; sampler.sample()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # ---- parity: the strips' streams against one context analysing the whole image (rank 0's GPU), compared through
+    # lengths + SHA-1 per stream per strip (the merged streams are the strips' streams one after the other)
+    mine = _stream_digests(strips.collect_results(ctx)) if active else None
+    parts = [mine]
+    if dist is not None:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    result = None
+    if rank == 0:
+        whole = capi.Context(side, side, planes=3, slots=1, device=local, lib=lib)
+        whole.set_upload_format(False)
+        whole.set_image(rows_of(0, side), 0)
+        whole.analyze(capi.STAGE_GRADIENT | capi.STAGE_RANGE1D)
+        ref = strips.collect_results(whole)
+        whole.close()
+        streams = []
+        for p in ref["passes"]:
+            streams += [p["bitmap"], p["rgb"]]
+        for q in ref["r2"]:
+            streams += [q["idx"], q["type"]]
+        offs = [0] * len(streams)
+        ok = True
+        for part in parts[:len(rows)]:
+            for k, (kind, n, sha) in enumerate(part[0]):
+                seg = streams[k][offs[k]:offs[k] + n]
+                ok = ok and seg.size == n and hashlib.sha1(seg.tobytes()).hexdigest() == sha
+                offs[k] += n
+        ok = ok and all(offs[k] == streams[k].size for k in range(len(streams)))
+        for k, p in enumerate(ref["passes"]):
+            ok = ok and p["tiledone"] == sum(part[1][k][0] for part in parts[:len(rows)])
+        if not ok:
+            raise SystemExit("bench.py: the strips' streams differ from the whole-image run")
+        mp = side * side / 1e6
+        result = {"metric": METRIC, "value": round(mp * steps / (ms / 1e3), 1), "unit": UNIT, "n_gpus": world, "steps": steps, "ms_per_image": round(ms / steps, 4),
+                  "workload": f"one {side}x{side} synthetic RGB image in {len(rows)} tile-row strips, one GPU each (BASELINE.json configs[3])",
+                  "scaling": "strong", "halo_bytes_per_boundary": int(3 * halo.planeRowBytes + 2 * halo.touchBytes),
+                  "exchange": "NVLink P2P copies into the neighbour's halo (CUDA IPC), ordered by epoch flags on the device; no host barrier in the timed region, no collective",
+                  "parity_checked": True, "parity_against": "one context analysing the whole image (itself compared with the oracle at 4096x16384 in tests/)",
+                  "clocks": sampler.result()}
+    if active:
+        for ptr in peers.values():
+            ctx.ipc_close(ptr)
+        ctx.close()
+    return result
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -210,6 +333,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=384)
     ap.add_argument("--e2e-threads", type=int, default=8, help="host threads (one context each) the end-to-end steps are pipelined over")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="batch", choices=["batch", "strips"],
+                    help="batch: configs[1] textures sharded by image (the metric's configuration); strips: one 16384x16384 RGB image in tile-row strips over the ranks (configs[3])")
+    ap.add_argument("--strips-side", type=int, default=16384)
+    ap.add_argument("--no-strips", action="store_true", help="N > 1, batch workload: skip the strips sub-measurement echoed in the line")
     ap.add_argument("--no-r1", action="store_true", help="skip the second timed region (the step with DynamicTileEncode behind it)")
     ap.add_argument("--no-other", action="store_true", help="skip the informational timing of the stages outside the metric")
     ap.add_argument("--streams", type=int, default=8, help="contexts/streams the steps are pipelined over (1, 2, 4 or 8)")
@@ -236,6 +363,15 @@ def main():
     torch.cuda.set_device(local)
 
     lib = capi.load_library()          # fails loudly if the CUDA library is missing: there is no fallback
+    if args.workload == "strips":
+        res = run_strips(args, torch, dist, lib, rank, world, local, max(1, args.steps), args.warmup)
+        if rank == 0:
+            line = dict(res, warmup=args.warmup, higher_is_better=True, vs_baseline=None, dtype="int32", data="synthetic",
+                        config={"workload": res["workload"]})
+            print(json.dumps(line), flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     # Textures are independent, so consecutive steps are pipelined over NCTX contexts (one CUDA stream each): while
     # one texture is in its emission / range kernels the next one's analysis kernel already runs.
     NCTX = max(1, args.streams)
@@ -560,6 +696,15 @@ def main():
                          "colour plane; yk_k_chroma (RGB -> YCoCg + half-width Co / Cg) and yk_k_r1_encode averaged over Y, Co, Cg. Not in `value`."}
         c.close()
 
+    # ---- N > 1: the other way the path shards (configs[3]): one large image in tile-row strips over the same ranks
+    strips_res = None
+    if world > 1 and not args.no_strips:
+        for c in ctxs:
+            c.close()
+        ctxs = []
+        torch.cuda.empty_cache()
+        strips_res = run_strips(args, torch, dist, lib, rank, world, local, 10, 3)
+
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -570,7 +715,7 @@ def main():
                         "region_ms": [round(x, 4) for x in region_ms]},
                 "parity_checked": parity_checked,
                 "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "with_r1": with_r1, "stages_outside_metric": other}
+                "with_r1": with_r1, "strips": strips_res, "stages_outside_metric": other}
         print(json.dumps(line), flush=True)
     for c in ctxs:
         c.close()

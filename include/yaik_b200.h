@@ -226,6 +226,26 @@ typedef struct yk_strip_halo {
 int  yk_strip_config(yk_ctx* ctx, int slot, int imgH, int y0);
 int  yk_strip_halo_ptrs(yk_ctx* ctx, int slot, yk_strip_halo* out);
 int  yk_strip_phase(yk_ctx* ctx, int slot, int phase, int rejectFactor);  /* 0 = accept phase, 1 = emission phase */
+/* The same protocol without the host in the loop: after yk_strip_config on every strip (and one host barrier, so that
+ * every halo is cleared before a neighbour writes into it) each strip is told where its neighbours' halo allocations
+ * are mapped in this process (their haloIn, direct or through yk_ipc_open; NULL where there is no neighbour), and
+ * yk_strip_run then enqueues a whole image on the strip's stream: reset, exchange 1, phase 0, exchange 2, phase 1.
+ * The exchanges are peer copies followed by a one-thread kernel that publishes an epoch number in the neighbour's halo;
+ * a one-thread kernel on the receiving stream waits for it, and a strip does not start the next image before both
+ * neighbours have finished the current one.  Images can be enqueued back to back; the planes must stay what
+ * yk_set_image / yk_set_image_device made them. */
+int  yk_strip_set_peers(yk_ctx* ctx, int slot, void* aboveHalo, void* belowHalo);
+int  yk_strip_run(yk_ctx* ctx, int slot, int rejectFactor);
+/* All strips of an image driven by one process (ctxs[k] = strip k, top to bottom, on one or several GPUs): link every
+ * strip to its neighbours (peer access is enabled between their devices), enqueue one image on every strip. */
+int  yk_strips_link(yk_ctx* const* ctxs, int n, int slot);
+int  yk_strips_run(yk_ctx* const* ctxs, int n, int slot, int rejectFactor);
+/* Alpha stage of a strip set (yk_alpha_reject serves whole images): the per-16x16-tile "has a non-zero alpha sample" bytes of
+ * one strip ([tilesH][tilesW], row-major) with the box of its kept tiles in image coordinates, and the assembly of
+ * MipPrefilter's results (EC.cpp:1287-1403) from the strips' arrays one after the other and the merged box: host code. */
+int  yk_alpha_kept(yk_ctx* ctx, int slot, uint8_t* kept, int keptCap, int* tilesW, int* tilesH, int boundPx[4], int* keptTiles);
+int  yk_alpha_assemble(const uint8_t* kept, int tilesW, int tilesH, int w, int h, const int boundPx[4],
+                       uint8_t* bitmap, int bitmapCap, int* bitmapBytes, int* remainingPixels, int* wroteChunk, int chunkBBoxTiles[4]);
 
 /* Plumbing for the exchanges: CUDA IPC handle of a device allocation (64 bytes, to be sent to the neighbour's
  * process by any host channel), mapping it in this process, and an asynchronous device-to-device copy on the

@@ -80,6 +80,7 @@ template <class F> inline unsigned long long collect(unsigned long long mine, F 
 static inline void __syncthreads() { yk_emu::g_cta->bar->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { yk_emu::warp().bar->arrive_and_wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 static inline void yk_emu_fullmask(unsigned m) { if (m != 0xffffffffu) { fprintf(stderr, "yk_emu: partial warp mask %08x\n", m); abort(); } }

@@ -7,6 +7,13 @@ from parity import _eq
 
 def check_against_oracle(merged, planes, r2=True):
     o = Oracle(planes)
+    if planes.shape[0] == 4 and merged.get("alpha") is not None:     # the alpha stage of the strip set (merged on the host)
+        want = o.alpha()
+        got = merged["alpha"]
+        if want is not None:
+            assert got["bound"] == want["bound"] and got["remaining"] == want["remaining"] and got["wrote"] == want["wrote"]
+            assert got["chunk_bbox"] == want["chunk_bbox"]
+            _eq(got["bitmap"], want["bitmap"], "alpha bitmap of the strip set")
     for k, (sx, sy) in enumerate(PASS_ORDER):
         want = o.gradient_pass(sx, sy)
         got = merged["passes"][k]

@@ -361,6 +361,22 @@ def test_strips_on_one_gpu_match_whole_image(lib, w, h, n):
             c.close()
 
 
+@pytest.mark.parametrize("w,h,n,ch", [(256, 512, 2, 3), (512, 512, 4, 4), (2048, 1024, 4, 3), (192, 328, 3, 3)])
+def test_strips_without_the_host_in_the_loop(lib, w, h, n, ch):
+    """yk_strips_link / yk_strips_run: every strip enqueues whole images on its stream, the halo exchanges are ordered by
+    epoch flags in (peer-mapped) halo memory; three images back to back, the last one's streams against the oracle."""
+    from strips_check import check_against_oracle
+    from yaik_b200 import strips
+    planes = make_image(w, h, ch, SEED_BASE + 3) if w >= 512 else cases._patchy(w, h, 43, 4, 3)
+    ctxs = [capi.Context(w, h, planes=ch, slots=1, lib=lib) for _ in range(n)]
+    try:
+        merged = strips.LocalTransport(ctxs).run_device_flags(planes, n_strips=n, images=3)
+        check_against_oracle(merged, planes)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_strips_4096x16384_match_oracle(lib):
     """configs[3] at a quarter of its width and its full height (67 Mpixel RGB, 4 strips of 4096 rows): the merged streams
     against the oracle on the whole image."""

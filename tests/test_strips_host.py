@@ -51,6 +51,25 @@ def test_strips_local_transport_matches_whole_image(emu_lib, name, w, h, n):
             c.close()
 
 
+@pytest.mark.parametrize("w,h,n,seed", [(128, 128, 2, 16), (256, 256, 4, 12), (128, 256, 3, 19)])
+def test_strips_rgba_alpha_stage_of_the_strip_set(emu_lib, w, h, n, seed):
+    """RGBA image in strips: the alpha-zero tile rejection of the strips merges into the image's bitmap / bound / remaining
+    pixels (pow2 squares are the reference's domain; the rectangle checks the gradient / range streams only)."""
+    from yaik_b200.synth import make_image, SEED_BASE
+    planes = make_image(w, h, 4, SEED_BASE + seed)
+    ctxs = [capi.Context(w, h, planes=4, slots=1, lib=emu_lib) for _ in range(n)]
+    try:
+        merged = strips.LocalTransport(ctxs).run(planes, n_strips=n)
+        if w == h:
+            check_against_oracle(merged, planes)
+        else:
+            check_against_oracle(dict(merged, alpha=None), planes[:3])
+            assert merged["alpha"] is not None
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 @pytest.mark.parametrize("i", range(6))
 def test_strips_random_shapes(emu_lib, i):
     """Random widths (any multiple of 8, odd region counts included), heights and strip counts, both upload formats."""

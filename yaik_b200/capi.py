@@ -25,7 +25,7 @@ EXPORTS = [
     "yk_device_plane", "yk_reset_state", "yk_reset_states", "yk_analyze", "yk_alpha_reject", "yk_prepare_quad_smooth",
     "yk_gradient_pass", "yk_range1d", "yk_range_dyn", "yk_chroma_prepare", "yk_chroma_plane", "yk_range_dyn_chroma", "yk_download_state", "yk_fetch_all", "yk_result_bytes", "yk_launch_count",
     "yk_profile", "yk_profile_read",
-    "yk_strip_config", "yk_strip_halo_ptrs", "yk_strip_phase",
+    "yk_strip_config", "yk_strip_halo_ptrs", "yk_strip_phase", "yk_strip_set_peers", "yk_strip_run", "yk_strips_link", "yk_strips_run", "yk_alpha_kept", "yk_alpha_assemble",
     "yk_ipc_export", "yk_ipc_open", "yk_ipc_close", "yk_copy_async", "yk_copy_to_host", "yk_copy_from_host",
     "yk_palette_create", "yk_palette_destroy", "yk_palette_reset", "yk_palette_compress",
     "yk_chunk_file_header", "yk_chunk_mipm", "yk_chunk_gtil", "yk_chunk_1dtl", "yk_chunk_plnt", "yk_chunk_end",
@@ -108,6 +108,13 @@ def load_library(path: str | None = None):
     L.yk_strip_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.yk_strip_halo_ptrs.argtypes = [C.c_void_p, C.c_int, C.POINTER(StripHalo)]
     L.yk_strip_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.yk_strip_set_peers.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.yk_strip_run.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.yk_strips_link.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
+    L.yk_strips_run.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
+    L.yk_alpha_kept.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.yk_alpha_assemble.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.yk_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
     L.yk_ipc_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
     L.yk_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
@@ -294,6 +301,22 @@ class Context:
         h = StripHalo()
         self._ck(self.L.yk_strip_halo_ptrs(self.ctx, slot, C.byref(h)), "yk_strip_halo_ptrs")
         return h
+
+    def strip_set_peers(self, above, below, slot=0):
+        self._ck(self.L.yk_strip_set_peers(self.ctx, slot, C.c_void_p(above or 0), C.c_void_p(below or 0)), "yk_strip_set_peers")
+
+    def strip_run(self, slot=0, reject=3):
+        self._ck(self.L.yk_strip_run(self.ctx, slot, reject), "yk_strip_run")
+
+    def alpha_kept(self, slot=0):
+        """Per-tile alpha results of one strip (or image): kept bytes [th][tw], box of the kept tiles in image coordinates."""
+        c, h, w = self.dims[slot]
+        tw, th = (w + 15) // 16, (h + 15) // 16
+        kept = np.zeros(tw * th, np.uint8)
+        a, b, n = C.c_int(), C.c_int(), C.c_int()
+        bound = (C.c_int * 4)()
+        self._ck(self.L.yk_alpha_kept(self.ctx, slot, _p(kept), kept.size, C.byref(a), C.byref(b), bound, C.byref(n)), "yk_alpha_kept")
+        return dict(kept=kept.reshape(th, tw), bound=list(bound), count=n.value)
 
     def strip_phase(self, phase, slot=0, reject=3):
         self._ck(self.L.yk_strip_phase(self.ctx, slot, phase, reject), "yk_strip_phase")

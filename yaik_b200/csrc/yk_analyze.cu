@@ -1012,3 +1012,16 @@ void yk_launch_expand(const YkSlotDev* slotsDev, int slot, int nPlanes, int w, i
 void yk_launch_fold_touch(const YkSlotDev* slotsDev, int slot0, int nSlots, int nWords, cudaStream_t st) {
     YK_LAUNCH(yk_k_fold_touch, dim3((nWords + 255) / 256, nSlots), dim3(256), 0, st, slotsDev, slot0, nWords);
 }
+
+// CUDA loads kernels lazily, and loading one synchronises the context: a kernel that waits for another stream (yk_strip_run)
+// would then never be released by a kernel that is launched for the first time.  Every kernel is loaded up front.
+int yk_preload_analyze() {
+#ifndef YK_EMULATE
+    cudaFuncAttributes fa;
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_analyze); if (e != cudaSuccess) return (int)e; }
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_analyze_u8); if (e != cudaSuccess) return (int)e; }
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_expand); if (e != cudaSuccess) return (int)e; }
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_fold_touch); if (e != cudaSuccess) return (int)e; }
+#endif
+    return 0;
+}

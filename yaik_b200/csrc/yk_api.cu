@@ -77,6 +77,9 @@ struct YkSlotHost {
     std::vector<void*> devAllocs;        // every device allocation of the slot (freed by yk_destroy)
     // strip mode: one allocation [3 * w int32 pixel row][latW touch words from above][latW touch words from below]
     uint8_t* haloIn = nullptr; size_t haloBytes = 0;
+    size_t haloFlagsOffset = 0;  // five u32 epoch flags written by the neighbours: see yk_strip_run
+    void* peerAbove = nullptr; void* peerBelow = nullptr;     // the neighbours' halo allocations as mapped in this process
+    unsigned stripEpoch = 0;
 };
 
 struct yk_ctx {
@@ -220,6 +223,8 @@ static int create_fill(yk_ctx* c) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->ownStream = true;
     { const int e = yk_analyze_setup(&c->numSMs); if (e) { g_lastCuda = std::string("yk_analyze_setup: ") + cudaGetErrorString((cudaError_t)e); return YK_ERR_CUDA; } }
+    { int e = yk_preload_analyze(); if (!e) e = yk_preload_emit(); if (!e) e = yk_preload_aux();
+      if (e) { g_lastCuda = std::string("kernel preload: ") + cudaGetErrorString((cudaError_t)e); return YK_ERR_CUDA; } }
     // CTAs of the persistent analysis kernel (default: one per SM).  Leaving a few SMs free lets the small ownership /
     // emission kernels of another stream run beside it when textures are pipelined over several contexts.
     c->analysisCtas = c->numSMs;
@@ -545,7 +550,7 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     CK(cudaSetDevice(c->device));
     const YkSlotHost& a = c->slots[slot0];
     const int nRegions = a.d.nbx * a.d.nby;
-    for (int i = slot0; i < slot0 + nSlots; i++)            // the header is about to be cleared: keep the previous run's numbers
+    for (int i = slot0; i < slot0 + nSlots && (phases & 1); i++)            // the header is about to be cleared: keep the previous run's numbers
         if (c->slots[i].pendingHarvest) { rc = fetch_hdr(c, c->slots[i]); if (rc && rc != YK_ERR_RANGE) return rc; }
     bool needFold = false;
     for (int i = slot0; i < slot0 + nSlots && (phases & 1); i++) {
@@ -1184,7 +1189,8 @@ extern "C" int yk_strip_config(yk_ctx* c, int slot, int imgH, int y0) {
     if (y0 + h < imgH && (h & 63)) return YK_ERR_ARG;            // only the last strip may end off the 64-row grid
     CK(cudaSetDevice(c->device));
     const size_t es = s.d.isU8 ? 1 : sizeof(int32_t), rowBytes = ((size_t)w * es + 15) / 16 * 16;
-    const size_t need = 3 * rowBytes + 2 * (size_t)s.d.latW * sizeof(uint32_t);
+    const size_t touchBytes = ((size_t)s.d.latW * sizeof(uint32_t) + 15) / 16 * 16;
+    const size_t need = 3 * rowBytes + 2 * touchBytes + 64;
     if (s.haloBytes < need) {
         if (s.haloIn) cudaFree(s.haloIn);
         s.haloIn = nullptr; s.haloBytes = 0;
@@ -1199,7 +1205,9 @@ extern "C" int yk_strip_config(yk_ctx* c, int slot, int imgH, int y0) {
     s.d.hasAbove = y0 > 0; s.d.hasBelow = y0 + h < imgH;
     for (int p = 0; p < 3; p++) s.d.rowBelow[p] = s.d.hasBelow ? (const void*)(s.haloIn + p * rowBytes) : nullptr;
     s.d.touchInTop = (const uint32_t*)(s.haloIn + 3 * rowBytes);
-    s.d.touchInBottom = s.d.touchInTop + s.d.latW;
+    s.d.touchInBottom = (const uint32_t*)(s.haloIn + 3 * rowBytes + touchBytes);
+    s.haloFlagsOffset = 3 * rowBytes + 2 * touchBytes;
+    s.stripEpoch = 0; s.peerAbove = nullptr; s.peerBelow = nullptr;
     s.dirty = true;
     return YK_OK;
 }
@@ -1215,7 +1223,7 @@ extern "C" int yk_strip_halo_ptrs(yk_ctx* c, int slot, yk_strip_halo* out) {
     out->pixelRowInOffset = 0; out->pixelRowBytes = 3 * rowBytes; out->pixelRowStride = rowBytes;
     out->touchInTopOffset = out->pixelRowBytes;
     out->touchBytes = (size_t)s.d.latW * sizeof(uint32_t);
-    out->touchInBottomOffset = out->touchInTopOffset + out->touchBytes;
+    out->touchInBottomOffset = (size_t)((const uint8_t*)s.d.touchInBottom - s.haloIn);
     for (int p = 0; p < 3; p++) out->pixelRowOut[p] = s.d.isU8 ? (const void*)s.d.planeU8[p] : (const void*)s.d.plane[p];   // first pixel row of each colour plane
     out->planeRowBytes = (size_t)w * es;
     out->touchOutTop = s.d.touchMap;                                                         // lattice row 0
@@ -1239,6 +1247,152 @@ extern "C" int yk_strip_phase(yk_ctx* c, int slot, int phase, int rejectFactor) 
     const int rc = enqueue(c, slot, 1, run, true, true, 2);
     if (rc) return rc;
     s.prepared = true; s.preparedReject = rejectFactor; s.nextPass = 0;
+    return YK_OK;
+}
+
+// ---- strips without the host in the loop ----------------------------------------------------------------------------
+// Every strip enqueues the whole image on its own stream: the two exchanges are device-to-device copies into the
+// neighbours' halo allocations (peer-mapped: NVLink P2P), each followed by a one-thread kernel that publishes an epoch
+// number in the neighbour's halo; before it uses what a neighbour sends, a strip's stream runs a one-thread kernel that
+// waits for that number.  No host barrier, no collective.  Flags (u32, in the strip's own halo, written by neighbours):
+//   [0] pixel row of the strip below has landed        [1] touch words of the strip above   [2] touch words of the strip below
+//   [3] the strip above has finished the image         [4] the strip below has finished the image
+extern "C" int yk_strip_set_peers(yk_ctx* c, int slot, void* aboveHalo, void* belowHalo) {
+    if (!slot_ok(c, slot)) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage || !s.haloIn) return YK_ERR_STATE;
+    if ((s.d.hasAbove && !aboveHalo) || (s.d.hasBelow && !belowHalo)) return YK_ERR_ARG;
+    s.peerAbove = s.d.hasAbove ? aboveHalo : nullptr; s.peerBelow = s.d.hasBelow ? belowHalo : nullptr;
+    return YK_OK;
+}
+
+extern "C" int yk_strip_run(yk_ctx* c, int slot, int rejectFactor) {
+    if (!slot_ok(c, slot) || rejectFactor < 0 || rejectFactor > 64) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage || !s.haloIn) return YK_ERR_STATE;
+    if ((s.d.hasAbove && !s.peerAbove) || (s.d.hasBelow && !s.peerBelow)) return YK_ERR_STATE;
+#ifdef YK_EMULATE
+    return YK_ERR_UNSUPPORTED;      // the emulated launches run to completion one after the other: a waiting kernel would never see its flag
+#endif
+    CK(cudaSetDevice(c->device));
+    // Nothing below may make the host wait for this stream: it is about to hold kernels that wait for the neighbours,
+    // whose work the same host thread may still have to enqueue.  So the slot descriptor goes up now (a copy from
+    // pageable memory drains the stream first), and the previous image's header is not fetched (its counters are lost
+    // unless they were read before the next yk_strip_run).
+    int rc = upload_slots(c, slot, 1);
+    if (rc) return rc;
+    s.pendingHarvest = false;
+    const unsigned e = ++s.stripEpoch;
+    const size_t es = s.d.isU8 ? 1 : sizeof(int32_t), rowBytes = ((size_t)s.d.w * es + 15) / 16 * 16;
+    const size_t touchBytes = (size_t)s.d.latW * sizeof(uint32_t);
+    const size_t offTop = (size_t)((const uint8_t*)s.d.touchInTop - s.haloIn), offBottom = (size_t)((const uint8_t*)s.d.touchInBottom - s.haloIn);
+    unsigned* mine = (unsigned*)(s.haloIn + s.haloFlagsOffset);
+    unsigned* above = s.peerAbove ? (unsigned*)((uint8_t*)s.peerAbove + s.haloFlagsOffset) : nullptr;     // same layout: same width and sample type
+    unsigned* below = s.peerBelow ? (unsigned*)((uint8_t*)s.peerBelow + s.haloFlagsOffset) : nullptr;
+    // the neighbours have finished the previous image: their halos may be overwritten, and they have read what we sent
+    if (e > 1 && (above || below)) { yk_launch_flag_wait(above ? mine + 3 : nullptr, below ? mine + 4 : nullptr, e - 1, c->stream); c->launches++; }
+    if ((rc = yk_reset_state(c, slot))) return rc;
+    // exchange 1: my first pixel row -> halo of the strip above
+    if (above) {
+        for (int p = 0; p < 3; p++) {
+            const void* src = s.d.isU8 ? (const void*)s.d.planeU8[p] : (const void*)s.d.plane[p];
+            CK(cudaMemcpyAsync((uint8_t*)s.peerAbove + p * rowBytes, src, (size_t)s.d.w * es, cudaMemcpyDefault, c->stream));
+        }
+        yk_launch_flag_set(above + 0, nullptr, e, c->stream); c->launches++;
+    }
+    if (below) { yk_launch_flag_wait(mine + 0, nullptr, e, c->stream); c->launches++; }
+    if ((rc = yk_strip_phase(c, slot, 0, rejectFactor))) return rc;
+    // exchange 2: boundary touch words, both directions
+    if (above) CK(cudaMemcpyAsync((uint8_t*)s.peerAbove + offBottom, s.d.touchMap, touchBytes, cudaMemcpyDefault, c->stream));
+    if (below) CK(cudaMemcpyAsync((uint8_t*)s.peerBelow + offTop, s.d.touchMap + (size_t)(s.d.latH - 1) * s.d.latW, touchBytes, cudaMemcpyDefault, c->stream));
+    if (above || below) { yk_launch_flag_set(above ? above + 2 : nullptr, below ? below + 1 : nullptr, e, c->stream); c->launches++; }
+    if (above || below) { yk_launch_flag_wait(above ? mine + 1 : nullptr, below ? mine + 2 : nullptr, e, c->stream); c->launches++; }
+    if ((rc = yk_strip_phase(c, slot, 1, rejectFactor))) return rc;
+    if (above || below) { yk_launch_flag_set(above ? above + 4 : nullptr, below ? below + 3 : nullptr, e, c->stream); c->launches++; }
+    CK(cudaGetLastError());
+    return YK_OK;
+}
+
+// all strips of an image driven by this process (one context per strip, on one or several GPUs): link every strip to its
+// neighbours' halo allocations directly, then enqueue an image on every strip
+extern "C" int yk_strips_link(yk_ctx* const* ctxs, int n, int slot) {
+    if (!ctxs || n < 1) return YK_ERR_ARG;
+    for (int k = 0; k < n; k++) if (!slot_ok(ctxs[k], slot) || !ctxs[k]->slots[slot].haloIn) return YK_ERR_STATE;
+#ifndef YK_EMULATE
+    for (int k = 0; k + 1 < n; k++) {
+        const int a = ctxs[k]->device, b = ctxs[k + 1]->device;
+        if (a == b) continue;
+        int ok1 = 0, ok2 = 0;
+        CK(cudaDeviceCanAccessPeer(&ok1, a, b)); CK(cudaDeviceCanAccessPeer(&ok2, b, a));
+        if (!ok1 || !ok2) return YK_ERR_UNSUPPORTED;
+        cudaError_t e;
+        CK(cudaSetDevice(a)); e = cudaDeviceEnablePeerAccess(b, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e); cudaGetLastError();
+        CK(cudaSetDevice(b)); e = cudaDeviceEnablePeerAccess(a, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e); cudaGetLastError();
+    }
+#endif
+    for (int k = 0; k < n; k++) {
+        const int rc = yk_strip_set_peers(ctxs[k], slot, k > 0 ? ctxs[k - 1]->slots[slot].haloIn : nullptr, k + 1 < n ? ctxs[k + 1]->slots[slot].haloIn : nullptr);
+        if (rc) return rc;
+    }
+    return YK_OK;
+}
+extern "C" int yk_strips_run(yk_ctx* const* ctxs, int n, int slot, int rejectFactor) {
+    if (!ctxs || n < 1) return YK_ERR_ARG;
+    for (int k = 0; k < n; k++) { const int rc = yk_strip_run(ctxs[k], slot, rejectFactor); if (rc) return rc; }
+    return YK_OK;
+}
+
+// ---- alpha stage of a strip set: the per-tile results of one strip, and their assembly (host code) ------------------
+extern "C" int yk_alpha_kept(yk_ctx* c, int slot, uint8_t* kept, int keptCap, int* tilesW, int* tilesH, int boundPx[4], int* keptTiles) {
+    if (!slot_ok(c, slot)) return YK_ERR_ARG;
+    YkSlotHost& s = c->slots[slot];
+    if (!s.haveImage || !s.alphaRan || s.d.nPlanes != 4) return YK_ERR_STATE;
+    CK(cudaSetDevice(c->device));
+    int rc = fetch_hdr(c, s);
+    if (rc) return rc;
+    const int tw = (s.d.w + 15) / 16, th = (s.d.h + 15) / 16;
+    if (tilesW) *tilesW = tw;
+    if (tilesH) *tilesH = th;
+    if (keptTiles) *keptTiles = s.hdr[YK_HD_ALPHA_KEPT0];
+    if (boundPx) {
+        if (s.hdr[YK_HD_ALPHA_KEPT0]) {
+            boundPx[0] = s.d.w - s.hdr[YK_HD_ALPHA_MINX]; boundPx[1] = INT_MAX / 2 - s.hdr[YK_HD_ALPHA_MINY];
+            boundPx[2] = s.hdr[YK_HD_ALPHA_MAXX]; boundPx[3] = s.hdr[YK_HD_ALPHA_MAXY];
+        } else { boundPx[0] = boundPx[1] = boundPx[2] = boundPx[3] = 0; }
+    }
+    if (kept) {
+        if (keptCap < tw * th) return YK_ERR_CAPACITY;
+        CK(cudaMemcpyAsync(kept, s.d.alphaKept, (size_t)tw * th, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return YK_OK;
+}
+
+// MipPrefilter's results (EC.cpp:1287-1403) from the per-tile "kept" bytes of a whole image ([tilesH][tilesW], e.g. the
+// strips' arrays one after the other) and the bound box of the kept tiles: bitmap over the box, remaining pixels, chunk box
+extern "C" int yk_alpha_assemble(const uint8_t* kept, int tilesW, int tilesH, int w, int h, const int boundPx[4],
+                                 uint8_t* bitmap, int bitmapCap, int* bitmapBytes, int* remainingPixels, int* wroteChunk, int chunkBBoxTiles[4]) {
+    if (!kept || !boundPx || tilesW < 1 || tilesH < 1 || !bitmapBytes) return YK_ERR_ARG;
+    const int L = boundPx[0], T = boundPx[1], R = boundPx[2], B = boundPx[3];
+    *bitmapBytes = 0;
+    if (L == 0 && T == 0 && R == w && B == h) {                    // EC.cpp:1400-1403: the rejection is discarded
+        if (remainingPixels) *remainingPixels = R * B;
+        if (wroteChunk) *wroteChunk = 0;
+        return YK_OK;
+    }
+    const int bx0 = L >> 4, bx1 = (R + 15) >> 4, by0 = T >> 4, by1 = (B + 15) >> 4;
+    const int tWB = bx1 - bx0, tHB = by1 - by0, nb = (tWB * tHB + 7) / 8;
+    if (tWB <= 0 || tHB <= 0 || bx1 > tilesW || by1 > tilesH) return YK_ERR_ARG;
+    if (nb > bitmapCap || !bitmap) return YK_ERR_CAPACITY;
+    memset(bitmap, 0, (size_t)nb);
+    int bit = 0, rem = 0;
+    for (int y = 0; y < tHB; y++)
+        for (int x = 0; x < tWB; x++, bit++)
+            if (kept[(size_t)(y + by0) * tilesW + x + bx0]) { bitmap[bit >> 3] |= (uint8_t)(1 << (bit & 7)); rem += 256; }   // EC.cpp:1317-1327
+    *bitmapBytes = nb;
+    if (remainingPixels) *remainingPixels = rem;
+    if (wroteChunk) *wroteChunk = 1;
+    if (chunkBBoxTiles) { chunkBBoxTiles[0] = bx0; chunkBBoxTiles[1] = by0; chunkBBoxTiles[2] = tWB; chunkBBoxTiles[3] = tHB; }
     return YK_OK;
 }
 

@@ -184,3 +184,31 @@ void yk_launch_owner(const YkSlotDev* slotsDev, int slot0, int nSlots, int nPoin
 void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int gradGroups, int r2Groups, const YkRun& run, cudaStream_t st) {
     YK_LAUNCH(yk_k_emit, dim3(gradGroups + r2Groups, nSlots), dim3(YK_EMIT_THREADS), 0, st, slotsDev, slot0, run, gradGroups, r2Groups);
 }
+
+// Strips (yk_strip_run): epoch flags in halo memory.  The setter runs after the copies it announces (stream order) and
+// makes them visible system-wide before the flag; the waiter spins on its own GPU's memory.
+__global__ void yk_k_flag_set(unsigned* a, unsigned* b, unsigned value) {
+    __threadfence_system();
+    if (a) yk_stv(a, value);
+    if (b) yk_stv(b, value);
+}
+__global__ void yk_k_flag_wait(const unsigned* a, const unsigned* b, unsigned value) {
+    while (a && (int)(yk_ldv(a) - value) < 0) yk_spin();
+    while (b && (int)(yk_ldv(b) - value) < 0) yk_spin();
+    __threadfence_system();
+}
+void yk_launch_flag_set(unsigned* a, unsigned* b, unsigned value, cudaStream_t st) { YK_LAUNCH(yk_k_flag_set, dim3(1), dim3(1), 0, st, a, b, value); }
+void yk_launch_flag_wait(const unsigned* a, const unsigned* b, unsigned value, cudaStream_t st) { YK_LAUNCH(yk_k_flag_wait, dim3(1), dim3(1), 0, st, a, b, value); }
+
+// CUDA loads kernels lazily, and loading one synchronises the context: a kernel that waits for another stream (yk_strip_run)
+// would then never be released by a kernel that is launched for the first time.  Every kernel is loaded up front.
+int yk_preload_emit() {
+#ifndef YK_EMULATE
+    cudaFuncAttributes fa;
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_owner); if (e != cudaSuccess) return (int)e; }
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_emit); if (e != cudaSuccess) return (int)e; }
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_flag_set); if (e != cudaSuccess) return (int)e; }
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_flag_wait); if (e != cudaSuccess) return (int)e; }
+#endif
+    return 0;
+}

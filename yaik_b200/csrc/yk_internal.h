@@ -100,10 +100,16 @@ struct YkRun {
 extern "C++" {
 #endif
 // launch wrappers (yk_kernels.cu); `slots` is a device array, grid.y indexes it from slot0
-int  yk_analyze_setup(int* numSMs);      // opt-in shared memory of the persistent kernel; returns a cudaError_t
+int  yk_analyze_setup(int* numSMs);
+int  yk_preload_analyze();              // force-load every kernel of a translation unit (see yk_analyze.cu); return a cudaError_t
+int  yk_preload_emit();
+int  yk_preload_aux();      // opt-in shared memory of the persistent kernel; returns a cudaError_t
 void yk_launch_analyze(const YkSlotDev* slotsDev, int slot0, int nSlots, int nRegions, int gridCtas, bool packedU8, const YkRun& run, cudaStream_t st);   // nRegions: of one image (nbx * nby)
 void yk_launch_expand(const YkSlotDev* slotsDev, int slot, int nPlanes, int w, int h, int32_t* const* dst, cudaStream_t st);
 void yk_launch_fold_touch(const YkSlotDev* slotsDev, int slot0, int nSlots, int nWords, cudaStream_t st);
+// one-thread kernels on a strip's stream: publish / wait for an epoch number in (peer-mapped) halo memory
+void yk_launch_flag_set(unsigned* a, unsigned* b, unsigned value, cudaStream_t st);
+void yk_launch_flag_wait(const unsigned* a, const unsigned* b, unsigned value, cudaStream_t st);
 void yk_launch_owner(const YkSlotDev* slotsDev, int slot0, int nSlots, int nPoints, const YkRun& run, cudaStream_t st);
 void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int gradGroups, int r2Groups, const YkRun& run, cudaStream_t st);
 void yk_launch_state(const YkSlotDev* slotsDev, int slot, int nRegions, int32_t* smoothMap, int32_t* mipmapMask,

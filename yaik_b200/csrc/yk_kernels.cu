@@ -597,3 +597,16 @@ void yk_launch_chroma(const YkSlotDev* slotsDev, int slot, int w, int h, const Y
     const int quads = (w >> 1) * (h >> 1);
     YK_LAUNCH(yk_k_chroma, dim3((quads + 255) / 256), dim3(256), 0, st, slotsDev, slot, args);
 }
+
+// CUDA loads kernels lazily, and loading one synchronises the context: a kernel that waits for another stream (yk_strip_run)
+// would then never be released by a kernel that is launched for the first time.  Every kernel is loaded up front.
+int yk_preload_aux() {
+#ifndef YK_EMULATE
+    cudaFuncAttributes fa;
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_state); if (e != cudaSuccess) return (int)e; }
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_r1_offsets); if (e != cudaSuccess) return (int)e; }
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_r1_encode); if (e != cudaSuccess) return (int)e; }
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_chroma); if (e != cudaSuccess) return (int)e; }
+#endif
+    return 0;
+}

@@ -50,6 +50,26 @@ def collect_results(ctx: "capi.Context", slot=0, r2=True):
     return res
 
 
+def merge_alpha(lib, parts, w, h):
+    """MipPrefilter's results for the whole image from the strips' per-tile alpha results (Context.alpha_kept, strip order):
+    the arrays stack (a strip is a whole number of 16-row tiles, except the last), the boxes merge, the bitmap / remaining
+    pixels / chunk box come from yk_alpha_assemble (EC.cpp:1287-1403)."""
+    kept = np.ascontiguousarray(np.concatenate([p["kept"] for p in parts], axis=0))
+    boxes = [p["bound"] for p in parts if p["count"] > 0]
+    if not boxes:
+        return None                                  # fully transparent: outside the reference's domain
+    bound = [min(b[0] for b in boxes), min(b[1] for b in boxes), max(b[2] for b in boxes), max(b[3] for b in boxes)]
+    th, tw = kept.shape
+    bm = np.zeros(tw * th // 8 + 8, np.uint8)
+    nb, rem, wrote = C.c_int(), C.c_int(), C.c_int()
+    cb = (C.c_int * 4)()
+    rc = lib.yk_alpha_assemble(kept.ctypes.data_as(C.c_void_p), tw, th, w, h, (C.c_int * 4)(*bound), bm.ctypes.data_as(C.c_void_p), bm.size,
+                               C.byref(nb), C.byref(rem), C.byref(wrote), cb)
+    if rc:
+        raise capi.YaikError(rc, "yk_alpha_assemble")
+    return dict(bitmap=bm[:nb.value].copy(), bound=bound, remaining=rem.value, wrote=wrote.value, chunk_bbox=list(cb) if wrote.value else [])
+
+
 def merge_results(parts):
     """Image-level streams from the strips' (in strip order): what one context would have returned for the whole image."""
     out = {"passes": [], "r2": []}
@@ -72,6 +92,32 @@ class LocalTransport:
 
     def __init__(self, ctxs):
         self.ctxs = ctxs
+
+    def run_device_flags(self, planes: np.ndarray, n_strips=None, reject=3, r2=True, images=1):
+        """The form without the host in the loop (yk_strips_link / yk_strips_run): every strip enqueues the whole image on
+        its stream, the exchanges are ordered by epoch flags in the halos.  `images` > 1 runs the image that many times
+        back to back (the last run's results are collected)."""
+        c, h, w = planes.shape
+        rows = strip_rows(h, n_strips or len(self.ctxs))
+        ctxs = self.ctxs[:len(rows)]
+        for ctx, (y0, sh) in zip(ctxs, rows):
+            ctx.set_image(planes[:, y0:y0 + sh], 0)
+            ctx.strip_config(h, y0)
+        L = ctxs[0].L
+        arr = (C.c_void_p * len(ctxs))(*[ctx.ctx for ctx in ctxs])
+        rc = L.yk_strips_link(arr, len(ctxs), 0)
+        if rc:
+            raise capi.YaikError(rc, "yk_strips_link")
+        for _ in range(images):
+            rc = L.yk_strips_run(arr, len(ctxs), 0, reject)
+            if rc:
+                raise capi.YaikError(rc, "yk_strips_run")
+        for ctx in ctxs:
+            ctx.sync()
+        merged = merge_results([collect_results(ctx, r2=r2) for ctx in ctxs])
+        if c == 4:
+            merged["alpha"] = merge_alpha(L, [ctx.alpha_kept() for ctx in ctxs], w, h)
+        return merged
 
     def run(self, planes: np.ndarray, n_strips=None, reject=3, r2=True):
         c, h, w = planes.shape
@@ -102,7 +148,10 @@ class LocalTransport:
             ctx.sync()
         for ctx in ctxs:
             ctx.strip_phase(1, reject=reject)
-        return merge_results([collect_results(ctx, r2=r2) for ctx in ctxs])
+        merged = merge_results([collect_results(ctx, r2=r2) for ctx in ctxs])
+        if c == 4:
+            merged["alpha"] = merge_alpha(ctxs[0].L, [ctx.alpha_kept() for ctx in ctxs], w, h)
+        return merged
 
 
 class DistTransport:
