@@ -611,8 +611,19 @@ def main():
         nbytes = W * H * 4
         nthr = max(1, args.e2e_threads)
         per = max(1, args.e2e_steps // nthr)
-        # host threads that pack the Plane samples: share the box's cores between the ranks and their worker threads
-        os.environ.setdefault("YK_PACK_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // max(1, world * nthr) + 1))))
+        # the ranks of a box share its host cores: every rank keeps to its own set, so that one rank's packing threads do
+        # not migrate over another's
+        cores = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 8))
+        if world > 1 and len(cores) >= world:
+            share = len(cores) // world
+            mine_cores = cores[local * share:(local + 1) * share]
+            try:
+                os.sched_setaffinity(0, mine_cores)
+                cores = mine_cores
+            except OSError:
+                pass
+        # host threads that pack the Plane samples: this rank's cores over its worker threads
+        os.environ.setdefault("YK_PACK_THREADS", str(max(1, min(8, len(cores) // nthr + 1))))
         ectx = [capi.Context(W, H, planes=CH, slots=1, device=local, lib=lib) for _ in range(nthr)]
         hps = []
         for t in range(nthr):
@@ -633,26 +644,56 @@ def main():
             for _ in range(n):
                 e2e_step(t)
 
-        for t in range(nthr):
-            worker(t, 2)
+        def run_threads(n_each):
+            t0 = time.perf_counter()
+            ths = [threading.Thread(target=worker, args=(t, n_each)) for t in range(nthr)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            torch.cuda.synchronize(local)
+            return time.perf_counter() - t0
+
+        def set_mix(n_int32):
+            """n_int32 of the worker threads upload the int32 planes as they are (plain pinned DMA, 16 B/pixel over PCIe, no
+            host work); the others pack to bytes on the host first (4 B/pixel over PCIe, host-memory-bound)."""
+            for t, c in enumerate(ectx):
+                c.set_upload_format(t >= n_int32)
+
+        # The upload format is chosen from measured throughput on this box, with all ranks running (they share the host):
+        # packing wins while there are cores to pack with, the plain DMA wins when a box's cores are spread over many GPUs,
+        # and a mix uses the cores and the PCIe link at the same time.
+        calib = {}
+        for n_int32 in sorted({0, max(1, nthr // 4), nthr // 2, nthr}):
+            set_mix(n_int32)
+            run_threads(1)
+            barrier()
+            dt_c = run_threads(3)
+            if dist is not None:
+                tc = torch.tensor([dt_c], device=f"cuda:{local}", dtype=torch.float64)
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+                dt_c = float(tc.item())
+            calib[n_int32] = world * mp_per_step * 3 * nthr / dt_c
+            barrier()
+        best = max(calib, key=calib.get)
+        set_mix(best)
+        run_threads(1)
         barrier()
-        t0 = time.perf_counter()
-        ths = [threading.Thread(target=worker, args=(t, per)) for t in range(nthr)]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        torch.cuda.synchronize(local)
-        dt = time.perf_counter() - t0
+        dt = run_threads(per)
         if dist is not None:
             t = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         pitch = (W + 15) // 16 * 16
-        e2e = {"value": round(world * mp_per_step * per * nthr / dt, 2), "unit": UNIT, "h2d_bytes_per_step": CH * pitch * H,
+        h2d = (best * CH * W * H * 4 + (nthr - best) * CH * pitch * H) // nthr
+        e2e = {"value": round(world * mp_per_step * per * nthr / dt, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(moved[0]), "steps": per * nthr, "host_threads": nthr,
-               "what": "per step: yk_set_image from pinned host int32 planes (64 MiB, packed to bytes by host threads, 16 MiB over PCIe) "
-                       "+ yk_analyze + yk_fetch_all (all result streams to pinned host memory); wall clock. The reference's host tails "
+               "upload": f"{nthr - best} of {nthr} worker threads pack the int32 planes to bytes on the host (4 B/pixel over PCIe), {best} upload them as they are (16 B/pixel, pinned DMA)",
+               "upload_calibration_mp_s": {f"{k}_int32_threads": round(v, 1) for k, v in sorted(calib.items())},
+               "host_cores_per_rank": len(cores),
+               "bound": ("host memory bandwidth / cores (packing)" if best == 0 else ("PCIe (int32 DMA)" if best == nthr else "host packing and PCIe together")),
+               "what": "per step: yk_set_image from pinned host int32 planes (64 MiB) + yk_analyze + yk_fetch_all (all result streams to pinned "
+                       "host memory); wall clock, steps pipelined over host threads with one context each. The reference's host tails "
                        "(PaletteCompressor + ZSTD-18 inside FittingQuadSmooth, about 3 % of the CPU arm's time) are not part of this figure"}
         for c in ectx:
             c.close()

@@ -18,13 +18,21 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC,-O2,-fvisibility=default", "-shared", "-cudart", "static"]
 
 
+LAST = {"nvcc_ran": False, "seconds": 0.0}      # what the last build() call did (the driver's build check reads the printed line)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    import time
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = [os.path.join(CSRC, d) for d in DEPS]
+    force = force or os.environ.get("YK_FORCE_BUILD") == "1"
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
+        LAST.update(nvcc_ran=False, seconds=0.0)
         return OUT
     cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", OUT, *srcs]
+    t0 = time.perf_counter()
     r = subprocess.run(cmd, capture_output=True, text=True)
+    LAST.update(nvcc_ran=True, seconds=round(time.perf_counter() - t0, 1))
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
