@@ -231,26 +231,38 @@ def run_strips(args, torch, dist, lib, rank, world, local, steps, warmup):
     def rows_of(y0, sh):
         return np.ascontiguousarray(np.tile(base, (1, reps, reps))[:, y0:y0 + sh, :side])
 
-    ctx = halo = None
-    st = torch.cuda.Stream(device=local)
+    # Two strip sets per rank on the same resident planes (own contexts, streams, halos and flags): consecutive images
+    # alternate between them, so the ownership / emission kernels of one image run beside the analysis of the next.
+    NSETS = 2
+    ctxs, halos, sts = [], [], []
     if active:
         y0, sh = rows[rank]
-        ctx = capi.Context(side, sh, planes=3, slots=1, device=local, lib=lib)
-        ctx.set_stream(st.cuda_stream)
-        ctx.set_upload_format(False)
-        ctx.set_image(rows_of(y0, sh), 0)
-        ctx.strip_config(side, y0)
-        halo = ctx.strip_halo()
-    peers = {}
+        for k in range(NSETS):
+            c = capi.Context(side, sh, planes=3, slots=1, device=local, lib=lib)
+            stream_k = torch.cuda.Stream(device=local)
+            c.set_stream(stream_k.cuda_stream)
+            c.set_upload_format(False)
+            if k == 0:
+                c.set_image(rows_of(y0, sh), 0)
+                c.sync()
+            else:
+                c.set_image_device([ctxs[0].device_plane(0, p) for p in range(3)], 3, side, sh, 0)
+            c.strip_config(side, y0)
+            ctxs.append(c); halos.append(c.strip_halo()); sts.append(stream_k)
+    ctx = ctxs[0] if active else None
+    halo = halos[0] if active else None
+    st = sts[0] if active else torch.cuda.Stream(device=local)
+    peers = [dict() for _ in range(NSETS)]
     if dist is not None:
         handles = [None] * world
-        dist.all_gather_object(handles, ctx.ipc_export(halo.haloIn) if active else None)      # control plane only
-        for r in (rank - 1, rank + 1):
-            if active and 0 <= r < len(rows):
-                peers[r] = ctx.ipc_open(handles[r])
+        dist.all_gather_object(handles, [c.ipc_export(h.haloIn) for c, h in zip(ctxs, halos)] if active else None)      # control plane only
+        for k in range(NSETS):
+            for r in (rank - 1, rank + 1):
+                if active and 0 <= r < len(rows):
+                    peers[k][r] = ctxs[k].ipc_open(handles[r][k])
         dist.barrier()                                   # every halo is cleared before a neighbour writes into it
-    if active:
-        ctx.strip_set_peers(peers.get(rank - 1), peers.get(rank + 1))
+    for k in range(NSETS if active else 0):
+        ctxs[k].strip_set_peers(peers[k].get(rank - 1), peers[k].get(rank + 1))
 
     def barrier():
         torch.cuda.synchronize(local)
@@ -258,25 +270,36 @@ def run_strips(args, torch, dist, lib, rank, world, local, steps, warmup):
             dist.barrier()
         torch.cuda.synchronize(local)
 
-    for _ in range(max(3, warmup)):
-        if active:
-            ctx.strip_run()
+    def run_images(n, nsets):
+        for i in range(n):
+            if active:
+                ctxs[i % nsets].strip_run()
+
+    run_images(max(4, warmup), NSETS)
     barrier()
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.sample(); sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(st)
-    for _ in range(steps):
-        if active:
-            ctx.strip_run()
-    ev1.record(st)
-    barrier()
+
+    def timed(n, nsets):
+        ev0, ev1, j = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
+        ev0.record(st)
+        if active and nsets > 1:
+            sts[1].wait_event(ev0)
+        run_images(n, nsets)
+        if active and nsets > 1:
+            j.record(sts[1]); st.wait_event(j)
+        ev1.record(st)
+        barrier()
+        t_ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([t_ms], device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms
+
+    ms = timed(steps, NSETS)                             # throughput: images pipelined over the two sets
+    ms_single = timed(max(2, steps // 2), 1)             # one set: every image waits for the one before it
     sampler.stop_flag = True; sampler.sample()
-    ms = ev0.elapsed_time(ev1)
-    if dist is not None:
-        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     # ---- parity: the strips' streams against one context analysing the whole image (rank 0's GPU), compared through
     # lengths + SHA-1 per stream per strip (the merged streams are the strips' streams one after the other)
     mine = _stream_digests(strips.collect_results(ctx)) if active else None
@@ -311,15 +334,19 @@ def run_strips(args, torch, dist, lib, rank, world, local, steps, warmup):
             raise SystemExit("bench.py: the strips' streams differ from the whole-image run")
         mp = side * side / 1e6
         result = {"metric": METRIC, "value": round(mp * steps / (ms / 1e3), 1), "unit": UNIT, "n_gpus": world, "steps": steps, "ms_per_image": round(ms / steps, 4),
+                  "ms_per_image_unpipelined": round(ms_single / max(2, steps // 2), 4),
+                  "pipelining": "consecutive images alternate between two strip sets per GPU (same resident planes): ownership / emission of one image runs beside the analysis of the next",
                   "workload": f"one {side}x{side} synthetic RGB image in {len(rows)} tile-row strips, one GPU each (BASELINE.json configs[3])",
                   "scaling": "strong", "halo_bytes_per_boundary": int(3 * halo.planeRowBytes + 2 * halo.touchBytes),
                   "exchange": "NVLink P2P copies into the neighbour's halo (CUDA IPC), ordered by epoch flags on the device; no host barrier in the timed region, no collective",
                   "parity_checked": True, "parity_against": "one context analysing the whole image (itself compared with the oracle at 4096x16384 in tests/)",
                   "clocks": sampler.result()}
     if active:
-        for ptr in peers.values():
-            ctx.ipc_close(ptr)
-        ctx.close()
+        for k in range(NSETS):
+            for ptr in peers[k].values():
+                ctxs[k].ipc_close(ptr)
+        for c in reversed(ctxs):
+            c.close()
     return result
 
 
