@@ -105,13 +105,21 @@ template <class T> static inline T __shfl_down_sync(unsigned m, T v, unsigned d,
 template <class T> static inline T __shfl_up_sync(unsigned m, T v, unsigned d, int width = 32) {
     int l = yk_emu::t_lane & (width - 1); int src = (l - (int)d >= 0) ? l - (int)d : l; return __shfl_sync(m, v, src, width);
 }
-static inline int __reduce_min_sync(unsigned m, int v) { yk_emu_fullmask(m); return (int)(long long)yk_emu::collect((unsigned long long)(long long)v, [](unsigned long long* s) { long long r = (long long)s[0]; for (int i = 1; i < 32; i++) r = std::min(r, (long long)s[i]); return (unsigned long long)r; }); }
-static inline int __reduce_max_sync(unsigned m, int v) { yk_emu_fullmask(m); return (int)(long long)yk_emu::collect((unsigned long long)(long long)v, [](unsigned long long* s) { long long r = (long long)s[0]; for (int i = 1; i < 32; i++) r = std::max(r, (long long)s[i]); return (unsigned long long)r; }); }
-static inline unsigned __reduce_max_sync(unsigned m, unsigned v) { yk_emu_fullmask(m); return (unsigned)yk_emu::collect(v, [](unsigned long long* s) { unsigned long long r = s[0]; for (int i = 1; i < 32; i++) r = std::max(r, s[i]); return r; }); }
-static inline unsigned __reduce_min_sync(unsigned m, unsigned v) { yk_emu_fullmask(m); return (unsigned)yk_emu::collect(v, [](unsigned long long* s) { unsigned long long r = s[0]; for (int i = 1; i < 32; i++) r = std::min(r, s[i]); return r; }); }
-static inline int __reduce_add_sync(unsigned m, int v) { yk_emu_fullmask(m); return (int)(long long)yk_emu::collect((unsigned long long)(long long)v, [](unsigned long long* s) { long long r = 0; for (int i = 0; i < 32; i++) r += (long long)s[i]; return (unsigned long long)r; }); }
-static inline unsigned __reduce_add_sync(unsigned m, unsigned v) { yk_emu_fullmask(m); return (unsigned)yk_emu::collect(v, [](unsigned long long* s) { unsigned long long r = 0; for (int i = 0; i < 32; i++) r += s[i]; return r; }); }
-static inline unsigned __reduce_or_sync(unsigned m, unsigned v) { yk_emu_fullmask(m); return (unsigned)yk_emu::collect(v, [](unsigned long long* s) { unsigned long long r = 0; for (int i = 0; i < 32; i++) r |= s[i]; return r; }); }
+// reductions take a member mask: every lane of the warp reaches the call (the kernels only split a warp into its two halves,
+// each half naming itself), and a lane's result covers the lanes of its own mask
+template <class F> static inline long long yk_emu_reduce(unsigned m, long long v, F op) {
+    return (long long)yk_emu::collect((unsigned long long)v, [m, op](unsigned long long* s) {
+        bool first = true; long long r = 0;
+        for (int i = 0; i < 32; i++) if ((m >> i) & 1u) { r = first ? (long long)s[i] : op(r, (long long)s[i]); first = false; }
+        return (unsigned long long)r; });
+}
+static inline int __reduce_min_sync(unsigned m, int v) { return (int)yk_emu_reduce(m, v, [](long long a, long long b) { return std::min(a, b); }); }
+static inline int __reduce_max_sync(unsigned m, int v) { return (int)yk_emu_reduce(m, v, [](long long a, long long b) { return std::max(a, b); }); }
+static inline unsigned __reduce_max_sync(unsigned m, unsigned v) { return (unsigned)yk_emu_reduce(m, (long long)v, [](long long a, long long b) { return std::max(a, b); }); }
+static inline unsigned __reduce_min_sync(unsigned m, unsigned v) { return (unsigned)yk_emu_reduce(m, (long long)v, [](long long a, long long b) { return std::min(a, b); }); }
+static inline int __reduce_add_sync(unsigned m, int v) { return (int)yk_emu_reduce(m, v, [](long long a, long long b) { return a + b; }); }
+static inline unsigned __reduce_add_sync(unsigned m, unsigned v) { return (unsigned)yk_emu_reduce(m, (long long)v, [](long long a, long long b) { return a + b; }); }
+static inline unsigned __reduce_or_sync(unsigned m, unsigned v) { return (unsigned)yk_emu_reduce(m, (long long)v, [](long long a, long long b) { return a | b; }); }
 
 static inline unsigned __match_any_sync(unsigned m, int v) {
     yk_emu_fullmask(m);
@@ -139,6 +147,8 @@ static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __int2float_rn(int a) { return (float)a; }
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { sh &= 31u; return (unsigned)(((((unsigned long long)hi << 32) | lo) << sh) >> 32); }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { sh &= 31u; return (unsigned)((((unsigned long long)hi << 32) | lo) >> sh); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 using std::max; using std::min;
 template <class T> static inline T __ldg(const T* p) { return *p; }

@@ -12,7 +12,7 @@ ctx.set_image(img, 0)
 st = capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D
 for _ in range(3):
     ctx.reset_state(0); ctx.analyze(st); ctx.sync()
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 24)()
 lib.yk_debug_timing(out, 1)
 N = 5
 for _ in range(N):
@@ -22,3 +22,13 @@ names = {0: "prod: lookahead+free wait", 6: "prod: shfl ticket", 7: "prod: issue
          8: "cons(w0): queue+wait raw", 9: "cons(w0): pack", 11: "cons(w0):   cascade passes (incl. pretest)", 12: "cons(w0):   cells + touch + latRGB", 13: "cons(w0):   range stage", 10: "cons(w0): rest of the item (incl. raw 16x16 pass)"}
 for i, n in names.items():
     print(f"{n:34s} {out[i] / N / 148:12.0f} cycles per CTA per launch")
+
+# wall-clock shape of the launches (globaltimer, ns; low 32 bits summed, so differences of averages are exact enough over 5 launches)
+# only meaningful for the LAST launch alone: rerun one launch
+lib.yk_debug_timing(out, 1)
+ctx.reset_state(0); ctx.sync(); ctx.analyze(st); ctx.sync()
+lib.yk_debug_timing(out, 0)
+t0 = (~out[16]) & 0xFFFFFFFFFFFFFFFF
+lo = t0 & 0xFFFFFFFF
+def avg(s, n): return (s / max(n, 1)) - lo
+print(f"one launch: CTA set-up done avg {avg(out[17], out[23]) / 1e3:7.2f} us after the first CTA;  consumer warps: first item avg {avg(out[18], out[19]) / 1e3:7.2f} us, exit avg {avg(out[20], out[21]) / 1e3:7.2f} us, last exit {(out[22] - t0) / 1e3:7.2f} us  ({out[19]} warps with work, {out[21]} warps)")

@@ -49,6 +49,12 @@
 #ifndef YKA_PRETEST_CHANNELS
 #define YKA_PRETEST_CHANNELS 1
 #endif
+#ifndef YKA_RANGE_SINGLE
+#define YKA_RANGE_SINGLE 0      // 1: the range stage one 8x8 tile at a time (round 1 form, kept for A/B builds)
+#endif
+#ifndef YKA_RANGE_UNROLL
+#define YKA_RANGE_UNROLL 0
+#endif
 #define YKP_RS 24                   // row pitch in bytes of a warp-private 17x17 byte tile
 #define YKP_CH (17 * YKP_RS)        // bytes of one channel of it
 #define YKP_TILE 1232               // 3 channels, rounded to a multiple of 16
@@ -95,7 +101,11 @@ struct YkaShared {
 // everything a consumer warp owns, in one block (one base address serves all of it)
 struct alignas(128) YkaWarpArea {
     uint8_t  priv[YKP_TILE];        // the macro tile's 17x17 samples, three channels, as bytes
+#if YKA_RANGE_UNROLL == 2
+    uint8_t  hist[1536];            // byte counters of the range stage: a 256-byte histogram per plane and half-warp
+#else
     uint8_t  hist[768];             // byte counters of the range stage, one 256-byte histogram per plane
+#endif
     uint32_t touch[28];             // touch words of the 5x5 lattice points of the macro tile
     int      wstat[40];             // 8 groups x 5 counters (see yka_stat_add)
     YkaSlotC slotc;
@@ -587,6 +597,158 @@ static __device__ __forceinline__ void yka_range_tile(const uint8_t* __restrict_
     __syncwarp();       // the histogram entries are clean again before the next tile fills them
 }
 
+// maximum over the lanes of the caller's half-warp.  Two full-warp reductions: a reduction whose member mask differs between
+// the lanes of a warp is compiled into a divergent path (WARPSYNC.COLLECTIVE per mask) that leaves the halves running apart.
+static __device__ __forceinline__ unsigned yka_half_max(unsigned v, int upper) {
+    const unsigned a = __reduce_max_sync(YK_FULL, upper ? 0u : v), b = __reduce_max_sync(YK_FULL, upper ? v : 0u);
+    return upper ? b : a;
+}
+
+// The same for the two 8x8 tiles of one half (upper / lower) of the macro tile at once: half-warp h codes the tile at
+// (8*h, ly8), a lane four consecutive pixels of a row - exactly one row of one 4x4 cell, so a lane is coded or not as a
+// whole and its four index bytes are one aligned word of the tile's compact output.  Per value the count comes back from
+// the shared-memory atomic itself (the last lane to add a value sees its count - 1, so the maximum of old << 8 | value
+// over the lanes is the most used value, highest index among equals: EC.cpp:8340) - no second look at the histogram;
+// the reductions run per half-warp (yka_half_max).  qL / qR: quadrants to code of the left / right tile.
+static __device__ __forceinline__ void yka_range_pair(const uint8_t* __restrict__ priv, const YkaSlotC& Rg, uint8_t* __restrict__ hist,
+                                                      const uint32_t* __restrict__ magicTab, size_t tileL, int ly8, unsigned qL, unsigned qR) {
+    const int lane = threadIdx.x & 31;
+    const int h = lane >> 4, l = lane & 15, r = l >> 1, right = l & 1;
+    const unsigned q = h ? qR : qL;
+    const int band = r >> 2;
+    const bool valid = (q >> (band * 2 + right)) & 1u;
+    const unsigned qb = (q >> (band * 2)) & 3u;             // coded quadrants of this band: bit0 left, bit1 right
+    const int lengthX = (qb == 3u) ? 8 : 4, x2 = (qb == 2u) ? 4 : 0;
+    const int pos = (band ? 16 * __popc(q & 3u) : 0) + (r & 3) * lengthX + (4 * right - x2);
+    const size_t tile = tileL + h;
+    uint32_t* hw = reinterpret_cast<uint32_t*>(hist) + 64 * h;              // byte counters, four to a word; one histogram per half-warp
+    const uint8_t* src = priv + (ly8 + r) * YKP_RS + 8 * h + 4 * right;
+#if YKA_RANGE_UNROLL
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+    for (int p = 0; p < 3; p++) {
+        const unsigned word = *reinterpret_cast<const unsigned*>(src + p * YKP_CH);      // CompressF(v,255) == v (EC.cpp:8442)
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = yka_byte(word, k);
+        // FindAndRemoveMostUsedColor (EC.cpp:8335-8356)
+        unsigned key = 0;
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned s8 = (unsigned)(v[k] & 3) * 8u - 8u;                         // rotations take it modulo 32
+                const unsigned old = atomicAdd(&hw[v[k] >> 2], __funnelshift_l(0x100u, 0x100u, s8));
+                key = max(key, (__funnelshift_r(old, old, s8) & 0xFF00u) | (unsigned)v[k]);
+            }
+        }
+        key = yka_half_max(key, h);
+        reinterpret_cast<uint4*>(hw)[l] = make_uint4(0u, 0u, 0u, 0u);                       // clean again (every add came back before the reduction)
+        const int color0 = min(max((int)(key & 255u), 1), 254);
+        // Model1 (EC.cpp:8358-8381) over what is left of the histogram
+        bool rem[4];
+        unsigned lo = 999u, hi = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            rem[k] = valid && (unsigned)(v[k] - (color0 - 1)) > 2u;
+            lo = min(lo, rem[k] ? (unsigned)v[k] : 999u);
+            hi = max(hi, rem[k] ? (unsigned)v[k] : 0u);
+        }
+        const unsigned mn = 999u - yka_half_max(999u - lo, h);
+        const unsigned mx = yka_half_max(hi, h);
+        int minCol = 0, delta = 0;
+        if (mn != 999u) { minCol = (int)mn; delta = (int)(mx - mn); }
+        // GetValueModel1 (EC.cpp:8383-8391): 1 + n / delta (C division), n = (v - minCol) * 15 + delta / 2 - 1 >= -1, is
+        // floor((n + delta) / delta) = ((2 * (n + delta)) * (ceil(2^22 / delta) << 9)) >> 32, exact for n + delta < 16448;
+        // delta == 0 (every remaining pixel == minCol) gives 1: the table holds 2^31 for it and the numerator is 2
+        const int K = delta ? 2 * ((delta >> 1) - 1 + delta - 15 * minCol) : 2 - 30 * minCol;
+        const unsigned magic = magicTab[delta];
+        if (valid) {
+            unsigned b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) b[k] = rem[k] ? __umulhi((unsigned)(v[k] * 30 + K), magic) : 0u;
+            *reinterpret_cast<uint32_t*>(Rg.r2Raw[p] + tile * 64 + pos) = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
+        }
+        if (l == 0 && q) Rg.r2RawType[p][tile] = (uint32_t)color0 | ((uint32_t)minCol << 8) | ((uint32_t)delta << 16);     // EC.cpp:8503-8505
+        __syncwarp();       // the cleared counters are in place before the next plane's adds
+    }
+}
+
+#if YKA_RANGE_UNROLL == 2
+// yka_range_pair with the three planes side by side: every step of the chain (histogram adds, the three half-warp
+// reductions, the index computation) is issued for the three planes before its results are needed, so that a warp waits
+// for one round trip per step instead of three.  One histogram per plane and half-warp.
+static __device__ __forceinline__ void yka_range_pair3(const uint8_t* __restrict__ priv, const YkaSlotC& Rg, uint8_t* __restrict__ hist,
+                                                       const uint32_t* __restrict__ magicTab, size_t tileL, int ly8, unsigned qL, unsigned qR) {
+    const int lane = threadIdx.x & 31;
+    const int h = lane >> 4, l = lane & 15, r = l >> 1, right = l & 1;
+    const unsigned q = h ? qR : qL;
+    const int band = r >> 2;
+    const bool valid = (q >> (band * 2 + right)) & 1u;
+    const unsigned qb = (q >> (band * 2)) & 3u;
+    const int lengthX = (qb == 3u) ? 8 : 4, x2 = (qb == 2u) ? 4 : 0;
+    const int pos = (band ? 16 * __popc(q & 3u) : 0) + (r & 3) * lengthX + (4 * right - x2);
+    const size_t tile = tileL + h;
+    uint32_t* hw = reinterpret_cast<uint32_t*>(hist) + 64 * h;              // plane p: hw + 128 * p
+    const uint8_t* src = priv + (ly8 + r) * YKP_RS + 8 * h + 4 * right;
+    int v[3][4];
+    unsigned key[3];
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        const unsigned word = *reinterpret_cast<const unsigned*>(src + p * YKP_CH);
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[p][k] = yka_byte(word, k);
+    }
+    const unsigned one = valid ? 0x100u : 0u;                               // lanes without coded pixels add nothing
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        key[p] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned s8 = (unsigned)(v[p][k] & 3) * 8u - 8u;
+            const unsigned old = atomicAdd(&hw[128 * p + (v[p][k] >> 2)], __funnelshift_l(one, one, s8));
+            key[p] = max(key[p], (__funnelshift_r(old, old, s8) & 0xFF00u) | (unsigned)v[p][k]);
+        }
+        if (!valid) key[p] = 0;
+    }
+#pragma unroll
+    for (int p = 0; p < 3; p++) key[p] = yka_half_max(key[p], h);
+#pragma unroll
+    for (int p = 0; p < 3; p++) reinterpret_cast<uint4*>(hw + 128 * p)[l] = make_uint4(0u, 0u, 0u, 0u);
+    unsigned lo[3], hi[3];
+    int color0[3];
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        color0[p] = min(max((int)(key[p] & 255u), 1), 254);
+        lo[p] = 999u; hi[p] = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool rem = valid && (unsigned)(v[p][k] - (color0[p] - 1)) > 2u;
+            lo[p] = min(lo[p], rem ? (unsigned)v[p][k] : 999u);
+            hi[p] = max(hi[p], rem ? (unsigned)v[p][k] : 0u);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 3; p++) { lo[p] = 999u - yka_half_max(999u - lo[p], h); hi[p] = yka_half_max(hi[p], h); }
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        int minCol = 0, delta = 0;
+        if (lo[p] != 999u) { minCol = (int)lo[p]; delta = (int)(hi[p] - lo[p]); }
+        const int K = delta ? 2 * ((delta >> 1) - 1 + delta - 15 * minCol) : 2 - 30 * minCol;
+        const unsigned magic = magicTab[delta];
+        if (valid) {
+            unsigned b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) b[k] = ((unsigned)(v[p][k] - (color0[p] - 1)) > 2u) ? __umulhi((unsigned)(v[p][k] * 30 + K), magic) : 0u;
+            *reinterpret_cast<uint32_t*>(Rg.r2Raw[p] + tile * 64 + pos) = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
+        }
+        if (l == 0 && q) Rg.r2RawType[p][tile] = (uint32_t)color0[p] | ((uint32_t)minCol << 8) | ((uint32_t)delta << 16);
+    }
+    __syncwarp();
+}
+#endif
+
 template <bool U8>
 static __device__ __forceinline__ int yka_pass16_raw(const void* __restrict__ rawv, const YkaSlotC& C, YkaStat* st, int gmx, int gmy, int mx, int R) {
     const int lane = threadIdx.x & 31, row = lane >> 1, half = lane & 1;
@@ -646,12 +808,13 @@ static __device__ __forceinline__ int yka_pass16_raw(const void* __restrict__ ra
 }
 
 #ifdef YK_TIMING
-__device__ unsigned long long yk_timing[16];
+__device__ unsigned long long yk_timing[24];
+static __device__ __forceinline__ unsigned long long ykt_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define YKT_DECL long long t__ = clock64(), t2__
 #define YKT(i) (t2__ = clock64(), atomicAdd(&yk_timing[i], (unsigned long long)(t2__ - t__)), t__ = t2__)
 extern "C" void yk_debug_timing(unsigned long long* out, int reset) {
     cudaMemcpyFromSymbol(out, yk_timing, sizeof(yk_timing));
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(yk_timing, z, sizeof(z)); }
+    if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(yk_timing, z, sizeof(z)); }
 }
 #else
 #define YKT_DECL
@@ -731,6 +894,7 @@ static __device__ __forceinline__ void yka_macro_tile(const uint8_t* __restrict_
     if (threadIdx.x == 32) YKT(12);
     if (run.doR2 && claimed != 0xFFFFu) {
         const int tilesW = C.w >> 3;
+#if YKA_RANGE_SINGLE
 #pragma unroll 1
         for (int t8 = 0; t8 < 4; t8++) {
             const int qx = t8 & 1, qy = t8 >> 1;
@@ -741,6 +905,22 @@ static __device__ __forceinline__ void yka_macro_tile(const uint8_t* __restrict_
                 yka_range_tile(priv, C, hist, magicTab, tile, 8 * qx, 8 * qy, q);
             }
         }
+#else
+#pragma unroll 1
+        for (int qy = 0; qy < 2; qy++) {
+            // unclaimed cells of the two cell rows of this half, as quadrant masks of its left and right 8x8 tile
+            const unsigned f = ~(claimed >> (8 * qy));
+            const unsigned qL = (f & 3u) | ((f >> 2) & 12u), qR = ((f >> 2) & 3u) | ((f >> 4) & 12u);
+            if (qL | qR) {
+                const size_t tileL = (size_t)((gmy + 8 * qy) >> 3) * tilesW + (gmx >> 3);
+#if YKA_RANGE_UNROLL == 2
+                yka_range_pair3(priv, C, hist, magicTab, tileL, 8 * qy, qL, qR);
+#else
+                yka_range_pair(priv, C, hist, magicTab, tileL, 8 * qy, qL, qR);
+#endif
+            }
+        }
+#endif
     }
     if (threadIdx.x == 32) YKT(13);
 }
@@ -770,8 +950,15 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
     // ---- start-up (the only block-wide barriers)
     for (int i = tid; i < (int)(sizeof(YkaShared) / 4); i += YKA_THREADS) reinterpret_cast<uint32_t*>(&sh)[i] = 0;
     for (int i = tid; i < YKA_SMEM_WARPS / 4; i += YKA_THREADS) reinterpret_cast<uint32_t*>(warpAreas)[i] = 0;
+#if YKA_RANGE_SINGLE
     if (tid < 256) sMagic[tid] = tid ? ((1u << 20) + (unsigned)tid - 1u) / (unsigned)tid : 0u;
+#else
+    if (tid < 256) sMagic[tid] = tid ? (((1u << 22) + (unsigned)tid - 1u) / (unsigned)tid) << 9 : 0x80000000u;      // see yka_range_pair
+#endif
     __syncthreads();
+#ifdef YK_TIMING
+    if (tid == 0) { const unsigned long long n = ykt_now(); atomicMax(&yk_timing[16], ~n); atomicAdd(&yk_timing[17], n & 0xFFFFFFFFull); atomicAdd(&yk_timing[23], 1ull); }
+#endif
     if (tid < 41) sh.pretestTab[tid] = yka_pretest_entry(tid);
     if (tid >= 128 && tid < 128 + YK_NPASS * 32) sh.passLane[(tid - 128) >> 5][(tid - 128) & 31] = yka_pass_lane_entry((tid - 128) >> 5, (tid - 128) & 31);
     if (tid >= 64 && tid < 64 + YKA_CONS_WARPS) warpAreas[tid - 64].slotc.slot = -1;
@@ -871,6 +1058,9 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
     YkaStat* st = WA.wstat;
     YKT_DECL;
     const bool fast16 = run.fresh && run.nPasses > 0 && run.passId[0] == 0;      // uniform for the launch
+#ifdef YK_TIMING
+    bool firstItem = true;
+#endif
     for (;;) {
         int q = 0;
         if (lane == 0) q = atomicAdd(&sh.queueHead, 1);
@@ -888,6 +1078,10 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         }
         alive = __all_sync(YK_FULL, alive);
         if (tid == 32) YKT(8);
+#ifdef YK_TIMING
+        if (lane == 0 && firstItem && alive) { atomicAdd(&yk_timing[18], ykt_now() & 0xFFFFFFFFull); atomicAdd(&yk_timing[19], 1ull); }
+        firstItem = false;
+#endif
         if (!alive) break;
         const YkaUnit U = sh.unit[i];
         const int cachedSlot = C.slot;
@@ -935,6 +1129,9 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         __syncwarp();
         if (tid == 32) YKT(10);
     }
+#ifdef YK_TIMING
+    if (lane == 0) { const unsigned long long n = ykt_now(); atomicAdd(&yk_timing[20], n & 0xFFFFFFFFull); atomicAdd(&yk_timing[21], 1ull); atomicMax(&yk_timing[22], n); }
+#endif
     if (C.slot >= 0) yka_stat_flush(sh, C, st);
     // the last consumer warp of the CTA adds the CTA's counters to the image's header
     __threadfence_block();

@@ -525,6 +525,187 @@ yk_k_r1_encode(const YkSlotDev* __restrict__ slots, int slot, const YkR1Launch L
     }
 }
 
+// The three full-resolution colour planes of one launch (nJobs == 3, the fused yk_analyze path and yk_range_dyn on R, G,
+// B): a warp takes a listed block and codes its three planes in one go.  What a block costs besides its per-pixel work is
+// shared by the planes (list entry, geometry, validity ballots), and the ordered error sums - 64 dependent float adds
+// that one lane per mode has to do whatever the other lanes are up to - run for the 18 (plane, mode) pairs side by side
+// in 18 lanes; the 16-pixel quadrants of the block that hold no coded pixel only add +0.0f and are skipped (exact).
+#ifndef YK_R1_MINB3
+#define YK_R1_MINB3 8
+#endif
+#ifndef YK_R1_CAP3
+#define YK_R1_CAP3 8
+#endif
+#ifndef YK_R1_NO3
+#define YK_R1_NO3 0
+#endif
+__global__ void __launch_bounds__(YK_R1_THREADS, YK_R1_MINB3)
+yk_k_r1_encode3(const YkSlotDev* __restrict__ slots, int slot, const YkR1Launch LP, const int* __restrict__ lut, const unsigned short* __restrict__ rtab, const short* __restrict__ r7tab) {
+    __shared__ __align__(16) float sTerm[YK_R1_THREADS / 32][3][6][64];
+    const YkSlotDev& S = slots[slot];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const YkR1Args& A0 = LP.job[0];
+    const int nList = __ldg(&S.hdr[YK_HD_R1_DEF0 + A0.out]);                                // written by yk_k_r1_offsets
+    const int r = lane >> 2, c0 = (lane & 3) * 2;
+    const int startMode = A0.mode3 ? 3 : 0;
+    float (*term)[6][64] = sTerm[warp];
+    // the lane that sums (plane sj, mode sm)
+    const int sj = lane / 6, sm = lane - 6 * sj;
+    const bool summing = lane < 18 && sm >= startMode;
+    const int stride = gridDim.x * (YK_R1_THREADS / 32);
+    int k = blockIdx.x * (YK_R1_THREADS / 32) + warp;
+    uint4 nItem = make_uint4(0u, 0u, 0u, 0u);
+    int nv[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
+    auto fetch = [&](int at) {
+        if (at >= nList) return;
+        nItem = __ldg(reinterpret_cast<const uint4*>(S.r1List) + at);
+        const bool on = (nItem.y >> lane) & 1u;
+        const int xx = nItem.x & 0xFFFF, yy = nItem.x >> 16;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const YkR1Args& An = LP.job[j];
+            nv[j][0] = 0; nv[j][1] = 0;
+            if (on) {
+                if (An.srcU8) {
+                    const unsigned short two = __ldg(reinterpret_cast<const unsigned short*>(An.srcU8 + (size_t)(yy + r) * An.pitchU8 + xx + c0));
+                    nv[j][0] = two & 255; nv[j][1] = two >> 8;
+                } else {
+                    const int2 p = __ldg(reinterpret_cast<const int2*>(An.src + (size_t)(yy + r) * An.pw + xx + c0));
+                    nv[j][0] = p.x; nv[j][1] = p.y;
+                }
+            }
+        }
+    };
+    fetch(k);
+    for (; k < nList; k += stride) {
+        const uint4 item = nItem;
+        int o[3][2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) { o[j][0] = nv[j][0]; o[j][1] = nv[j][1]; }
+        fetch(k + stride);
+        const int x = item.x & 0xFFFF, y = item.x >> 16;
+        const bool valid = (item.y >> lane) & 1u;
+        int meta[3];                                                           // b6 | r7 << 8 | sgn << 16 | tabled << 24
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            // ---- min / max over the coded pixels (Plane::GetMinMax_Y, Plane.cpp:489-587), table index (EC.cpp:635-650, 764-768)
+            const int v0 = o[j][0], v1 = o[j][1];
+            int mn = __reduce_min_sync(YK_FULL, valid ? min(v0, v1) : INT_MAX);
+            int mx = __reduce_max_sync(YK_FULL, valid ? max(v0, v1) : INT_MIN);
+            if (mn == INT_MAX) { mn = 0; mx = 0; }
+            int sgn = 0;
+            if (mn < 0) { mn += 128; mx += 128; sgn = 128; }
+            mn = min(max(mn, 0), 255); mx = min(max(mx, mn), 255);
+            const int m = min(mn, 224);
+            const int diff = max(mx - m, 16);
+            const int b6 = (m * 63 + 112) / 224;
+            const int r7 = __ldg(r7tab + b6 * 224 + (max(diff, 32) - 32));
+            const int o0 = v0 + sgn, o1 = v1 + sgn;
+            o[j][0] = o0; o[j][1] = o1;
+            const bool tabled = r7 < YK_R1_RTAB_R7 && b6 < 63 && __all_sync(YK_FULL, (unsigned)o0 < (unsigned)YK_R1_RTAB_VALUES && (unsigned)o1 < (unsigned)YK_R1_RTAB_VALUES);
+            meta[j] = b6 | (r7 << 8) | (sgn << 16) | ((int)tabled << 24);
+            // relative error terms, float32 (EC.cpp:884-886); invalid pixels and zero samples add +0.0f
+            const bool use0 = valid && o0 != 0, use1 = valid && o1 != 0;
+            const float f0 = __int2float_rn(use0 ? o0 : 1), f1 = __int2float_rn(use1 ? o1 : 1);
+            const float rc0 = use0 ? __frcp_rn(f0) : 0.0f, rc1 = use1 ? __frcp_rn(f1) : 0.0f;
+            if (tabled) {
+                const unsigned short* RT = rtab + (size_t)(b6 * YK_R1_RTAB_R7 + r7) * (6 * YK_R1_RTAB_VALUES);
+#pragma unroll
+                for (int mode = 0; mode < 6; mode++) {
+                    if (mode < startMode) continue;
+                    const int L0 = __ldg(RT + mode * YK_R1_RTAB_VALUES + o0) & 255, L1 = __ldg(RT + mode * YK_R1_RTAB_VALUES + o1) & 255;
+                    *reinterpret_cast<float2*>(&term[j][mode][2 * lane]) = make_float2(yk_r1_quot(abs(L0 - o0), f0, rc0), yk_r1_quot(abs(L1 - o1), f1, rc1));
+                }
+            } else {
+                const int* T = lut + (size_t)(b6 * 176 + min(r7, 175)) * YK_R1_LUT_INTS;
+#pragma unroll 1
+                for (int mode = startMode; mode < 6; mode++) {
+                    const int off = mode < 3 ? 16 * mode : 48 + 8 * (mode - 3);
+                    int g0 = 0, g1 = 0;
+                    for (int st = (mode < 3 ? 8 : 4); st > 0; st >>= 1) {
+                        if (o0 > __ldg(T + 72 + off + g0 + st)) g0 += st;
+                        if (o1 > __ldg(T + 72 + off + g1 + st)) g1 += st;
+                    }
+                    const int d0 = abs(__ldg(T + off + g0) - o0), d1 = abs(__ldg(T + off + g1) - o1);
+                    term[j][mode][2 * lane] = (use0 && d0 != 0) ? __fdiv_rn(__int2float_rn(d0), f0) : 0.0f;
+                    term[j][mode][2 * lane + 1] = (use1 && d1 != 0) ? __fdiv_rn(__int2float_rn(d1), f1) : 0.0f;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- ordered sums: row-major pixel order, one lane per (plane, mode).  float4 group q = pixels 4q .. 4q + 3 = row
+        // q >> 1, left (q even) or right half: a quadrant without coded pixels holds zeros only
+        float err = 0.0f;
+        if (summing) {
+            const float4* P = reinterpret_cast<const float4*>(term[sj][sm]);
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const unsigned hm = (item.y >> (16 * half)) & 0xFFFFu;
+                if (hm) {
+                    const bool Lq = (hm & 0x3333u) != 0u, Rq = (hm & 0xCCCCu) != 0u;
+                    if (Lq && Rq) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float4 t = P[8 * half + q];
+                            err = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(err, t.x), t.y), t.z), t.w);
+                        }
+                    } else {
+                        const float4* Q = P + 8 * half + (Rq ? 1 : 0);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const float4 t = Q[2 * q];
+                            err = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(err, t.x), t.y), t.z), t.w);
+                        }
+                    }
+                }
+            }
+        }
+        // `<=`: later modes win ties (EC.cpp:897-905); order-preserving map of the bit patterns (-0 counted as +0)
+        const unsigned eraw = __float_as_uint(__fadd_rn(err, 0.0f));
+        const unsigned ebits = summing ? (eraw ^ ((eraw >> 31) ? 0xFFFFFFFFu : 0x80000000u)) : 0xFFFFFFFFu;
+        int best[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const bool mine = summing && sj == j;
+            const unsigned emin = __reduce_min_sync(YK_FULL, mine ? ebits : 0xFFFFFFFFu);
+            best[j] = 31 - __clz((int)__ballot_sync(YK_FULL, mine && ebits == emin)) - 6 * j;
+        }
+        __syncwarp();                                                           // the terms are rewritten by the next block
+        const unsigned bv0 = item.y;                                            // coded pairs == lanes with pixels
+        const int before = 2 * __popc(bv0 & ((1u << lane) - 1u));
+        const int n0 = (int)item.z + before;                                    // even: the two nibbles share a byte
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const YkR1Args& A = LP.job[j];
+            const int b6 = meta[j] & 255, r7 = (meta[j] >> 8) & 255, sgn = (meta[j] >> 16) & 255;
+            const bool tabled = (meta[j] >> 24) & 1;
+            const int bestMode = best[j];
+            if (valid) {
+                const int boff = bestMode < 3 ? 16 * bestMode : 48 + 8 * (bestMode - 3);
+                const int* T = lut + (size_t)(b6 * 176 + min(r7, 175)) * YK_R1_LUT_INTS;
+                const int o0 = o[j][0], o1 = o[j][1];
+                int c0v = 0, c1v = 0;
+                if (tabled) {
+                    const unsigned short* RT = rtab + (size_t)(b6 * YK_R1_RTAB_R7 + r7) * (6 * YK_R1_RTAB_VALUES);
+                    c0v = __ldg(RT + bestMode * YK_R1_RTAB_VALUES + o0) >> 8; c1v = __ldg(RT + bestMode * YK_R1_RTAB_VALUES + o1) >> 8;
+                } else {
+                    for (int st = (bestMode < 3 ? 8 : 4); st > 0; st >>= 1) {
+                        if (o0 > __ldg(T + 72 + boff + c0v + st)) c0v += st;
+                        if (o1 > __ldg(T + 72 + boff + c1v + st)) c1v += st;
+                    }
+                }
+                reinterpret_cast<uint8_t*>(S.r1Nib[A.out])[n0 >> 1] = (uint8_t)(c0v | (c1v << 4));   // low nibble first, EC.cpp:1180-1184
+                if (A.dst) {
+                    const int offset = (A.chroma && sgn) ? -128 : 0;
+                    int* d = A.dst + (size_t)(y + r) * S.w + (x + c0);
+                    d[0] = __ldg(T + boff + c0v) + offset; d[1] = __ldg(T + boff + c1v) + offset;
+                }
+            }
+            if (lane == 0) S.r1Defs[A.out][k] = (uint16_t)((bestMode << 13) | (r7 << 7) | b6);    // EncodeTileType, YAIK_private.h:358
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Chroma front-end: Image::ConvertToRGB2YCoCg (Image.cpp:285-321, RGBtoYCoCg EC.cpp:53-67) fused
 // with EncoderContext::chromaReduction (EC.cpp:2770-2782) = Plane::SampleDown (Plane.cpp:278-369) of Co and of Cg.
@@ -591,6 +772,15 @@ void yk_launch_range_dyn_encode(const YkSlotDev* slotsDev, int slot, const YkR1L
     long long want = ((long long)maxBlocks * launch.nJobs + perCta - 1) / perCta;
     const long long cap = (long long)numSMs * YK_R1_CAP;
     if (want > cap) want = cap;
+    const bool three = launch.nJobs == 3 && !(launch.job[0].shX | launch.job[0].shY) && !YK_R1_NO3;
+    if (three) {
+        // a warp codes the three planes of a block: one third of the items
+        want = ((long long)maxBlocks + perCta - 1) / perCta;
+        const long long cap3 = (long long)numSMs * YK_R1_CAP3;
+        if (want > cap3) want = cap3;
+        YK_LAUNCH(yk_k_r1_encode3, dim3(want > 0 ? (unsigned)want : 1u), dim3(YK_R1_THREADS), 0, st, slotsDev, slot, launch, lutDev, reinterpret_cast<const unsigned short*>(rtabDev), reinterpret_cast<const short*>(r7Dev));
+        return;
+    }
     YK_LAUNCH(yk_k_r1_encode, dim3(want > 0 ? (unsigned)want : 1u), dim3(YK_R1_THREADS), 0, st, slotsDev, slot, launch, lutDev, reinterpret_cast<const unsigned short*>(rtabDev), reinterpret_cast<const short*>(r7Dev));
 }
 void yk_launch_chroma(const YkSlotDev* slotsDev, int slot, int w, int h, const YkChromaArgs& args, cudaStream_t st) {
@@ -606,6 +796,7 @@ int yk_preload_aux() {
     { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_state); if (e != cudaSuccess) return (int)e; }
     { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_r1_offsets); if (e != cudaSuccess) return (int)e; }
     { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_r1_encode); if (e != cudaSuccess) return (int)e; }
+    { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_r1_encode3); if (e != cudaSuccess) return (int)e; }
     { const cudaError_t e = cudaFuncGetAttributes(&fa, yk_k_chroma); if (e != cudaSuccess) return (int)e; }
 #endif
     return 0;
