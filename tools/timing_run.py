@@ -12,7 +12,7 @@ ctx.set_image(img, 0)
 st = capi.STAGE_ALPHA | capi.STAGE_GRADIENT | capi.STAGE_RANGE1D
 for _ in range(3):
     ctx.reset_state(0); ctx.analyze(st); ctx.sync()
-out = (C.c_ulonglong * 24)()
+out = (C.c_ulonglong * 32)()
 lib.yk_debug_timing(out, 1)
 N = 5
 for _ in range(N):
@@ -32,3 +32,9 @@ t0 = (~out[16]) & 0xFFFFFFFFFFFFFFFF
 lo = t0 & 0xFFFFFFFF
 def avg(s, n): return (s / max(n, 1)) - lo
 print(f"one launch: CTA set-up done avg {avg(out[17], out[23]) / 1e3:7.2f} us after the first CTA;  consumer warps: first item avg {avg(out[18], out[19]) / 1e3:7.2f} us, exit avg {avg(out[20], out[21]) / 1e3:7.2f} us, last exit {(out[22] - t0) / 1e3:7.2f} us  ({out[19]} warps with work, {out[21]} warps)")
+n = out[23]
+print("producer: loads of unit 0 / 1 / 2 issued avg " + " / ".join(f"{avg(out[24 + k], n) / 1e3:6.2f}" for k in range(3)) + " us;  first item of unit 0 / 1 / 2 taken avg " + " / ".join(f"{avg(out[27 + k], n) / 1e3:6.2f}" for k in range(3)) + " us")
+te = (~out[30]) & 0xFFFFFFFFFFFFFFFF
+print(f"kernel entry: first CTA {(te - t0) / 1e3:7.2f} us, avg {(out[31] / max(n, 1) - (t0 & 0xFFFFFFFF)) / 1e3:7.2f} us relative to the first CTA's set-up done")
+import torch
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -33,6 +33,9 @@
 #ifndef YKA_TICKETS
 #define YKA_TICKETS 4               // tickets a CTA holds ahead of the unit it is issuing
 #endif
+#ifndef YKA_LAZY_AHEAD
+#define YKA_LAZY_AHEAD 1
+#endif
 #define YKA_LOOKAHEAD 3             // units the producer may run ahead of the unit the consumers are taking items from
 #ifndef YKA_CONS_WARPS
 #define YKA_CONS_WARPS 23
@@ -51,6 +54,12 @@
 #endif
 #ifndef YKA_RANGE_SINGLE
 #define YKA_RANGE_SINGLE 0      // 1: the range stage one 8x8 tile at a time (round 1 form, kept for A/B builds)
+#endif
+#ifndef YKA_STATIC_ROUND_MIN
+#define YKA_STATIC_ROUND_MIN 32     // units per CTA from which a launch hands out a whole round of ticket registers statically (a short launch pays for it in its tail)
+#endif
+#ifndef YKA_STATIC_FIRST
+#define YKA_STATIC_FIRST 1
 #endif
 #ifndef YKA_RANGE_UNROLL
 #define YKA_RANGE_UNROLL 0
@@ -201,10 +210,11 @@ static __device__ __forceinline__ int yka_byte(unsigned word, int k) { return (i
 // (so a pass over 4-wide tiles is one sweep as well).  Entry: x = lanes sharing my tile; y = byte offset of quad 0 | of
 // quad 1 << 16 inside a channel of the private tile; z = offset of the tile's top-left sample | the tile's 4x4 cells
 // (bit = 4*cellY + cellX) << 16; w = dx0 | dy << 8 | tile index << 16 | leader << 24 (dx0, dy: quad 0 inside the tile).
-static __device__ __forceinline__ uint4 yka_pass_lane_entry(int pid, int lane) {
-    const YkGeomS g = yk_geom_s(pid);
-    const int shx = g.shx, shy = g.shy, TW = 1 << shx, TH = 1 << shy;
-    int x0, y0, x1, y1;
+struct alignas(16) YkaLaneEntry { unsigned x, y, z, w; };
+static constexpr YkaLaneEntry yka_pass_lane_entry(int pid, int lane) {
+    constexpr int SHX[YK_NPASS] = { 4, 4, 3, 3, 3, 2, 2 }, SHY[YK_NPASS] = { 4, 3, 4, 3, 2, 3, 2 };     // yk_geom_s_tab
+    const int shx = SHX[pid], shy = SHY[pid], TW = 1 << shx, TH = 1 << shy;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     if (shx == 2) { x0 = x1 = 4 * (lane & 3); y0 = 2 * (lane >> 2); y1 = y0 + 1; }
     else { x0 = 8 * (lane & 1); x1 = x0 + 4; y0 = y1 = lane >> 1; }
     const int tx = x0 >> shx, ty = y0 >> shy, lxT = tx << shx, lyT = ty << shy;
@@ -213,14 +223,24 @@ static __device__ __forceinline__ uint4 yka_pass_lane_entry(int pid, int lane) {
         const int lx = (shx == 2) ? 4 * (l & 3) : 8 * (l & 1), ly = (shx == 2) ? 2 * (l >> 2) : (l >> 1);
         if ((lx >> shx) == tx && (ly >> shy) == ty) gmask |= 1u << l;
     }
-    const int leader = lane == __ffs((int)gmask) - 1;
+    int first = 0;
+    while (!((gmask >> first) & 1u)) first++;
+    const int leader = lane == first;
     const unsigned cols = ((1u << (TW >> 2)) - 1u) << (lxT >> 2);
     unsigned cells = 0;
     for (int cy = lyT >> 2; cy < (lyT + TH) >> 2; cy++) cells |= cols << (4 * cy);
     const int t = ty * (16 >> shx) + tx;
-    return make_uint4(gmask, (unsigned)(y0 * YKP_RS + x0) | ((unsigned)(y1 * YKP_RS + x1) << 16), (unsigned)(lyT * YKP_RS + lxT) | (cells << 16),
-                      (unsigned)(x0 - lxT) | ((unsigned)(y0 - lyT) << 8) | ((unsigned)t << 16) | ((unsigned)leader << 24));
+    return YkaLaneEntry{ gmask, (unsigned)(y0 * YKP_RS + x0) | ((unsigned)(y1 * YKP_RS + x1) << 16), (unsigned)(lyT * YKP_RS + lxT) | (cells << 16),
+                         (unsigned)(x0 - lxT) | ((unsigned)(y0 - lyT) << 8) | ((unsigned)t << 16) | ((unsigned)leader << 24) };
 }
+// the table, built by the compiler (a CTA copies it to shared memory when it starts: 224 entries that took a 32-step loop each)
+struct YkaLaneTable { YkaLaneEntry e[YK_NPASS][32]; };
+static constexpr YkaLaneTable yka_make_lane_table() {
+    YkaLaneTable t{};
+    for (int p = 0; p < YK_NPASS; p++) for (int l = 0; l < 32; l++) t.e[p][l] = yka_pass_lane_entry(p, l);
+    return t;
+}
+__device__ const YkaLaneTable yka_lane_table = yka_make_lane_table();     // global memory: a lane reads its own entry (a constant bank serialises that)
 
 // table entry of tile ti (0..40) of a macro tile: offX | offY << 4 | shx << 8 | shy << 11 | cell << 14
 static __device__ __forceinline__ uint32_t yka_pretest_entry(int ti) {
@@ -808,13 +828,13 @@ static __device__ __forceinline__ int yka_pass16_raw(const void* __restrict__ ra
 }
 
 #ifdef YK_TIMING
-__device__ unsigned long long yk_timing[24];
+__device__ unsigned long long yk_timing[32];
 static __device__ __forceinline__ unsigned long long ykt_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define YKT_DECL long long t__ = clock64(), t2__
 #define YKT(i) (t2__ = clock64(), atomicAdd(&yk_timing[i], (unsigned long long)(t2__ - t__)), t__ = t2__)
 extern "C" void yk_debug_timing(unsigned long long* out, int reset) {
     cudaMemcpyFromSymbol(out, yk_timing, sizeof(yk_timing));
-    if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(yk_timing, z, sizeof(z)); }
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(yk_timing, z, sizeof(z)); }
 }
 #else
 #define YKT_DECL
@@ -943,42 +963,66 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
     YkaShared& sh = *reinterpret_cast<YkaShared*>(smem + YKA_SMEM_RAW + YKA_SMEM_WARPS + 1024);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef YK_TIMING
+    if (tid == 0) { const unsigned long long n = ykt_now(); atomicMax(&yk_timing[30], ~n); atomicAdd(&yk_timing[31], n & 0xFFFFFFFFull); }
+#endif
     // units of one image: (pair of regions, macro-tile row); every image of a launch has the same size
     const int nbxAll = slots[slot0].nbx, nPairs = (nbxAll + 1) >> 1;
     const int unitsPerSlot = nPairs * (nRegions / nbxAll) * 4, total = nSlots * unitsPerSlot;
 
-    // ---- start-up (the only block-wide barriers)
-    for (int i = tid; i < (int)(sizeof(YkaShared) / 4); i += YKA_THREADS) reinterpret_cast<uint32_t*>(&sh)[i] = 0;
-    for (int i = tid; i < YKA_SMEM_WARPS / 4; i += YKA_THREADS) reinterpret_cast<uint32_t*>(warpAreas)[i] = 0;
+    // the producer warp asks for what its first unit needs from global memory before the set-up below (the round trips
+    // overlap the set-up instead of following it)
+    const int firstSlot = slot0 + (YKA_STATIC_FIRST && nSlots > 1 ? (int)blockIdx.x / unitsPerSlot : 0);
+    int firstPlanes = 0;
+    int* ticket = nullptr;
+    if (warp == 0) {
+        firstPlanes = slots[firstSlot].nPlanes;
+        ticket = slots[slot0].hdr + YK_HD_TICKET_ANALYZE;
+        if (lane < 4) yka_tmap_acquire(&slots[firstSlot].tmap[lane]);        // all four: nothing here waits for a load
+    }
+    uint4 laneEntry = make_uint4(0u, 0u, 0u, 0u);
+    if (tid >= 128 && tid < 128 + YK_NPASS * 32) laneEntry = *reinterpret_cast<const uint4*>(&yka_lane_table.e[(tid - 128) >> 5][(tid - 128) & 31]);
+    // ---- start-up (the only block-wide barrier).  Nothing is cleared wholesale: every field that is read before it is
+    // written has one thread that initialises it, and a consumer warp prepares its own area.
 #if YKA_RANGE_SINGLE
     if (tid < 256) sMagic[tid] = tid ? ((1u << 20) + (unsigned)tid - 1u) / (unsigned)tid : 0u;
 #else
     if (tid < 256) sMagic[tid] = tid ? (((1u << 22) + (unsigned)tid - 1u) / (unsigned)tid) << 9 : 0x80000000u;      // see yka_range_pair
 #endif
-    __syncthreads();
+    if (tid >= 384 && tid < 384 + YKA_NSTAT) sh.stat[tid - 384] = 0;
+    if (warp >= 1) {
+        YkaWarpArea& mine = warpAreas[warp - 1];
+        for (int i = lane; i < (int)sizeof(mine.hist) / 16; i += 32) reinterpret_cast<uint4*>(mine.hist)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = lane; i < 40; i += 32) mine.wstat[i] = 0;
+        if (lane < 28) mine.touch[lane] = 0u;
+        if (lane == 0) mine.slotc.slot = -1;
+    }
 #ifdef YK_TIMING
     if (tid == 0) { const unsigned long long n = ykt_now(); atomicMax(&yk_timing[16], ~n); atomicAdd(&yk_timing[17], n & 0xFFFFFFFFull); atomicAdd(&yk_timing[23], 1ull); }
 #endif
     if (tid < 41) sh.pretestTab[tid] = yka_pretest_entry(tid);
-    if (tid >= 128 && tid < 128 + YK_NPASS * 32) sh.passLane[(tid - 128) >> 5][(tid - 128) & 31] = yka_pass_lane_entry((tid - 128) >> 5, (tid - 128) & 31);
-    if (tid >= 64 && tid < 64 + YKA_CONS_WARPS) warpAreas[tid - 64].slotc.slot = -1;
+    if (tid >= 128 && tid < 128 + YK_NPASS * 32) sh.passLane[(tid - 128) >> 5][(tid - 128) & 31] = laneEntry;
     if (tid < 41) sh.passOfTile[tid] = (uint8_t)((tid >= 1) + (tid >= 3) + (tid >= 5) + (tid >= 9) + (tid >= 17) + (tid >= 25));
-    if (tid == 96) {
-        sh.run = runArg;
-        unsigned long long rt = 0;
-        for (int rp = 0; rp < sh.run.nPasses; rp++) {
-            const YkGeomS g = yk_geom_s(sh.run.passId[rp]);
-            rt |= ((1ull << (256 >> (g.shx + g.shy))) - 1ull) << g.start;
-            sh.rpOf[sh.run.passId[rp]] = rp;
+    if (warp == 3) {
+        // the run's parameters, the tiles its passes cover (one lane per pass) and the barriers of the raw ring (one lane each):
+        // every other warp waits for this at the barrier below, so it is spread over the lanes
+        if (lane == 0) { sh.run = runArg; sh.queueHead = 0; sh.endSeq = INT_MAX; sh.statSlot = -1; sh.consLeft = YKA_CONS_WARPS; }
+        unsigned rtLo = 0, rtHi = 0;
+        if (lane < runArg.nPasses) {
+            const int pid = runArg.passId[lane];
+            const YkGeomS g = yk_geom_s(pid);
+            const unsigned long long rt = ((1ull << (256 >> (g.shx + g.shy))) - 1ull) << g.start;
+            rtLo = (unsigned)rt; rtHi = (unsigned)(rt >> 32);
+            sh.rpOf[pid] = lane;
         }
-        sh.runTiles = rt;
-        sh.endSeq = INT_MAX;
-        sh.statSlot = -1;
-        sh.consLeft = YKA_CONS_WARPS;
-        for (int i = 0; i < YKA_NR; i++) { yka_mbar_init(&sh.rawFull[i], 1); yka_mbar_init(&sh.rawFree[i], YKA_ITEMS); sh.unit[i].seq = -1; }
+        rtLo = __reduce_or_sync(YK_FULL, rtLo); rtHi = __reduce_or_sync(YK_FULL, rtHi);
+        if (lane == 0) sh.runTiles = ((unsigned long long)rtHi << 32) | rtLo;
+        if (lane < YKA_NR) {
+            yka_mbar_init(&sh.rawFull[lane], 1); yka_mbar_init(&sh.rawFree[lane], YKA_ITEMS); sh.unit[lane].seq = -1;
 #ifndef YK_EMULATE
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
+        }
     }
     __syncthreads();
     const YkRun& run = sh.run;
@@ -986,7 +1030,6 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
     if (warp == 0) {
         // ================================================== producer (warp 0: the oldest warp of its scheduler) ==================================================
         // u-th unit of this CTA -> raw buffer u % YKA_NR
-        int* ticket = slots[slot0].hdr + YK_HD_TICKET_ANALYZE;
         const bool wantAlpha = run.doAlpha != 0;
         // tickets: lane 0 holds YKA_TICKETS tickets in separate registers (the loop is unrolled by that many units), each
         // fetched YKA_TICKETS units ahead, so that the latency of the global atomic is never on the path of a unit.
@@ -1000,24 +1043,41 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         const YkSlotDev* S = nullptr;
         // pair index -> (pair column, by) by a multiply-high (exact for index * nPairs < 2^32)
         const unsigned pairMagic = nPairs > 1 ? 0xFFFFFFFFu / (unsigned)nPairs + 1u : 0u;
+        // tk[] holds ticket values as the counter returned them; unit = value + tbase.  YKA_TK_LAZY: to be taken when the unit comes up.
+        constexpr int YKA_TK_LAZY = INT_MIN;
+#if YKA_STATIC_FIRST
+        // A CTA's first unit(s) are known without asking: unit r * grid + its own index, r < nStatic (one round of the
+        // ticket registers when the launch is long enough, else one unit) - nothing to wait for before their loads are
+        // issued.  The counter hands out the units after those; the first round of real tickets is taken with one atomic
+        // once the static units' loads are on their way.
+        const int nStatic = total >= YKA_STATIC_ROUND_MIN * (int)gridDim.x ? YKA_TICKETS : 1;
+        const int tbase = nStatic * (int)gridDim.x;
 #pragma unroll
-        for (int r = 0; r < YKA_TICKETS; r++) { tk[r] = total; if (lane == 0) tk[r] = atomicAdd(ticket, 1); }
+        for (int r = 0; r < YKA_TICKETS; r++) tk[r] = (int)blockIdx.x + (r < nStatic ? r : 0) * (int)gridDim.x - tbase;
+        // the image of the first unit (descriptors acquired at the top of the kernel)
+        S = &slots[firstSlot];
+        alpha = wantAlpha && firstPlanes == 4;
+        curSlot = firstSlot;
+        if (lane == 0) sh.statSlot = firstSlot;
+#else
+        const int nStatic = 0, tbase = 0;
+#pragma unroll
+        for (int r = 0; r < YKA_TICKETS; r++) { tk[r] = 0; if (lane == 0) tk[r] = atomicAdd(ticket, 1); }
+#endif
         YKT_DECL;
         for (int u0 = 0;; u0 += YKA_TICKETS) {
 #pragma unroll
             for (int r = 0; r < YKA_TICKETS; r++) {
                 const int u = u0 + r, i = u % YKA_NR;
                 // never more than YKA_LOOKAHEAD units ahead of the consumers: the CTAs then run out of work together
-                while (u - (yka_flag_ld(&sh.queueHead) >> 3) > (lazy ? 1 : YKA_LOOKAHEAD)) yk_spin();
+                while (u - (yka_flag_ld(&sh.queueHead) >> 3) > (lazy ? YKA_LAZY_AHEAD : YKA_LOOKAHEAD)) yk_spin();
                 if (u >= YKA_NR) yka_mbar_wait(&sh.rawFree[i], (unsigned)((u / YKA_NR - 1) & 1));
                 if (lane == 0) YKT(0);
-                if (lane == 0 && tk[r] < 0) tk[r] = atomicAdd(ticket, 1);               // endgame: taken on demand
-                const int item = __shfl_sync(YK_FULL, tk[r], 0);
+                if (lane == 0 && tk[r] == YKA_TK_LAZY) tk[r] = atomicAdd(ticket, 1);           // endgame: taken on demand
+                const int item = __shfl_sync(YK_FULL, tk[r], 0) + tbase;
                 if (lane == 0) YKT(6);
                 if (item >= total) { if (lane == 0) yka_flag_st(&sh.endSeq, u); return; }
                 lazy = item >= endgame;
-                if (lane == 0) tk[r] = lazy ? -1 : (int)atomicAdd(ticket, 1);          // not looked at before the unit that uses it
-                if (lane == 0) YKT(7);
                 int slot = slot0, rem = item;
                 if (nSlots > 1) { const int q = item / unitsPerSlot; slot += q; rem -= q * unitsPerSlot; }
                 if (slot != curSlot) {
@@ -1042,6 +1102,19 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
                         yka_tma_box(dst + c * PLANE_BYTES, &S->tmap[c], bx * 64, by * 64 + 16 * k, U8 ? YK_U8_BOX : YK_RAW_PITCH, YK_RAW_ROWS, &sh.rawFull[i], !alpha && c == 2);
                     if (alpha) yka_tma_box(dst + 3 * PLANE_BYTES, &S->tmap[3], bx * 64, by * 64 + 16 * k, YK_UNIT_W, 16, &sh.rawFull[i], 1);
                     YKT(2);
+#ifdef YK_TIMING
+                    if (u < 3) atomicAdd(&yk_timing[24 + u], ykt_now() & 0xFFFFFFFFull);
+#endif
+                    // the ticket this register holds next (used YKA_TICKETS units from now).  After the loads: the compiler
+                    // turns an atomic on a uniform address into "leader adds, SHFL broadcasts" - inline PTX, atom.inc and a
+                    // non-constant increment included - and that shuffle waits for the round trip to L2 where it stands.
+                    if (u >= nStatic) tk[r] = lazy ? YKA_TK_LAZY : atomicAdd(ticket, 1);
+                    else if (u == nStatic - 1) {
+                        const int base = atomicAdd(ticket, YKA_TICKETS);
+#pragma unroll
+                        for (int j = 0; j < YKA_TICKETS; j++) tk[(r + 1 + j) % YKA_TICKETS] = base + j;      // units u + 1 .. u + YKA_TICKETS
+                    }
+                    YKT(7);
                 }
             }
         }
@@ -1079,7 +1152,7 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         alive = __all_sync(YK_FULL, alive);
         if (tid == 32) YKT(8);
 #ifdef YK_TIMING
-        if (lane == 0 && firstItem && alive) { atomicAdd(&yk_timing[18], ykt_now() & 0xFFFFFFFFull); atomicAdd(&yk_timing[19], 1ull); }
+        if (lane == 0 && firstItem && alive) { atomicAdd(&yk_timing[18], ykt_now() & 0xFFFFFFFFull); atomicAdd(&yk_timing[19], 1ull); if (u < 3 && mx == 0) atomicAdd(&yk_timing[27 + u], ykt_now() & 0xFFFFFFFFull); }
         firstItem = false;
 #endif
         if (!alive) break;

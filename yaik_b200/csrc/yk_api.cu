@@ -3,6 +3,9 @@
 // There is no CPU path here: every compute entry point needs a CUDA device.
 #include "../../include/yaik_b200.h"
 #include "yk_internal.h"
+#ifndef YK_ENDGAME_UNITS
+#define YK_ENDGAME_UNITS 6      // units per CTA at the end of a full-GPU launch that are taken on demand (yk_analyze.cu, producer)
+#endif
 
 #include <limits.h>
 #include <stdio.h>
@@ -246,7 +249,7 @@ static int create_fill(yk_ctx* c) {
         offNib[p] = off;
         off += up(((W + g.bw - 1) / g.bw) * ((H + g.bh - 1) / g.bh) * (size_t)g.bits / 2 + 16);
     }
-    const size_t offR2 = off; off += up(((W / 8) * (H / 8) / 256 + 2) * sizeof(unsigned long long));
+    const size_t offR2 = off; off += up(((W / 8) * (H / 8) / YK_EMIT_THREADS + 2) * sizeof(unsigned long long));
     c->zeroABytes = off;
     const size_t offCell = off; off += up((H / 4 + 1) * nbx * sizeof(uint16_t) + 4);
     const size_t offTouch = off; off += up(latW * latH * sizeof(uint32_t));
@@ -580,7 +583,7 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
     krun.fresh = fresh ? 1 : 0;
     // a launch that has the GPU to itself balances its tail by taking its last units on demand; a partial launch runs
     // beside others (pipelined contexts) which fill its tail anyway
-    krun.endgameUnits = c->analysisCtas >= c->numSMs ? 6 : 0;
+    krun.endgameUnits = c->analysisCtas >= c->numSMs ? YK_ENDGAME_UNITS : 0;
     if ((phases & 1) && (krun.nPasses > 0 || krun.doAlpha || krun.doR2)) {
         YkTimed t(c, 0);
         yk_launch_analyze(c->slotsDev, slot0, nSlots, nRegions, c->analysisCtas, a.d.isU8 != 0, krun, c->stream); c->launches++;
@@ -593,10 +596,10 @@ static int enqueue(yk_ctx* c, int slot0, int nSlots, const YkRun& run, bool doEm
             for (int p = 0; p < krun.nPasses; p++) {
                 const YkPassGeom& g = kGeom[krun.passId[p]];
                 const int nWords = ((a.d.w + g.bw - 1) / g.bw) * ((a.d.h + g.bh - 1) / g.bh) * g.bits / 8;
-                gradGroups += (nWords + 255) / 256;
+                gradGroups += (nWords + YK_EMIT_THREADS - 1) / YK_EMIT_THREADS;
             }
         const int nTiles = (a.d.w / 8) * (a.d.h / 8);
-        const int r2Groups = (r2Domain && nTiles > 0) ? (nTiles + 255) / 256 : 0;
+        const int r2Groups = (r2Domain && nTiles > 0) ? (nTiles + YK_EMIT_THREADS - 1) / YK_EMIT_THREADS : 0;
         if (gradGroups > 0) { YkTimed t(c, 2); yk_launch_owner(c->slotsDev, slot0, nSlots, a.d.latW * a.d.latH, krun, c->stream); c->launches++; }
         if (gradGroups + r2Groups > 0) { YkTimed t(c, 1); yk_launch_emit(c->slotsDev, slot0, nSlots, gradGroups, r2Groups, krun, c->stream); c->launches++; }
     }

@@ -18,7 +18,10 @@
 // boundary is touched by tiles of both strips.  Each strip ORs in the words its neighbour computed (touchInTop /
 // touchInBottom); a tile of the upper strip always precedes a tile of the lower strip in a pass's stream, and only the
 // strip that holds the owner tile marks it.
-__global__ void __launch_bounds__(256)
+#ifndef YK_OWNER_THREADS
+#define YK_OWNER_THREADS 256
+#endif
+__global__ void __launch_bounds__(YK_OWNER_THREADS)
 yk_k_owner(const YkSlotDev* __restrict__ slots, int slot0, int nPoints, YkRun run) {
     const YkSlotDev& S = slots[slot0 + blockIdx.y];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,9 +54,12 @@ yk_k_owner(const YkSlotDev* __restrict__ slots, int slot0, int nPoints, YkRun ru
     atomicOr(&S.emitNib[pid][best >> 3], 1u << (4 * (best & 7) + bestK));
 }
 
-#define YK_EMIT_THREADS 256
-
-__global__ void __launch_bounds__(YK_EMIT_THREADS)
+// four CTAs per SM (64 registers): the kernel is a chain of dependent global accesses per CTA, and in the pipelined step its
+// CTAs hold SMs that the next analysis launch is waiting for - 3 CTAs per SM at 78 registers: 47.6 us per step, 4: 46.4
+#ifndef YK_EMIT_MINB
+#define YK_EMIT_MINB 4
+#endif
+__global__ void __launch_bounds__(YK_EMIT_THREADS, YK_EMIT_MINB)
 yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGroups, int r2Groups) {
     __shared__ int sTicket;
     __shared__ unsigned sA[YK_EMIT_THREADS / 32 + 1], sB[YK_EMIT_THREADS / 32 + 1];
@@ -179,7 +185,7 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGro
 }
 
 void yk_launch_owner(const YkSlotDev* slotsDev, int slot0, int nSlots, int nPoints, const YkRun& run, cudaStream_t st) {
-    YK_LAUNCH(yk_k_owner, dim3((nPoints + 255) / 256, nSlots), dim3(256), 0, st, slotsDev, slot0, nPoints, run);
+    YK_LAUNCH(yk_k_owner, dim3((nPoints + YK_OWNER_THREADS - 1) / YK_OWNER_THREADS, nSlots), dim3(YK_OWNER_THREADS), 0, st, slotsDev, slot0, nPoints, run);
 }
 void yk_launch_emit(const YkSlotDev* slotsDev, int slot0, int nSlots, int gradGroups, int r2Groups, const YkRun& run, cudaStream_t st) {
     YK_LAUNCH(yk_k_emit, dim3(gradGroups + r2Groups, nSlots), dim3(YK_EMIT_THREADS), 0, st, slotsDev, slot0, run, gradGroups, r2Groups);

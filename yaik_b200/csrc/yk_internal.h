@@ -37,6 +37,9 @@ enum {
 // neighbouring 64x64 regions plus its right / bottom corner samples: the TMA unit's cost is per box row, so rows are
 // made long), 128 x 16 for alpha; out-of-image samples arrive as zeros and are never used unclamped.
 struct alignas(64) YkTmap { unsigned long long opaque[16]; };
+#ifndef YK_EMIT_THREADS
+#define YK_EMIT_THREADS 256    // threads of a yk_k_emit CTA == nibble words / range tiles per look-back group (host and device agree on it)
+#endif
 #define YK_UNIT_W 128           // pixels a unit of the analysis kernel is wide (two regions)
 #define YK_RAW_PITCH 132        // samples per row of a staged colour box
 #define YK_RAW_ROWS 17
