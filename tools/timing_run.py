@@ -20,6 +20,7 @@ for _ in range(N):
 lib.yk_debug_timing(out, 0)
 names = {0: "prod: lookahead+free wait", 6: "prod: shfl ticket", 7: "prod: issue ticket atomic", 3: "prod: decode", 2: "prod: fence + expect_tx + 4x TMA issue",
          8: "cons(w0): queue+wait raw", 9: "cons(w0): pack", 11: "cons(w0):   cascade passes (incl. pretest)", 12: "cons(w0):   cells + touch + latRGB", 13: "cons(w0):   range stage", 10: "cons(w0): rest of the item (incl. raw 16x16 pass)"}
+print(f'all consumer warps, cycles per warp per launch: wait for the first item {out[14] / N / 3404:.0f}, waits between items {out[5] / N / 3404:.0f} ({out[4] / N / 3404:.1f} items), wait at the end {out[15] / N / 3404:.0f}')
 for i, n in names.items():
     print(f"{n:34s} {out[i] / N / 148:12.0f} cycles per CTA per launch")
 

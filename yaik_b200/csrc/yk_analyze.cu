@@ -1135,6 +1135,9 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
     bool firstItem = true;
 #endif
     for (;;) {
+#ifdef YK_TIMING
+        const long long tw0 = clock64();
+#endif
         int q = 0;
         if (lane == 0) q = atomicAdd(&sh.queueHead, 1);
         q = __shfl_sync(YK_FULL, q, 0);
@@ -1152,6 +1155,7 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         alive = __all_sync(YK_FULL, alive);
         if (tid == 32) YKT(8);
 #ifdef YK_TIMING
+        if (lane == 0) { const unsigned long long dt = (unsigned long long)(clock64() - tw0); atomicAdd(&yk_timing[!alive ? 15 : firstItem ? 14 : 5], dt); if (alive && !firstItem) atomicAdd(&yk_timing[4], 1ull); }
         if (lane == 0 && firstItem && alive) { atomicAdd(&yk_timing[18], ykt_now() & 0xFFFFFFFFull); atomicAdd(&yk_timing[19], 1ull); if (u < 3 && mx == 0) atomicAdd(&yk_timing[27 + u], ykt_now() & 0xFFFFFFFFull); }
         firstItem = false;
 #endif
@@ -1166,6 +1170,11 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         const int X0 = U.bx * 64, Yk = U.by * 64 + 16 * U.k;
         const int gmx = X0 + 16 * mx;
         const unsigned char* rawU = raw + i * STAGE_BYTES;
+#ifdef YKA_DEBUG_SKIP_WORK      // measurement only: how long the launch takes when the consumers only hand the raw rows back
+        __syncwarp();
+        if (lane == 0) yka_mbar_arrive(&sh.rawFree[i]);
+        continue;
+#endif
         // fresh state, 16x16 pass first, interior macro tile: try that pass straight from the raw rows
         int fast = 0;
         if (fast16 && gmx + 20 <= C.w && Yk + YK_RAW_ROWS <= C.h)
