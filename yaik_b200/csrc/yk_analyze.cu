@@ -61,9 +61,6 @@
 #ifndef YKA_STATIC_FIRST
 #define YKA_STATIC_FIRST 1
 #endif
-#ifndef YKA_RANGE_UNROLL
-#define YKA_RANGE_UNROLL 0
-#endif
 #define YKP_RS 24                   // row pitch in bytes of a warp-private 17x17 byte tile
 #define YKP_CH (17 * YKP_RS)        // bytes of one channel of it
 #define YKP_TILE 1232               // 3 channels, rounded to a multiple of 16
@@ -110,11 +107,7 @@ struct YkaShared {
 // everything a consumer warp owns, in one block (one base address serves all of it)
 struct alignas(128) YkaWarpArea {
     uint8_t  priv[YKP_TILE];        // the macro tile's 17x17 samples, three channels, as bytes
-#if YKA_RANGE_UNROLL == 2
-    uint8_t  hist[1536];            // byte counters of the range stage: a 256-byte histogram per plane and half-warp
-#else
-    uint8_t  hist[768];             // byte counters of the range stage, one 256-byte histogram per plane
-#endif
+    uint8_t  hist[768];             // byte counters of the range stage: a 256-byte histogram per half-warp (yka_range_pair), per plane in the single-tile form
     uint32_t touch[28];             // touch words of the 5x5 lattice points of the macro tile
     int      wstat[40];             // 8 groups x 5 counters (see yka_stat_add)
     YkaSlotC slotc;
@@ -643,11 +636,7 @@ static __device__ __forceinline__ void yka_range_pair(const uint8_t* __restrict_
     const size_t tile = tileL + h;
     uint32_t* hw = reinterpret_cast<uint32_t*>(hist) + 64 * h;              // byte counters, four to a word; one histogram per half-warp
     const uint8_t* src = priv + (ly8 + r) * YKP_RS + 8 * h + 4 * right;
-#if YKA_RANGE_UNROLL
-#pragma unroll
-#else
 #pragma unroll 1
-#endif
     for (int p = 0; p < 3; p++) {
         const unsigned word = *reinterpret_cast<const unsigned*>(src + p * YKP_CH);      // CompressF(v,255) == v (EC.cpp:8442)
         int v[4];
@@ -695,79 +684,6 @@ static __device__ __forceinline__ void yka_range_pair(const uint8_t* __restrict_
     }
 }
 
-#if YKA_RANGE_UNROLL == 2
-// yka_range_pair with the three planes side by side: every step of the chain (histogram adds, the three half-warp
-// reductions, the index computation) is issued for the three planes before its results are needed, so that a warp waits
-// for one round trip per step instead of three.  One histogram per plane and half-warp.
-static __device__ __forceinline__ void yka_range_pair3(const uint8_t* __restrict__ priv, const YkaSlotC& Rg, uint8_t* __restrict__ hist,
-                                                       const uint32_t* __restrict__ magicTab, size_t tileL, int ly8, unsigned qL, unsigned qR) {
-    const int lane = threadIdx.x & 31;
-    const int h = lane >> 4, l = lane & 15, r = l >> 1, right = l & 1;
-    const unsigned q = h ? qR : qL;
-    const int band = r >> 2;
-    const bool valid = (q >> (band * 2 + right)) & 1u;
-    const unsigned qb = (q >> (band * 2)) & 3u;
-    const int lengthX = (qb == 3u) ? 8 : 4, x2 = (qb == 2u) ? 4 : 0;
-    const int pos = (band ? 16 * __popc(q & 3u) : 0) + (r & 3) * lengthX + (4 * right - x2);
-    const size_t tile = tileL + h;
-    uint32_t* hw = reinterpret_cast<uint32_t*>(hist) + 64 * h;              // plane p: hw + 128 * p
-    const uint8_t* src = priv + (ly8 + r) * YKP_RS + 8 * h + 4 * right;
-    int v[3][4];
-    unsigned key[3];
-#pragma unroll
-    for (int p = 0; p < 3; p++) {
-        const unsigned word = *reinterpret_cast<const unsigned*>(src + p * YKP_CH);
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[p][k] = yka_byte(word, k);
-    }
-    const unsigned one = valid ? 0x100u : 0u;                               // lanes without coded pixels add nothing
-#pragma unroll
-    for (int p = 0; p < 3; p++) {
-        key[p] = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const unsigned s8 = (unsigned)(v[p][k] & 3) * 8u - 8u;
-            const unsigned old = atomicAdd(&hw[128 * p + (v[p][k] >> 2)], __funnelshift_l(one, one, s8));
-            key[p] = max(key[p], (__funnelshift_r(old, old, s8) & 0xFF00u) | (unsigned)v[p][k]);
-        }
-        if (!valid) key[p] = 0;
-    }
-#pragma unroll
-    for (int p = 0; p < 3; p++) key[p] = yka_half_max(key[p], h);
-#pragma unroll
-    for (int p = 0; p < 3; p++) reinterpret_cast<uint4*>(hw + 128 * p)[l] = make_uint4(0u, 0u, 0u, 0u);
-    unsigned lo[3], hi[3];
-    int color0[3];
-#pragma unroll
-    for (int p = 0; p < 3; p++) {
-        color0[p] = min(max((int)(key[p] & 255u), 1), 254);
-        lo[p] = 999u; hi[p] = 0u;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const bool rem = valid && (unsigned)(v[p][k] - (color0[p] - 1)) > 2u;
-            lo[p] = min(lo[p], rem ? (unsigned)v[p][k] : 999u);
-            hi[p] = max(hi[p], rem ? (unsigned)v[p][k] : 0u);
-        }
-    }
-#pragma unroll
-    for (int p = 0; p < 3; p++) { lo[p] = 999u - yka_half_max(999u - lo[p], h); hi[p] = yka_half_max(hi[p], h); }
-#pragma unroll
-    for (int p = 0; p < 3; p++) {
-        int minCol = 0, delta = 0;
-        if (lo[p] != 999u) { minCol = (int)lo[p]; delta = (int)(hi[p] - lo[p]); }
-        const int K = delta ? 2 * ((delta >> 1) - 1 + delta - 15 * minCol) : 2 - 30 * minCol;
-        const unsigned magic = magicTab[delta];
-        if (valid) {
-            unsigned b[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) b[k] = ((unsigned)(v[p][k] - (color0[p] - 1)) > 2u) ? __umulhi((unsigned)(v[p][k] * 30 + K), magic) : 0u;
-            *reinterpret_cast<uint32_t*>(Rg.r2Raw[p] + tile * 64 + pos) = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
-        }
-        if (l == 0 && q) Rg.r2RawType[p][tile] = (uint32_t)color0[p] | ((uint32_t)minCol << 8) | ((uint32_t)delta << 16);
-    }
-    __syncwarp();
-}
-#endif
 
 template <bool U8>
 static __device__ __forceinline__ int yka_pass16_raw(const void* __restrict__ rawv, const YkaSlotC& C, YkaStat* st, int gmx, int gmy, int mx, int R) {
@@ -933,11 +849,7 @@ static __device__ __forceinline__ void yka_macro_tile(const uint8_t* __restrict_
             const unsigned qL = (f & 3u) | ((f >> 2) & 12u), qR = ((f >> 2) & 3u) | ((f >> 4) & 12u);
             if (qL | qR) {
                 const size_t tileL = (size_t)((gmy + 8 * qy) >> 3) * tilesW + (gmx >> 3);
-#if YKA_RANGE_UNROLL == 2
-                yka_range_pair3(priv, C, hist, magicTab, tileL, 8 * qy, qL, qR);
-#else
                 yka_range_pair(priv, C, hist, magicTab, tileL, 8 * qy, qL, qR);
-#endif
             }
         }
 #endif
@@ -1007,9 +919,10 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         // the run's parameters, the tiles its passes cover (one lane per pass) and the barriers of the raw ring (one lane each):
         // every other warp waits for this at the barrier below, so it is spread over the lanes
         if (lane == 0) { sh.run = runArg; sh.queueHead = 0; sh.endSeq = INT_MAX; sh.statSlot = -1; sh.consLeft = YKA_CONS_WARPS; }
+        __syncwarp();                                       // passId is read from the shared copy: indexing the kernel parameter by lane would put it on the stack
         unsigned rtLo = 0, rtHi = 0;
         if (lane < runArg.nPasses) {
-            const int pid = runArg.passId[lane];
+            const int pid = sh.run.passId[lane];
             const YkGeomS g = yk_geom_s(pid);
             const unsigned long long rt = ((1ull << (256 >> (g.shx + g.shy))) - 1ull) << g.start;
             rtLo = (unsigned)rt; rtHi = (unsigned)(rt >> 32);
