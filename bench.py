@@ -297,6 +297,28 @@ def run_strips(args, torch, dist, lib, rank, world, local, steps, warmup):
             t_ms = float(t.item())
         return t_ms
 
+    # CTAs of the strips' analysis launches, calibrated before the timed run with all ranks running: a launch that takes
+    # every SM leaves none for the other set's ownership / emission kernels (a resident analysis CTA holds an SM's whole
+    # shared memory), so the two sets take turns instead of overlapping; a launch a little narrower lasts longer but
+    # runs beside them.  Pays when a strip's analysis is short (many GPUs), not when it dominates.
+    sms = ctx.sm_count() if active else 0
+    cal = {}
+    cands = [0] if args.strips_ctas >= 0 else [0, sms * 7 // 8, sms * 3 // 4, sms * 5 // 8]
+    if args.strips_ctas > 0:
+        cands = [args.strips_ctas]
+    best = cands[0]
+    if len(cands) > 1:
+        for n_ctas in cands:
+            for c in ctxs:
+                c.set_analysis_ctas(n_ctas)
+            run_images(2, NSETS)
+            barrier()
+            cal[n_ctas] = timed(max(4, steps // 2), NSETS) / max(4, steps // 2)
+        best = min(cal, key=cal.get)
+    for c in ctxs:
+        c.set_analysis_ctas(best)
+    run_images(2, NSETS)
+    barrier()
     ms = timed(steps, NSETS)                             # throughput: images pipelined over the two sets
     ms_single = timed(max(2, steps // 2), 1)             # one set: every image waits for the one before it
     sampler.stop_flag = True; sampler.sample()
@@ -335,6 +357,7 @@ def run_strips(args, torch, dist, lib, rank, world, local, steps, warmup):
         mp = side * side / 1e6
         result = {"metric": METRIC, "value": round(mp * steps / (ms / 1e3), 1), "unit": UNIT, "n_gpus": world, "steps": steps, "ms_per_image": round(ms / steps, 4),
                   "ms_per_image_unpipelined": round(ms_single / max(2, steps // 2), 4),
+                  "analysis_ctas": int(best) if best else "one per SM", "analysis_ctas_calibration_ms_per_image": {str(k): round(v, 4) for k, v in cal.items()},
                   "pipelining": "consecutive images alternate between two strip sets per GPU (same resident planes): ownership / emission of one image runs beside the analysis of the next",
                   "workload": f"one {side}x{side} synthetic RGB image in {len(rows)} tile-row strips, one GPU each (BASELINE.json configs[3])",
                   "scaling": "strong", "halo_bytes_per_boundary": int(3 * halo.planeRowBytes + 2 * halo.touchBytes),
@@ -363,6 +386,7 @@ def main():
     ap.add_argument("--workload", default="batch", choices=["batch", "strips"],
                     help="batch: configs[1] textures sharded by image (the metric's configuration); strips: one 16384x16384 RGB image in tile-row strips over the ranks (configs[3])")
     ap.add_argument("--strips-side", type=int, default=16384)
+    ap.add_argument("--strips-ctas", type=int, default=-1, help="CTAs of a strip's analysis launch (-1: calibrated, 0: one per SM)")
     ap.add_argument("--no-strips", action="store_true", help="N > 1, batch workload: skip the strips sub-measurement echoed in the line")
     ap.add_argument("--no-r1", action="store_true", help="skip the second timed region (the step with DynamicTileEncode behind it)")
     ap.add_argument("--no-other", action="store_true", help="skip the informational timing of the stages outside the metric")
