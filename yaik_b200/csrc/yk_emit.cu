@@ -7,7 +7,7 @@
 //
 //   yk_k_owner   one thread per lattice point: resolves the owner and sets the owner tile's bit in emitNib
 //                (4 bits per tile in stream order: it emits TL / TR / BL / BR).
-//   yk_k_emit    one thread per 8 tiles of a pass, groups of 2048 tiles taken in stream order by ticket: byte counts from
+//   yk_k_emit    one thread per 8 tiles of a pass, groups of 8 x YK_EMIT_THREADS tiles taken in stream order by ticket: byte counts from
 //                the nibbles (popc), block scan + one decoupled look-back per group, then the colours are copied from
 //                latRGB.  Tickets past the gradient groups gather DynamicTileCompressor's per-tile output (written at
 //                fixed places by yk_k_analyze) into the reference's row-major tile order (EC.cpp:8412-8413), offsets by
@@ -54,10 +54,12 @@ yk_k_owner(const YkSlotDev* __restrict__ slots, int slot0, int nPoints, YkRun ru
     atomicOr(&S.emitNib[pid][best >> 3], 1u << (4 * (best & 7) + bestK));
 }
 
-// four CTAs per SM (64 registers): the kernel is a chain of dependent global accesses per CTA, and in the pipelined step its
-// CTAs hold SMs that the next analysis launch is waiting for - 3 CTAs per SM at 78 registers: 47.6 us per step, 4: 46.4
+// 512 threads at 64 registers (two CTAs per SM): the kernel is a chain of dependent global accesses per CTA (ticket, masks,
+// per-tile output, look-back), and in the pipelined step its CTAs hold SMs that the next analysis launch is waiting for.
+// Per pipelined step: 256 threads x 3 CTAs per SM at 78 registers 47.6 us, 256 x 4 at 64 registers 45.8, 512 x 2 44.7
+// (half the tickets and look-backs), 1024 x 1 the same with a longer lone launch, 512 x 3 at 42 registers (spills) 46.0.
 #ifndef YK_EMIT_MINB
-#define YK_EMIT_MINB 4
+#define YK_EMIT_MINB 2
 #endif
 __global__ void __launch_bounds__(YK_EMIT_THREADS, YK_EMIT_MINB)
 yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGroups, int r2Groups) {
@@ -133,7 +135,7 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGro
         return;
     }
 
-    // ---- rgbStream of one pass: ticket -> (pass position, group of 2048 tiles)
+    // ---- rgbStream of one pass: ticket -> (pass position, group of 8 x YK_EMIT_THREADS tiles)
     int rp = 0, grp = ticket, nWords = 0, nSwzX = 0, nGroups = 0;
     YkGeomS g = yk_geom_s(run.passId[0]);
     for (;;) {

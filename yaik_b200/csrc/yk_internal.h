@@ -38,7 +38,7 @@ enum {
 // made long), 128 x 16 for alpha; out-of-image samples arrive as zeros and are never used unclamped.
 struct alignas(64) YkTmap { unsigned long long opaque[16]; };
 #ifndef YK_EMIT_THREADS
-#define YK_EMIT_THREADS 256    // threads of a yk_k_emit CTA == nibble words / range tiles per look-back group (host and device agree on it)
+#define YK_EMIT_THREADS 512    // threads of a yk_k_emit CTA == nibble words / range tiles per look-back group (host and device agree on it)
 #endif
 #define YK_UNIT_W 128           // pixels a unit of the analysis kernel is wide (two regions)
 #define YK_RAW_PITCH 132        // samples per row of a staged colour box
@@ -75,7 +75,7 @@ struct alignas(128) YkSlotDev {
     uint8_t*  latRGB;               // [latH][latW][3]  CompressF(Round6(clamped pixel),250) at every lattice point
     uint32_t* emitNib[YK_NPASS];    // per tile in stream order 4 bits: which of TL,TR,BL,BR the tile emits (8 tiles per word)
     // ---- range stage R2 (DynamicTileCompressor)
-    unsigned long long* r2Status;   // per group of 256 tiles (row-major tile order): look-back word (chunks << 32 | codedTiles << 2 | flag)
+    unsigned long long* r2Status;   // per group of YK_EMIT_THREADS tiles (row-major tile order): look-back word (chunks << 32 | codedTiles << 2 | flag)
     uint8_t*  r2Raw[3];         // [h/8][w/8][64] index bytes of every coded tile at a fixed place (written by the analysis kernel)
     uint32_t* r2RawType[3];     // [h/8][w/8] color0 | minCol << 8 | delta << 16
     uint8_t*  r2Idx[3];         // the streams in the reference's order (gathered by yk_k_emit)
