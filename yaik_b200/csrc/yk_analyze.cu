@@ -554,6 +554,7 @@ static __device__ __forceinline__ unsigned long long yka_eligible(unsigned claim
     return (unsigned long long)lo | ((unsigned long long)f << 25);           // 4x4: every cell
 }
 
+#if YKA_RANGE_SINGLE     // the round 1 form, one 8x8 tile at a time: kept for A/B builds (tools/ab_build.py)
 // DynamicTileCompressor (EC.cpp:8398-8522) for the 8x8 tile at (lx8, ly8) of the macro tile; q = its quadrants to code
 // (bit0 TL, 1 TR, 2 BL, 3 BR: top-left map pixel 0, EC.cpp:8420-8430 == 4x4 cell unclaimed).  Lane = two pixels; the
 // three planes side by side.  Output goes to the tile's fixed place in r2Raw / r2RawType.
@@ -609,6 +610,7 @@ static __device__ __forceinline__ void yka_range_tile(const uint8_t* __restrict_
     }
     __syncwarp();       // the histogram entries are clean again before the next tile fills them
 }
+#endif
 
 // maximum over the lanes of the caller's half-warp.  Two full-warp reductions: a reduction whose member mask differs between
 // the lanes of a warp is compiled into a divergent path (WARPSYNC.COLLECTIVE per mask) that leaves the halves running apart.
