@@ -58,6 +58,9 @@
 #ifndef YKA_STATIC_ROUND_MIN
 #define YKA_STATIC_ROUND_MIN 32     // units per CTA from which a launch hands out a whole round of ticket registers statically (a short launch pays for it in its tail)
 #endif
+#ifndef YKA_PRODUCER_ROLLED
+#define YKA_PRODUCER_ROLLED 0
+#endif
 #ifndef YKA_STATIC_FIRST
 #define YKA_STATIC_FIRST 1
 #endif
@@ -980,10 +983,19 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
         for (int r = 0; r < YKA_TICKETS; r++) { tk[r] = 0; if (lane == 0) tk[r] = atomicAdd(ticket, 1); }
 #endif
         YKT_DECL;
+#if YKA_PRODUCER_ROLLED
+        static_assert(YKA_TICKETS == 4, "the rolled producer loop rotates four ticket registers");
+#pragma unroll 1
+        for (int u = 0;; u++) {
+            {
+                constexpr int r = 0;                         // the current unit's ticket is always in tk[0]: the registers rotate at the end of the body
+                const int i = u % YKA_NR;
+#else
         for (int u0 = 0;; u0 += YKA_TICKETS) {
 #pragma unroll
             for (int r = 0; r < YKA_TICKETS; r++) {
                 const int u = u0 + r, i = u % YKA_NR;
+#endif
                 // never more than YKA_LOOKAHEAD units ahead of the consumers: the CTAs then run out of work together
                 while (u - (yka_flag_ld(&sh.queueHead) >> 3) > (lazy ? YKA_LAZY_AHEAD : YKA_LOOKAHEAD)) yk_spin();
                 if (u >= YKA_NR) yka_mbar_wait(&sh.rawFree[i], (unsigned)((u / YKA_NR - 1) & 1));
@@ -1031,6 +1043,9 @@ static __device__ __forceinline__ void yk_analyze_body(const YkSlotDev* __restri
                     }
                     YKT(7);
                 }
+#if YKA_PRODUCER_ROLLED
+                { const int t0 = tk[0]; tk[0] = tk[1]; tk[1] = tk[2]; tk[2] = tk[3]; tk[3] = t0; }     // what was just taken is used four units from now
+#endif
             }
         }
         return;
