@@ -28,7 +28,9 @@
 // No tensor cores: the work is integer min/max reductions over bytes, bounded by HBM and the integer pipes.
 #include "yk_device.h"
 
+#ifndef YKA_NR
 #define YKA_NR 4                    // raw staging buffers (TMA destinations), one unit each
+#endif
 #define YKA_ITEMS 8                 // macro tiles per unit
 #ifndef YKA_TICKETS
 #define YKA_TICKETS 4               // tickets a CTA holds ahead of the unit it is issuing
@@ -36,7 +38,10 @@
 #ifndef YKA_LAZY_AHEAD
 #define YKA_LAZY_AHEAD 1
 #endif
-#define YKA_LOOKAHEAD 3             // units the producer may run ahead of the unit the consumers are taking items from
+#ifndef YKA_LOOKAHEAD
+#define YKA_LOOKAHEAD 3
+#endif
+// YKA_LOOKAHEAD: units the producer may run ahead of the unit the consumers are taking items from
 #ifndef YKA_CONS_WARPS
 #define YKA_CONS_WARPS 23
 #endif
