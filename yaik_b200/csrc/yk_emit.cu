@@ -18,10 +18,17 @@
 // boundary is touched by tiles of both strips.  Each strip ORs in the words its neighbour computed (touchInTop /
 // touchInBottom); a tile of the upper strip always precedes a tile of the lower strip in a pass's stream, and only the
 // strip that holds the owner tile marks it.
+#ifndef YK_EMIT_SLIM
+#define YK_EMIT_SLIM 0
+#endif
 #ifndef YK_OWNER_THREADS
 #define YK_OWNER_THREADS 256
 #endif
+#if YK_EMIT_SLIM
+__global__ void __launch_bounds__(YK_OWNER_THREADS, 16)
+#else
 __global__ void __launch_bounds__(YK_OWNER_THREADS)
+#endif
 yk_k_owner(const YkSlotDev* __restrict__ slots, int slot0, int nPoints, YkRun run) {
     const YkSlotDev& S = slots[slot0 + blockIdx.y];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,6 +93,7 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGro
             chunks = 4u - (unsigned)__popc(((r0 >> s2) & 3u) | (((r1 >> s2) & 3u) << 2));       // quadrants whose top-left map pixel is 0 (EC.cpp:8420-8430)
         }
         const unsigned tiles = chunks > 0;
+#if !YK_EMIT_SLIM
         // the tile's output is fetched while the offsets are being scanned
         uint4 v[3][4];
         uint32_t ty3[3] = { 0, 0, 0 };
@@ -98,6 +106,7 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGro
                 ty3[p] = S.r2RawType[p][t];
             }
         }
+#endif
         unsigned ic = chunks, it = tiles;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -123,6 +132,19 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGro
         __syncthreads();
         if (chunks) {
             const unsigned chunkOff = sA[warp] + ic - chunks, tileOff = sB[warp] + it - tiles;
+#if YK_EMIT_SLIM
+            // the slim build (32 registers, 128 threads: a CTA fits on an SM next to a resident analysis CTA) copies after the
+            // scan instead of holding the tile's 12 x 16 bytes in registers across it
+#pragma unroll 1
+            for (int p = 0; p < 3; p++) {
+                const uint4* src = reinterpret_cast<const uint4*>(S.r2Raw[p] + (size_t)t * 64);
+                uint4* dst = reinterpret_cast<uint4*>(S.r2Idx[p] + (size_t)chunkOff * 16);
+                for (int k = 0; k < (int)chunks; k++) dst[k] = src[k];
+                const uint32_t ty = S.r2RawType[p][t];
+                uint8_t* td = S.r2Type[p] + (size_t)tileOff * 3;                                // EC.cpp:8503-8505
+                td[0] = (uint8_t)ty; td[1] = (uint8_t)(ty >> 8); td[2] = (uint8_t)(ty >> 16);
+            }
+#else
 #pragma unroll
             for (int p = 0; p < 3; p++) {
                 uint4* dst = reinterpret_cast<uint4*>(S.r2Idx[p] + (size_t)chunkOff * 16);
@@ -131,6 +153,7 @@ yk_k_emit(const YkSlotDev* __restrict__ slots, int slot0, YkRun run, int gradGro
                 uint8_t* td = S.r2Type[p] + (size_t)tileOff * 3;                                // EC.cpp:8503-8505
                 td[0] = (uint8_t)ty3[p]; td[1] = (uint8_t)(ty3[p] >> 8); td[2] = (uint8_t)(ty3[p] >> 16);
             }
+#endif
         }
         return;
     }
